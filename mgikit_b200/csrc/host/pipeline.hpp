@@ -1,0 +1,49 @@
+// The demultiplex run: gunzip -> record-aligned chunk pairs -> hot path
+// (through the C ABI of include/mgikit_gpu.h) -> per-sample gzip members ->
+// reports.  Replaces demultiplex()/analyse_fastq() of the reference
+// (/root/reference/src/lib.rs:511-838, :1350-1604) and its reader threads
+// (src/file_utils.rs:99-164, :239-373).
+#pragma once
+
+#include <cstdint>
+#include <string>
+
+#include "../../../include/mgikit_gpu.h"
+#include "report.hpp"
+#include "run_info.hpp"
+#include "sample_sheet.hpp"
+
+namespace mgikit {
+
+// The hot path as the host sees it: exactly the entry points of mgikit_gpu.h.
+// The product binds these to libmgikit_gpu.so; the test-only oracle CLI binds
+// them to oracle/ — the host code does not know which.
+struct Backend {
+  const char* name;
+  int (*create)(const mgk_config*, void**);
+  void (*destroy)(void*);
+  const char* (*last_error)(const void*);
+  int (*submit)(void*, uint64_t, const uint8_t*, uint64_t, const uint8_t*, uint64_t, uint32_t);
+  int (*collect)(void*, mgk_result*);
+  int (*release)(void*, uint64_t);
+  int (*counters)(void*, uint64_t*, uint64_t*);
+  int (*allreduce)(void* const*, int);
+  void* (*host_alloc)(size_t);
+  void (*host_free)(void*);
+};
+
+struct DemuxOptions {
+  int mismatches = 1;
+  bool per_index_error = false;
+  int report_level = 2;
+  size_t report_limit = 20;
+  int compression_level = 1;
+  int threads = 0;          // -t: host codec threads (0 = all cores)
+  int gpus = 1;             // --gpus (extension): chunk k goes to GPU k % gpus
+  size_t chunk_bytes = 64u << 20;  // decompressed bytes per read file per chunk
+};
+
+// Runs the whole command; throws Fatal on any error the reference would panic on.
+void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, const DemuxOptions& opt);
+
+}  // namespace mgikit
