@@ -23,8 +23,8 @@ REF_BIN   := /root/reference/bins/mgikit
 all: gpu host oracle
 
 gpu: mgikit_b200/lib/libmgikit_gpu.so
-host: mgikit_b200/bin/mgikit mgikit_b200/lib/libmgikit_host.so
-oracle: oracle/_ref/liboracle.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit
+host: mgikit_b200/bin/mgikit
+oracle: oracle/_ref/liboracle.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit oracle/_ref/libemu.so oracle/_ref/mgikit_emu
 
 mgikit_b200/lib/libmgikit_gpu.so: $(GPU_SRC) $(GPU_HDR)
 	@mkdir -p mgikit_b200/lib
@@ -34,10 +34,6 @@ mgikit_b200/bin/mgikit: $(HOST_SRC) $(H)/main_gpu.cpp $(HOST_HDR) mgikit_b200/li
 	@mkdir -p mgikit_b200/bin
 	$(CXX) $(CXXFLAGS) -o $@ $(H)/main_gpu.cpp $(HOST_SRC) -Lmgikit_b200/lib -lmgikit_gpu -lz \
 	    -Wl,-rpath,'$$ORIGIN/../lib' -Wl,-rpath,$(CUDA_HOME)/lib64
-
-mgikit_b200/lib/libmgikit_host.so: $(HOST_SRC) $(H)/host_capi.cpp $(HOST_HDR)
-	@mkdir -p mgikit_b200/lib
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(H)/host_capi.cpp $(HOST_SRC) -lz
 
 oracle/_ref/liboracle.so: oracle/mgikit_oracle.c oracle/mgikit_oracle.h include/mgikit_gpu.h
 	@mkdir -p oracle/_ref
@@ -50,6 +46,15 @@ oracle/_ref/mgikit_oracle.o: oracle/mgikit_oracle.c oracle/mgikit_oracle.h inclu
 oracle/_ref/mgikit_oracle: oracle/oracle_cli.cpp oracle/_ref/mgikit_oracle.o $(HOST_SRC) $(HOST_HDR)
 	$(CXX) $(CXXFLAGS) -o $@ oracle/oracle_cli.cpp $(HOST_SRC) oracle/_ref/mgikit_oracle.o -lz
 
+# CPU emulation of the device logic (tests only): device_logic.cuh compiled by g++
+EMU_DEP := tests/emu/emu.cpp mgikit_b200/csrc/gpu/device_logic.cuh mgikit_b200/csrc/gpu/params_build.hpp include/mgikit_gpu.h
+oracle/_ref/libemu.so: $(EMU_DEP)
+	@mkdir -p oracle/_ref
+	$(CXX) $(CXXFLAGS) -shared -o $@ tests/emu/emu.cpp
+
+oracle/_ref/mgikit_emu: tests/emu/emu_cli.cpp $(EMU_DEP) $(HOST_SRC) $(HOST_HDR)
+	$(CXX) $(CXXFLAGS) -o $@ tests/emu/emu_cli.cpp tests/emu/emu.cpp $(HOST_SRC) -lz
+
 # The reference cannot be compiled here (no cargo/rustc, no vendored crates);
 # its own prebuilt, version-matched binary is the strongest oracle we can get.
 oracle/_ref/mgikit:
@@ -58,6 +63,6 @@ oracle/_ref/mgikit:
 	 else echo "reference binary not available here (GPU box): skipping"; fi
 
 clean:
-	rm -rf mgikit_b200/lib mgikit_b200/bin oracle/_ref/liboracle.so oracle/_ref/mgikit_oracle oracle/_ref/*.o
+	rm -rf mgikit_b200/lib mgikit_b200/bin oracle/_ref/liboracle.so oracle/_ref/libemu.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit_emu oracle/_ref/*.o
 
 .PHONY: all gpu host oracle clean

@@ -1,0 +1,659 @@
+// libmgikit_gpu.so — the C ABI of include/mgikit_gpu.h over the sm_100a kernels.
+// One context per GPU; each in-flight chunk owns a slot (its own stream, device
+// scratch and pinned result buffers), so copies of chunk k+1 overlap the kernels
+// of chunk k.  No CPU fallback: without a usable B200 mgk_create() fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "params_build.hpp"
+
+using namespace mgk;
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+struct Slot {
+  int state = 0;  // 0 free, 1 submitted, 2 collected (waiting for release)
+  uint64_t seq = 0;
+  uint32_t flags = 0;
+  uint64_t len2 = 0, len1 = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};  // start, after scan, after match, after bin scan, after scatter, end
+  cudaEvent_t ev_status = nullptr;
+  // device
+  uint8_t *d_r2 = nullptr, *d_r1 = nullptr, *out2 = nullptr, *out1 = nullptr;
+  uint32_t *nl2 = nullptr, *nl1 = nullptr, *ctrl = nullptr, *tile_bins = nullptr, *group_sums = nullptr, *unassigned = nullptr;
+  unsigned long long *look2 = nullptr, *look1 = nullptr, *seg = nullptr;
+  RecMeta* meta = nullptr;
+  Status* status = nullptr;
+  // pinned host
+  uint8_t *h_out2 = nullptr, *h_out1 = nullptr;
+  Status* h_status = nullptr;
+  unsigned long long* h_seg = nullptr;
+  uint32_t* h_unassigned = nullptr;
+  std::vector<uint64_t> off2, len2v, off1, len1v;
+  ChunkDev cd{};
+  float ms[5] = {0, 0, 0, 0, 0};
+};
+
+}  // namespace
+
+struct mgk_ctx {
+  int device = 0;
+  Params hp{};              // host copy (pointers are device pointers)
+  Params* d_params = nullptr;
+  uint64_t* d_codes = nullptr;
+  int32_t *d_pairs = nullptr, *d_xlat = nullptr, *d_writing = nullptr;
+  uint8_t* d_consts = nullptr;
+  unsigned long long *d_stats = nullptr, *d_mism = nullptr;
+  Status* h_status_init = nullptr;
+  int total = 0, mism_w = 0;
+  uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
+  uint32_t scan_tiles_max = 0, tiles_max = 0, groups_max = 0;
+  size_t match_smem = 0;
+  int grid_match = 0, grid_scatter = 0, n_sm = 0;
+  std::vector<Slot> slots;
+  std::deque<int> fifo;     // submitted slots, oldest first
+  uint64_t launches = 0;
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  ncclComm_t comm = nullptr;
+  char err[512] = "";
+};
+
+namespace {
+
+int fail(mgk_ctx* c, int code, const char* fmt, ...) {
+  char* dst = c ? c->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, MGK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), n ? n * sizeof(T) : sizeof(T));
+}
+
+void free_slot(Slot& s) {
+  cudaFree(s.d_r2); cudaFree(s.d_r1); cudaFree(s.out2); cudaFree(s.out1);
+  cudaFree(s.nl2); cudaFree(s.nl1); cudaFree(s.ctrl); cudaFree(s.tile_bins); cudaFree(s.group_sums);
+  cudaFree(s.unassigned); cudaFree(s.look2); cudaFree(s.look1); cudaFree(s.seg); cudaFree(s.meta); cudaFree(s.status);
+  cudaFreeHost(s.h_out2); cudaFreeHost(s.h_out1); cudaFreeHost(s.h_status); cudaFreeHost(s.h_seg); cudaFreeHost(s.h_unassigned);
+  for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+  if (s.ev_status) cudaEventDestroy(s.ev_status);
+  if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+// ---------------------------------------------------------------- NCCL (resolved at run time)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+#define SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, sym))
+      SYM(GetUniqueId, "ncclGetUniqueId");
+      SYM(CommInitRank, "ncclCommInitRank");
+      SYM(CommInitAll, "ncclCommInitAll");
+      SYM(AllReduce, "ncclAllReduce");
+      SYM(GroupStart, "ncclGroupStart");
+      SYM(GroupEnd, "ncclGroupEnd");
+      SYM(CommDestroy, "ncclCommDestroy");
+      SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.AllReduce || !api.GroupStart || !api.GroupEnd) {
+        dlclose(api.lib);
+        api.lib = nullptr;
+      }
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+
+}  // namespace
+
+// ====================================================================== create / destroy
+extern "C" const char* mgk_last_error(const mgk_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" void mgk_destroy(mgk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& s : ctx->slots) free_slot(s);
+  cudaFree(ctx->d_params); cudaFree(ctx->d_codes); cudaFree(ctx->d_pairs); cudaFree(ctx->d_xlat);
+  cudaFree(ctx->d_writing); cudaFree(ctx->d_consts); cudaFree(ctx->d_stats); cudaFree(ctx->d_mism);
+  cudaFreeHost(ctx->h_status_init);
+  if (ctx->comm) {
+    NcclApi* n = nccl_api();
+    if (n && n->CommDestroy) n->CommDestroy(ctx->comm);
+  }
+  delete ctx;
+}
+
+extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
+  mgk_ctx* ctx = nullptr;  // errors before the context exists go to the thread-local buffer
+  if (!cfg || !out) return fail(ctx, MGK_ERR_ARG, "mgk_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MGK_ABI_VERSION) return fail(ctx, MGK_ERR_ARG, "mgk_create: ABI version %d, library speaks %d", cfg->abi_version, MGK_ABI_VERSION);
+  if (cfg->n_templates < 1 || cfg->n_templates > MGK_MAX_TEMPLATES || cfg->n_samples < 1 || !cfg->templates || !cfg->writing_sample)
+    return fail(ctx, MGK_ERR_ARG, "mgk_create: bad sample/template tables");
+  if (cfg->n_samples + 2 > 60000) return fail(ctx, MGK_ERR_ARG, "mgk_create: more than 60000 samples are not supported");
+  if (cfg->max_chunk_bytes == 0 || cfg->max_chunk_bytes >= (1ull << 31) || cfg->max_chunk_records == 0)
+    return fail(ctx, MGK_ERR_ARG, "mgk_create: max_chunk_bytes must be in (0, 2^31) and max_chunk_records > 0");
+  if (cfg->allowed_mismatches < 0 || cfg->allowed_mismatches > 100) return fail(ctx, MGK_ERR_ARG, "mgk_create: bad mismatch count");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(ctx, MGK_ERR_NO_DEVICE, "no CUDA device is visible: the demultiplex hot path has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(ctx, MGK_ERR_NO_DEVICE, "CUDA device %d does not exist (%d visible)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(ctx, MGK_ERR_NO_DEVICE, "can not query device %d", cfg->device);
+  if (prop.major != 10)
+    return fail(ctx, MGK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only (B200)", cfg->device, prop.major, prop.minor);
+
+  ctx = new mgk_ctx();
+  ctx->device = cfg->device;
+  ctx->n_sm = prop.multiProcessorCount;
+#define CUC(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      fail(nullptr, MGK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                               \
+      mgk_destroy(ctx);                                                                                   \
+      return MGK_ERR_CUDA;                                                                                \
+    }                                                                                                     \
+  } while (0)
+#define BAD(...)                                 \
+  do {                                           \
+    fail(nullptr, MGK_ERR_ARG, __VA_ARGS__);     \
+    mgk_destroy(ctx);                            \
+    return MGK_ERR_ARG;                          \
+  } while (0)
+  CUC(cudaSetDevice(cfg->device));
+
+  Params& P = ctx->hp;
+  HostTables tb;
+  {
+    std::string why;
+    if (!build_params_host(cfg, P, tb, why)) BAD("mgk_create: %s", why.c_str());
+  }
+  ctx->total = P.total;
+  ctx->mism_w = P.mism_w;
+  const std::vector<uint64_t>& codes = tb.codes;
+  const std::vector<int32_t>&pairs = tb.pairs, &xlat = tb.xlat;
+  const std::string& consts = tb.consts;
+
+  CUC(dalloc(&ctx->d_codes, codes.size() + 1));
+  CUC(dalloc(&ctx->d_pairs, pairs.size() + 1));
+  CUC(dalloc(&ctx->d_xlat, xlat.size() + 1));
+  CUC(dalloc(&ctx->d_writing, (size_t)P.total));
+  CUC(dalloc(&ctx->d_consts, consts.size()));
+  CUC(dalloc(&ctx->d_stats, (size_t)P.total * MGK_N_STATS));
+  CUC(dalloc(&ctx->d_mism, (size_t)P.total * P.mism_w));
+  CUC(dalloc(&ctx->d_params, 1));
+  CUC(cudaMemcpy(ctx->d_codes, codes.data(), codes.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(ctx->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(ctx->d_xlat, xlat.data(), xlat.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(ctx->d_writing, cfg->writing_sample, (size_t)P.total * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(ctx->d_consts, consts.data(), consts.size(), cudaMemcpyHostToDevice));
+  CUC(cudaMemset(ctx->d_stats, 0, (size_t)P.total * MGK_N_STATS * sizeof(uint64_t)));
+  CUC(cudaMemset(ctx->d_mism, 0, (size_t)P.total * P.mism_w * sizeof(uint64_t)));
+  P.codes = ctx->d_codes;
+  P.pairs = ctx->d_pairs;
+  P.xlat = ctx->d_xlat;
+  P.writing = ctx->d_writing;
+  P.consts = ctx->d_consts;
+  CUC(cudaMemcpy(ctx->d_params, &P, sizeof P, cudaMemcpyHostToDevice));
+
+  // capacities
+  ctx->cap_bytes = cfg->max_chunk_bytes;
+  ctx->cap_records = cfg->max_chunk_records;
+  const uint64_t growth = (uint64_t)P.prefix_len + 2ull * P.BL + 32ull;
+  ctx->out_cap = ctx->cap_bytes + ctx->cap_records * growth;
+  if (ctx->out_cap >= (1ull << 32) - 4096) BAD("mgk_create: chunk capacity too large for 32-bit output offsets; lower max_chunk_bytes");
+  ctx->scan_tiles_max = (uint32_t)((ctx->cap_bytes + SCAN_TILE - 1) / SCAN_TILE) + 1;
+  ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
+  ctx->groups_max = (ctx->tiles_max + GROUP_TILES - 1) / GROUP_TILES;
+  ctx->match_smem = (size_t)P.n_codes * 8 + (size_t)2 * P.total * 4 + 16;
+  if (ctx->match_smem > 200 * 1024) BAD("mgk_create: index tables (%zu B) do not fit the shared-memory staging area", ctx->match_smem);
+  CUC(cudaFuncSetAttribute(k_match_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
+  CUC(cudaFuncSetAttribute(k_match_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
+  int occ_m = 1, occ_s = 1;
+  CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, k_match_plan, TILE_RECORDS, ctx->match_smem));
+  CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_scatter, TILE_RECORDS, 0));
+  ctx->grid_match = ctx->n_sm * (occ_m > 0 ? occ_m : 1);
+  ctx->grid_scatter = ctx->n_sm * (occ_s > 0 ? occ_s : 1);
+
+  CUC(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status_init), sizeof(Status), cudaHostAllocDefault));
+  memset(ctx->h_status_init, 0, sizeof(Status));
+  ctx->h_status_init->fmt_record = ~0ull;
+  ctx->h_status_init->validate_key = ~0ull;
+
+  const int n_slots = cfg->n_slots < 1 ? 1 : (cfg->n_slots > 8 ? 8 : cfg->n_slots);
+  ctx->slots.resize((size_t)n_slots);
+  const size_t B2 = (size_t)2 * P.total;
+  for (auto& s : ctx->slots) {
+    CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto& e : s.ev) CUC(cudaEventCreate(&e));
+    CUC(cudaEventCreateWithFlags(&s.ev_status, cudaEventDisableTiming));
+    CUC(dalloc(&s.d_r2, ctx->cap_bytes + 256));
+    if (P.paired) CUC(dalloc(&s.d_r1, ctx->cap_bytes + 256));
+    CUC(dalloc(&s.out2, ctx->out_cap + 256));
+    if (P.paired) CUC(dalloc(&s.out1, ctx->out_cap + 256));
+    CUC(dalloc(&s.nl2, ctx->cap_records * 4 + 8));
+    if (P.paired) CUC(dalloc(&s.nl1, ctx->cap_records * 4 + 8));
+    CUC(dalloc(&s.look2, (size_t)ctx->scan_tiles_max));
+    CUC(dalloc(&s.look1, (size_t)ctx->scan_tiles_max));
+    CUC(dalloc(&s.ctrl, 8));
+    CUC(dalloc(&s.meta, ctx->cap_records + 1));
+    CUC(dalloc(&s.tile_bins, (size_t)ctx->tiles_max * B2));
+    CUC(dalloc(&s.group_sums, (size_t)ctx->groups_max * B2));
+    CUC(dalloc(&s.seg, (size_t)4 * P.total));
+    CUC(dalloc(&s.unassigned, ctx->cap_records + 1));
+    CUC(dalloc(&s.status, 1));
+    CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_out2), ctx->out_cap + 256, cudaHostAllocDefault));
+    if (P.paired) CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_out1), ctx->out_cap + 256, cudaHostAllocDefault));
+    CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(Status), cudaHostAllocDefault));
+    CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_seg), (size_t)4 * P.total * 8, cudaHostAllocDefault));
+    CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_unassigned), (ctx->cap_records + 1) * 4, cudaHostAllocDefault));
+    s.off2.resize((size_t)P.total); s.len2v.resize((size_t)P.total); s.off1.resize((size_t)P.total); s.len1v.resize((size_t)P.total);
+    ChunkDev& c = s.cd;
+    c.nl2 = s.nl2; c.nl1 = s.nl1;
+    c.nl_cap = (uint32_t)(ctx->cap_records * 4 + 4);
+    c.max_records = (uint32_t)ctx->cap_records;
+    c.look2 = s.look2; c.look1 = s.look1;
+    c.tickets = s.ctrl; c.counts = s.ctrl + 2;
+    c.meta = s.meta; c.tile_bins = s.tile_bins; c.group_sums = s.group_sums; c.seg = s.seg;
+    c.out2 = s.out2; c.out1 = s.out1;
+    c.out_cap2 = ctx->out_cap; c.out_cap1 = ctx->out_cap;
+    c.unassigned = s.unassigned; c.status = s.status;
+    c.stats = ctx->d_stats; c.mism = ctx->d_mism;
+  }
+#undef CUC
+#undef BAD
+  *out = ctx;
+  return MGK_OK;
+}
+
+// ====================================================================== submit / collect / release
+extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_t r2_len, const uint8_t* r1, uint64_t r1_len,
+                          uint32_t flags) {
+  if (!ctx) return MGK_ERR_ARG;
+  const Params& P = ctx->hp;
+  if (!r2 && r2_len) return fail(ctx, MGK_ERR_ARG, "mgk_submit: null barcode-read buffer");
+  if (P.paired && !r1 && r1_len) return fail(ctx, MGK_ERR_ARG, "mgk_submit: paired run needs both reads");
+  if (!P.paired) r1_len = 0;
+  if (r2_len > ctx->cap_bytes || r1_len > ctx->cap_bytes)
+    return fail(ctx, MGK_ERR_CAPACITY, "mgk_submit: chunk of %llu/%llu bytes exceeds max_chunk_bytes %llu", (unsigned long long)r2_len,
+                (unsigned long long)r1_len, (unsigned long long)ctx->cap_bytes);
+  if ((flags & MGK_IN_DEVICE) && ((((uintptr_t)r2) | ((uintptr_t)r1)) & 15u))
+    return fail(ctx, MGK_ERR_ARG, "mgk_submit: device input pointers must be 16-byte aligned");
+  int si = -1;
+  for (size_t i = 0; i < ctx->slots.size(); ++i)
+    if (ctx->slots[i].state == 0) {
+      si = (int)i;
+      break;
+    }
+  if (si < 0) return fail(ctx, MGK_ERR_STATE, "mgk_submit: all %zu slots are in flight; collect and release first", ctx->slots.size());
+  CU(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slots[(size_t)si];
+  s.seq = seq;
+  s.flags = flags;
+  s.len2 = r2_len;
+  s.len1 = r1_len;
+  ChunkDev& c = s.cd;
+  c.len2 = (uint32_t)r2_len;
+  c.len1 = (uint32_t)r1_len;
+  cudaStream_t st = s.stream;
+  CU(cudaEventRecord(s.ev[0], st));
+  if (flags & MGK_IN_DEVICE) {
+    c.r2 = r2;
+    c.r1 = r1;
+  } else {
+    if (r2_len) CU(cudaMemcpyAsync(s.d_r2, r2, r2_len, cudaMemcpyHostToDevice, st));
+    if (r1_len) CU(cudaMemcpyAsync(s.d_r1, r1, r1_len, cudaMemcpyHostToDevice, st));
+    c.r2 = s.d_r2;
+    c.r1 = s.d_r1;
+  }
+  CU(cudaMemsetAsync(s.ctrl, 0, 8 * sizeof(uint32_t), st));
+  CU(cudaMemcpyAsync(s.status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice, st));
+  const uint32_t t2 = (uint32_t)((r2_len + SCAN_TILE - 1) / SCAN_TILE), t1 = (uint32_t)((r1_len + SCAN_TILE - 1) / SCAN_TILE);
+  if (t2) CU(cudaMemsetAsync(s.look2, 0, (size_t)t2 * 8, st));
+  if (t1) CU(cudaMemsetAsync(s.look1, 0, (size_t)t1 * 8, st));
+  CU(cudaEventRecord(s.ev[1], st));  // [0..1): input copy
+  const uint32_t tmax = t2 > t1 ? t2 : t1;
+  if (tmax) {
+    k_scan_newlines<<<dim3(tmax, P.paired ? 2 : 1), SCAN_THREADS, 0, st>>>(c, P.paired ? 2 : 1);
+    ++ctx->launches;
+  }
+  CU(cudaEventRecord(s.ev[2], st));
+  // the grids below are sized from the byte length (a record is >= 8 bytes); the kernels
+  // themselves read the record count the scan left on the device
+  const uint64_t rec_bound = std::min<uint64_t>(ctx->cap_records, r2_len / 8 + 1);
+  const uint32_t tiles_bound = (uint32_t)((rec_bound + TILE_RECORDS - 1) / TILE_RECORDS);
+  const uint32_t groups_bound = (tiles_bound + GROUP_TILES - 1) / GROUP_TILES;
+  const uint32_t B2 = 2u * (uint32_t)P.total;
+  k_match_plan<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_match), TILE_RECORDS, ctx->match_smem, st>>>(ctx->d_params, c);
+  CU(cudaEventRecord(s.ev[3], st));
+  const uint32_t scan_threads = groups_bound * B2;
+  k_scan_groups<<<(scan_threads + 255) / 256, 256, 0, st>>>(ctx->d_params, c);
+  k_scan_bins<<<1, 1024, 0, st>>>(ctx->d_params, c);
+  k_scan_tiles<<<(scan_threads + 255) / 256, 256, 0, st>>>(ctx->d_params, c);
+  CU(cudaEventRecord(s.ev[4], st));
+  k_scatter<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_scatter), TILE_RECORDS, 0, st>>>(ctx->d_params, c);
+  ctx->launches += 5;
+  CU(cudaEventRecord(s.ev[5], st));
+  CU(cudaMemcpyAsync(s.h_status, s.status, sizeof(Status), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.h_seg, s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(s.ev_status, st));
+  CU(cudaGetLastError());
+  s.state = 1;
+  ctx->fifo.push_back(si);
+  return MGK_OK;
+}
+
+extern "C" int mgk_collect(mgk_ctx* ctx, mgk_result* res) {
+  if (!ctx || !res) return MGK_ERR_ARG;
+  if (ctx->fifo.empty()) return fail(ctx, MGK_ERR_STATE, "mgk_collect: nothing in flight");
+  CU(cudaSetDevice(ctx->device));
+  const int si = ctx->fifo.front();
+  Slot& s = ctx->slots[(size_t)si];
+  const Params& P = ctx->hp;
+  CU(cudaEventSynchronize(s.ev_status));
+  ctx->fifo.pop_front();
+  s.state = 2;
+  const Status& hs = *s.h_status;
+  for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&s.ms[i], s.ev[i + 1], s.ev[i + 2]);
+  cudaEventElapsedTime(&s.ms[4], s.ev[0], s.ev[5]);
+  memcpy(ctx->last_ms, s.ms, sizeof s.ms);
+  if (hs.error & ERR_PANIC)
+    return fail(ctx, MGK_ERR_FORMAT, "chunk %llu: a read hits a sample-sheet combination on which the reference panics (stale template dictionary)",
+                (unsigned long long)s.seq);
+  if (hs.error & (ERR_NL_CAPACITY | ERR_REC_CAPACITY))
+    return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu holds more records than max_chunk_records = %llu", (unsigned long long)s.seq,
+                (unsigned long long)ctx->cap_records);
+  if (hs.error & ERR_OUT_CAPACITY) return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: output does not fit the output buffer", (unsigned long long)s.seq);
+  if (hs.fmt_record != ~0ull)
+    return fail(ctx, MGK_ERR_FORMAT, "chunk %llu, read %llu: lines shorter than the barcode/header layout", (unsigned long long)s.seq, hs.fmt_record);
+  const int total = P.total;
+  for (int b = 0; b < total; ++b) {
+    s.off2[(size_t)b] = s.h_seg[0 * total + b];
+    s.len2v[(size_t)b] = s.h_seg[1 * total + b];
+    s.off1[(size_t)b] = s.h_seg[2 * total + b];
+    s.len1v[(size_t)b] = s.h_seg[3 * total + b];
+  }
+  const uint64_t tot2 = s.off2[(size_t)total - 1] + s.len2v[(size_t)total - 1];
+  const uint64_t tot1 = s.off1[(size_t)total - 1] + s.len1v[(size_t)total - 1];
+  memset(res, 0, sizeof *res);
+  if (!(s.flags & MGK_OUT_DEVICE)) {
+    if (tot2) CU(cudaMemcpyAsync(s.h_out2, s.out2, tot2, cudaMemcpyDeviceToHost, s.stream));
+    if (tot1) CU(cudaMemcpyAsync(s.h_out1, s.out1, tot1, cudaMemcpyDeviceToHost, s.stream));
+    res->out_r2 = s.h_out2;
+    res->out_r1 = P.paired ? s.h_out1 : nullptr;
+  } else {
+    res->out_r2 = s.out2;
+    res->out_r1 = P.paired ? s.out1 : nullptr;
+  }
+  if (hs.n_unassigned) CU(cudaMemcpyAsync(s.h_unassigned, s.unassigned, (size_t)hs.n_unassigned * 4, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  res->seq = s.seq;
+  res->n_records = hs.n_records;
+  res->consumed_r2 = hs.consumed2;
+  res->consumed_r1 = hs.consumed1;
+  res->out_r2_bytes = tot2;
+  res->out_r1_bytes = tot1;
+  res->seg_off_r2 = s.off2.data();
+  res->seg_len_r2 = s.len2v.data();
+  res->seg_off_r1 = s.off1.data();
+  res->seg_len_r1 = s.len1v.data();
+  res->unassigned = s.h_unassigned;
+  res->n_unassigned = hs.n_unassigned;
+  if (hs.validate_key != ~0ull) {
+    res->validate_error = validate_kind((int)(hs.validate_key & 15u));
+    res->validate_record = hs.validate_key >> 4;
+  }
+  return MGK_OK;
+}
+
+extern "C" int mgk_release(mgk_ctx* ctx, uint64_t seq) {
+  if (!ctx) return MGK_ERR_ARG;
+  for (auto& s : ctx->slots)
+    if (s.state == 2 && s.seq == seq) {
+      s.state = 0;
+      return MGK_OK;
+    }
+  return fail(ctx, MGK_ERR_STATE, "mgk_release: chunk %llu is not waiting for release", (unsigned long long)seq);
+}
+
+// ====================================================================== counters
+extern "C" int mgk_counters(mgk_ctx* ctx, uint64_t* stats, uint64_t* mism) {
+  if (!ctx) return MGK_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  if (stats) CU(cudaMemcpy(stats, ctx->d_stats, (size_t)ctx->total * MGK_N_STATS * 8, cudaMemcpyDeviceToHost));
+  if (mism) CU(cudaMemcpy(mism, ctx->d_mism, (size_t)ctx->total * ctx->mism_w * 8, cudaMemcpyDeviceToHost));
+  return MGK_OK;
+}
+
+extern "C" int mgk_reset_counters(mgk_ctx* ctx) {
+  if (!ctx) return MGK_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemset(ctx->d_stats, 0, (size_t)ctx->total * MGK_N_STATS * 8));
+  CU(cudaMemset(ctx->d_mism, 0, (size_t)ctx->total * ctx->mism_w * 8));
+  return MGK_OK;
+}
+
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    ncclResult_t r_ = (call);                                                                                 \
+    if (r_ != ncclSuccess) return fail(ctx, MGK_ERR_NCCL, "%s: %s", #call, n->GetErrorString ? n->GetErrorString(r_) : "nccl error"); \
+  } while (0)
+
+extern "C" int mgk_allreduce_counters(mgk_ctx* const* ctxs, int n_ctx) {
+  if (!ctxs || n_ctx < 1 || !ctxs[0]) return MGK_ERR_ARG;
+  mgk_ctx* ctx = ctxs[0];
+  if (n_ctx == 1) return MGK_OK;
+  NcclApi* n = nccl_api();
+  if (!n) return fail(ctx, MGK_ERR_NCCL, "libnccl.so.2 can not be loaded");
+  std::vector<int> devs((size_t)n_ctx);
+  for (int i = 0; i < n_ctx; ++i) {
+    if (!ctxs[i] || ctxs[i]->total != ctx->total || ctxs[i]->mism_w != ctx->mism_w) return fail(ctx, MGK_ERR_ARG, "contexts describe different runs");
+    devs[(size_t)i] = ctxs[i]->device;
+  }
+  std::vector<ncclComm_t> comms((size_t)n_ctx);
+  NC(n->CommInitAll(comms.data(), n_ctx, devs.data()));
+  for (int i = 0; i < n_ctx; ++i) {
+    cudaSetDevice(ctxs[i]->device);
+    cudaDeviceSynchronize();
+  }
+  NC(n->GroupStart());
+  for (int i = 0; i < n_ctx; ++i) {
+    n->AllReduce(ctxs[i]->d_stats, ctxs[i]->d_stats, (size_t)ctx->total * MGK_N_STATS, ncclUint64, ncclSum, comms[(size_t)i], 0);
+    n->AllReduce(ctxs[i]->d_mism, ctxs[i]->d_mism, (size_t)ctx->total * ctx->mism_w, ncclUint64, ncclSum, comms[(size_t)i], 0);
+  }
+  NC(n->GroupEnd());
+  for (int i = 0; i < n_ctx; ++i) {
+    cudaSetDevice(ctxs[i]->device);
+    cudaDeviceSynchronize();
+    if (n->CommDestroy) n->CommDestroy(comms[(size_t)i]);
+  }
+  // every context now holds the run total; keep only rank 0's copy additive
+  for (int i = 1; i < n_ctx; ++i) {
+    cudaSetDevice(ctxs[i]->device);
+    cudaMemset(ctxs[i]->d_stats, 0, (size_t)ctx->total * MGK_N_STATS * 8);
+    cudaMemset(ctxs[i]->d_mism, 0, (size_t)ctx->total * ctx->mism_w * 8);
+  }
+  return MGK_OK;
+}
+
+extern "C" int mgk_nccl_unique_id(uint8_t id[MGK_NCCL_ID_BYTES]) {
+  mgk_ctx* ctx = nullptr;
+  NcclApi* n = nccl_api();
+  if (!n) return fail(ctx, MGK_ERR_NCCL, "libnccl.so.2 can not be loaded");
+  static_assert(sizeof(ncclUniqueId) <= MGK_NCCL_ID_BYTES, "nccl id size");
+  ncclUniqueId uid;
+  NC(n->GetUniqueId(&uid));
+  memset(id, 0, MGK_NCCL_ID_BYTES);
+  memcpy(id, &uid, sizeof uid);
+  return MGK_OK;
+}
+
+extern "C" int mgk_nccl_join(mgk_ctx* ctx, const uint8_t id[MGK_NCCL_ID_BYTES], int rank, int nranks) {
+  if (!ctx) return MGK_ERR_ARG;
+  NcclApi* n = nccl_api();
+  if (!n) return fail(ctx, MGK_ERR_NCCL, "libnccl.so.2 can not be loaded");
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  NC(n->CommInitRank(&ctx->comm, nranks, uid, rank));
+  return MGK_OK;
+}
+
+extern "C" int mgk_nccl_allreduce_counters(mgk_ctx* ctx) {
+  if (!ctx) return MGK_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, MGK_ERR_STATE, "mgk_nccl_allreduce_counters: call mgk_nccl_join first");
+  NcclApi* n = nccl_api();
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  NC(n->GroupStart());
+  n->AllReduce(ctx->d_stats, ctx->d_stats, (size_t)ctx->total * MGK_N_STATS, ncclUint64, ncclSum, ctx->comm, 0);
+  n->AllReduce(ctx->d_mism, ctx->d_mism, (size_t)ctx->total * ctx->mism_w, ncclUint64, ncclSum, ctx->comm, 0);
+  NC(n->GroupEnd());
+  CU(cudaDeviceSynchronize());
+  return MGK_OK;
+}
+
+// ====================================================================== misc
+extern "C" void* mgk_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void mgk_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int mgk_last_timings(const mgk_ctx* ctx, float ms[5]) {
+  if (!ctx || !ms) return MGK_ERR_ARG;
+  memcpy(ms, ctx->last_ms, sizeof ctx->last_ms);
+  return MGK_OK;
+}
+extern "C" uint64_t mgk_launch_count(const mgk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ====================================================================== single-stage entry points
+extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len, uint32_t* positions, uint64_t capacity, uint64_t* count) {
+  if (!ctx || (!buf && len) || !count || len >= (1ull << 31)) return MGK_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  uint8_t* d_buf = nullptr;
+  uint32_t *d_nl = nullptr, *d_ctrl = nullptr;
+  unsigned long long* d_look = nullptr;
+  Status* d_status = nullptr;
+  const uint32_t tiles = (uint32_t)((len + SCAN_TILE - 1) / SCAN_TILE);
+  int rc = MGK_OK;
+  Status hs;
+  uint32_t h_ctrl[8] = {0};
+  do {
+#define TRY(call)                                                                  \
+  if ((call) != cudaSuccess) {                                                     \
+    rc = fail(ctx, MGK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); \
+    break;                                                                         \
+  }
+    TRY(dalloc(&d_buf, len + 256));
+    TRY(dalloc(&d_nl, capacity + 4));
+    TRY(dalloc(&d_ctrl, 8));
+    TRY(dalloc(&d_look, (size_t)tiles + 1));
+    TRY(dalloc(&d_status, 1));
+    TRY(cudaMemcpy(d_buf, buf, len, cudaMemcpyHostToDevice));
+    TRY(cudaMemset(d_ctrl, 0, 32));
+    TRY(cudaMemset(d_look, 0, ((size_t)tiles + 1) * 8));
+    TRY(cudaMemcpy(d_status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice));
+    ChunkDev c{};
+    c.r2 = d_buf;
+    c.len2 = (uint32_t)len;
+    c.nl2 = d_nl;
+    c.nl_cap = (uint32_t)std::min<uint64_t>(capacity, 0xffffffffu);
+    c.look2 = d_look;
+    c.tickets = d_ctrl;
+    c.counts = d_ctrl + 2;
+    c.status = d_status;
+    if (tiles) {
+      k_scan_newlines<<<dim3(tiles, 1), SCAN_THREADS>>>(c, 1);
+      ++ctx->launches;
+    }
+    TRY(cudaDeviceSynchronize());
+    TRY(cudaMemcpy(h_ctrl, d_ctrl, 32, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(&hs, d_status, sizeof hs, cudaMemcpyDeviceToHost));
+    *count = h_ctrl[2];
+    const uint64_t ncopy = std::min<uint64_t>(*count, capacity);
+    if (ncopy) TRY(cudaMemcpy(positions, d_nl, ncopy * 4, cudaMemcpyDeviceToHost));
+    if (*count > capacity) rc = fail(ctx, MGK_ERR_CAPACITY, "mgk_scan_newlines: %llu newlines, capacity %llu", (unsigned long long)*count, (unsigned long long)capacity);
+  } while (0);
+  cudaFree(d_buf); cudaFree(d_nl); cudaFree(d_ctrl); cudaFree(d_look); cudaFree(d_status);
+  return rc;
+}
+
+extern "C" int mgk_match_barcodes(mgk_ctx* ctx, const uint8_t* barcodes, uint64_t n, int32_t* sample_id, int32_t* mismatches) {
+  if (!ctx || (!barcodes && n) || n >= (1ull << 31)) return MGK_ERR_ARG;
+  if (n == 0) return MGK_OK;
+  CU(cudaSetDevice(ctx->device));
+  uint8_t* d_bars = nullptr;
+  int32_t *d_s = nullptr, *d_m = nullptr;
+  uint32_t* d_err = nullptr;
+  int rc = MGK_OK;
+  uint32_t herr = 0;
+  const size_t bytes = (size_t)n * ctx->hp.BL;
+  do {
+    TRY(dalloc(&d_bars, bytes + 64));
+    TRY(dalloc(&d_s, (size_t)n));
+    TRY(dalloc(&d_m, (size_t)n));
+    TRY(dalloc(&d_err, 1));
+    TRY(cudaMemcpy(d_bars, barcodes, bytes, cudaMemcpyHostToDevice));
+    TRY(cudaMemset(d_err, 0, 4));
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 8);
+    k_match_only<<<blocks, 256, ctx->match_smem>>>(ctx->d_params, d_bars, (uint32_t)n, d_s, d_m, d_err);
+    ++ctx->launches;
+    TRY(cudaDeviceSynchronize());
+    TRY(cudaMemcpy(sample_id, d_s, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(mismatches, d_m, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost));
+    if (herr & ERR_PANIC) rc = fail(ctx, MGK_ERR_FORMAT, "a barcode hits a sample-sheet combination on which the reference panics");
+#undef TRY
+  } while (0);
+  cudaFree(d_bars); cudaFree(d_s); cudaFree(d_m); cudaFree(d_err);
+  return rc;
+}

@@ -1,0 +1,106 @@
+// mgk_config -> Params + flat tables (host side).  Shared by libmgikit_gpu.so
+// (which then uploads the tables) and by the CPU emulation used in tests.
+#pragma once
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_logic.cuh"
+
+namespace mgk {
+
+struct HostTables {
+  std::vector<uint64_t> codes;   // 2-bit packed unique indexes, all templates
+  std::vector<int32_t> pairs;    // pair -> sample tables
+  std::vector<int32_t> xlat;     // index-id translation between templates
+  std::vector<int32_t> writing;
+  std::string consts;            // illumina prefix + literal bytes
+};
+
+// Fills P (pointer members left null) and tb.  Returns false with a reason.
+inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, std::string& why) {
+  memset(&P, 0, sizeof P);
+  P.paired = cfg->paired;
+  P.read2_has_sequence = cfg->read2_has_sequence;
+  P.out_mode = cfg->out_mode;
+  P.keep_barcode = cfg->keep_barcode;
+  P.comprehensive = cfg->comprehensive_scan;
+  P.validate = cfg->validate;
+  P.report_level = cfg->report_level;
+  P.mgi_data = cfg->mgi_data;
+  P.m = cfg->allowed_mismatches;
+  P.M = cfg->total_allowed_mismatches;
+  P.L = cfg->l_position;
+  P.S = cfg->n_samples;
+  P.total = cfg->n_samples + 2;
+  P.BL = cfg->templates[0].geometry[9];
+  P.mism_w = 2 * cfg->allowed_mismatches + 2;
+  P.n_tpl = cfg->n_templates;
+  const std::string prefix = cfg->illumina_prefix ? cfg->illumina_prefix : "";
+  P.prefix_len = (int)prefix.size();
+  if (P.out_mode < 0 || P.out_mode > 2) { why = "unknown out_mode"; return false; }
+  if (P.out_mode == MGK_OUT_ILLUMINA && prefix.empty()) { why = "illumina output needs the header prefix"; return false; }
+  if (P.BL < 1 || P.BL > MGK_MAX_BARCODE_LEN) { why = "barcode length outside [1,255]"; return false; }
+  if (P.L < 0) { why = "negative l_position"; return false; }
+  for (int t = 0; t < P.n_tpl; ++t) {
+    const mgk_template& s = cfg->templates[t];
+    TemplateDev& T = P.tpl[t];
+    for (int k = 0; k < 10; ++k) T.g[k] = s.geometry[k];
+    if (T.g[9] != P.BL) { why = "all templates must describe the same barcode length"; return false; }
+    if (T.g[1] < 1 || T.g[1] > MGK_MAX_INDEX_LEN || T.g[4] < 0 || T.g[4] > MGK_MAX_INDEX_LEN) { why = "index lengths must be in [1,32]"; return false; }
+    if (T.g[2] > P.BL || T.g[2] < T.g[1] || (s.has_i5 && (T.g[5] > P.BL || T.g[5] < T.g[4])) || (T.g[6] && (T.g[8] > P.BL || T.g[8] < T.g[7]))) {
+      why = "a template places an item outside the barcode";
+      return false;
+    }
+    T.has_i5 = s.has_i5 ? 1 : 0;
+    T.n_i7 = s.n_i7;
+    T.n_i5 = s.has_i5 ? s.n_i5 : 0;
+    if (T.n_i7 < 0 || T.n_i5 < 0 || !s.pair_sample) { why = "a template has no index table"; return false; }
+    T.wide = (T.g[1] > 16 || (T.has_i5 && T.g[4] > 16)) ? 1 : 0;
+    T.off_i7 = (int)tb.codes.size();
+    for (int i = 0; i < T.n_i7; ++i) tb.codes.push_back(pack_index_host(s.i7 + (size_t)i * T.g[1], T.g[1]));
+    T.off_i5 = (int)tb.codes.size();
+    for (int i = 0; i < T.n_i5; ++i) tb.codes.push_back(pack_index_host(s.i5 + (size_t)i * T.g[4], T.g[4]));
+    T.off_pair = (int)tb.pairs.size();
+    const size_t np = T.has_i5 ? (size_t)T.n_i7 * T.n_i5 : (size_t)T.n_i7;
+    tb.pairs.insert(tb.pairs.end(), s.pair_sample, s.pair_sample + np);
+  }
+  // index-id translation between templates (stale dictionary iterator of the reference)
+  for (int d = 0; d < P.n_tpl; ++d)
+    for (int t = 0; t < P.n_tpl; ++t)
+      for (int which = 0; which < 2; ++which) {
+        int32_t* off = which == 0 ? P.xl7_off : P.xl5_off;
+        off[d * MGK_MAX_TEMPLATES + t] = (int)tb.xlat.size();
+        const mgk_template &sd = cfg->templates[d], &st = cfg->templates[t];
+        const int nd = which == 0 ? P.tpl[d].n_i7 : P.tpl[d].n_i5, nt = which == 0 ? P.tpl[t].n_i7 : P.tpl[t].n_i5;
+        const int ld = which == 0 ? P.tpl[d].g[1] : P.tpl[d].g[4], lt = which == 0 ? P.tpl[t].g[1] : P.tpl[t].g[4];
+        const char* seqd = which == 0 ? sd.i7 : sd.i5;
+        const char* seqt = which == 0 ? st.i7 : st.i5;
+        for (int i = 0; i < nd; ++i) {
+          int found = -1;
+          if (d == t) found = i;
+          else if (ld == lt)
+            for (int j = 0; j < nt && found < 0; ++j)
+              if (memcmp(seqd + (size_t)i * ld, seqt + (size_t)j * lt, (size_t)ld) == 0) found = j;
+          tb.xlat.push_back(found);
+        }
+        if (nd == 0) tb.xlat.push_back(-1);
+      }
+  P.n_codes = (int)tb.codes.size();
+  tb.consts = prefix;
+  char lit[LIT_BYTES];
+  memset(lit, 0, sizeof lit);
+  lit[LIT_COLON] = ':';
+  lit[LIT_SPACE] = ' ';
+  memcpy(lit + LIT_TAIL, ":N:0:", 5);
+  lit[LIT_PLUS] = '+';
+  lit[LIT_NL] = '\n';
+  tb.consts.append(lit, LIT_BYTES);
+  tb.writing.assign(cfg->writing_sample, cfg->writing_sample + P.total);
+  for (int i = 0; i < P.total; ++i)
+    if (tb.writing[(size_t)i] < 0 || tb.writing[(size_t)i] >= P.total) { why = "writing_sample out of range"; return false; }
+  return true;
+}
+
+}  // namespace mgk
