@@ -178,6 +178,11 @@ void mgk_host_free(void* p);
  * most recently collected chunk: [0] record scan, [1] match+lengths,
  * [2] bin scan, [3] scatter(+QC), [4] whole chunk incl. copies.               */
 int mgk_last_timings(const mgk_ctx* ctx, float ms[5]);
+/* Device time (ms) from the start of the first chunk submitted after the last
+ * call (or after create) to the end of the last chunk submitted: one pair of
+ * CUDA events on the launching streams, so overlapped chunks are not counted
+ * twice.  Waits for that last chunk.                                          */
+int mgk_span_ms(mgk_ctx* ctx, float* ms);
 /* Number of kernel launches issued by this context so far. */
 uint64_t mgk_launch_count(const mgk_ctx* ctx);
 

@@ -55,7 +55,7 @@ class MgkResult(C.Structure):
 # every entry point include/mgikit_gpu.h declares
 ABI_SYMBOLS = ["create", "destroy", "last_error", "submit", "collect", "release", "counters", "reset_counters",
                "allreduce_counters", "nccl_unique_id", "nccl_join", "nccl_allreduce_counters", "host_alloc",
-               "host_free", "last_timings", "launch_count", "scan_newlines", "match_barcodes"]
+               "host_free", "last_timings", "span_ms", "launch_count", "scan_newlines", "match_barcodes"]
 
 
 def load_gpu_library() -> C.CDLL:
@@ -200,6 +200,13 @@ class HotPath:
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         self._check(fn(self.ctx, ms))
         return list(ms)
+
+    def span_ms(self) -> float:
+        ms = C.c_float()
+        fn = self._f("span_ms")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self._check(fn(self.ctx, C.byref(ms)))
+        return float(ms.value)
 
     def launch_count(self) -> int:
         fn = self._f("launch_count")

@@ -67,6 +67,8 @@ struct mgk_ctx {
   uint64_t launches = 0;
   float last_ms[5] = {0, 0, 0, 0, 0};
   ncclComm_t comm = nullptr;
+  cudaEvent_t span_begin = nullptr, span_end = nullptr;
+  bool span_open = false;
   char err[512] = "";
 };
 
@@ -157,6 +159,8 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
   cudaFree(ctx->d_params); cudaFree(ctx->d_codes); cudaFree(ctx->d_pairs); cudaFree(ctx->d_xlat);
   cudaFree(ctx->d_writing); cudaFree(ctx->d_consts); cudaFree(ctx->d_stats); cudaFree(ctx->d_mism);
   cudaFreeHost(ctx->h_status_init);
+  if (ctx->span_begin) cudaEventDestroy(ctx->span_begin);
+  if (ctx->span_end) cudaEventDestroy(ctx->span_end);
   if (ctx->comm) {
     NcclApi* n = nccl_api();
     if (n && n->CommDestroy) n->CommDestroy(ctx->comm);
@@ -258,6 +262,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   ctx->grid_match = ctx->n_sm * (occ_m > 0 ? occ_m : 1);
   ctx->grid_scatter = ctx->n_sm * (occ_s > 0 ? occ_s : 1);
 
+  CUC(cudaEventCreate(&ctx->span_begin));
+  CUC(cudaEventCreate(&ctx->span_end));
   CUC(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status_init), sizeof(Status), cudaHostAllocDefault));
   memset(ctx->h_status_init, 0, sizeof(Status));
   ctx->h_status_init->fmt_record = ~0ull;
@@ -340,6 +346,10 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   c.len1 = (uint32_t)r1_len;
   cudaStream_t st = s.stream;
   CU(cudaEventRecord(s.ev[0], st));
+  if (!ctx->span_open) {
+    CU(cudaEventRecord(ctx->span_begin, st));
+    ctx->span_open = true;
+  }
   if (flags & MGK_IN_DEVICE) {
     c.r2 = r2;
     c.r1 = r1;
@@ -377,6 +387,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   k_scatter<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_scatter), TILE_RECORDS, 0, st>>>(ctx->d_params, c);
   ctx->launches += 5;
   CU(cudaEventRecord(s.ev[5], st));
+  CU(cudaEventRecord(ctx->span_end, st));
   CU(cudaMemcpyAsync(s.h_status, s.status, sizeof(Status), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(s.h_seg, s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(s.ev_status, st));
@@ -571,6 +582,16 @@ extern "C" void mgk_host_free(void* p) {
 extern "C" int mgk_last_timings(const mgk_ctx* ctx, float ms[5]) {
   if (!ctx || !ms) return MGK_ERR_ARG;
   memcpy(ms, ctx->last_ms, sizeof ctx->last_ms);
+  return MGK_OK;
+}
+extern "C" int mgk_span_ms(mgk_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return MGK_ERR_ARG;
+  *ms = 0.f;
+  if (!ctx->span_open) return MGK_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->span_end));
+  CU(cudaEventElapsedTime(ms, ctx->span_begin, ctx->span_end));
+  ctx->span_open = false;
   return MGK_OK;
 }
 extern "C" uint64_t mgk_launch_count(const mgk_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -183,6 +183,18 @@ typedef struct {
   dict d7, d5;
 } otpl;
 
+struct oslot {
+  int state; /* 0 free, 1 submitted, 2 collected */
+  uint64_t seq, order;
+  bytebuf* bin_r2; /* [total] */
+  bytebuf* bin_r1;
+  bytebuf out_r2, out_r1;
+  uint64_t *off2, *len2, *off1, *len1;
+  uint32_t* unassigned;
+  size_t n_unassigned, cap_unassigned;
+  mgk_result res;
+};
+
 struct orc_ctx {
   mgk_config cfg;
   char* prefix;
@@ -193,16 +205,10 @@ struct orc_ctx {
   int S, total, BL, mism_w;
   uint64_t* stats; /* [total][10] */
   uint64_t* mism;  /* [total][2m+2] */
-  /* one result slot */
-  int have_result;
-  uint64_t seq;
-  bytebuf* bin_r2; /* [total] */
-  bytebuf* bin_r1;
-  bytebuf out_r2, out_r1;
-  uint64_t *off2, *len2, *off1, *len1;
-  uint32_t* unassigned;
-  size_t n_unassigned, cap_unassigned;
-  mgk_result res;
+  /* result slots: cfg.n_slots chunks may be submitted before the first is released */
+  struct oslot* slots;
+  int n_slots;
+  uint64_t submit_clock;
   char err[512];
 };
 
@@ -253,12 +259,17 @@ int orc_create(const mgk_config* cfg, orc_ctx** out) {
   c->BL = c->tpl[0].g[9]; /* src/lib.rs:878-879 */
   c->stats = (uint64_t*)calloc((size_t)c->total * MGK_N_STATS, sizeof(uint64_t));
   c->mism = (uint64_t*)calloc((size_t)c->total * (size_t)c->mism_w, sizeof(uint64_t));
-  c->bin_r2 = (bytebuf*)calloc((size_t)c->total, sizeof(bytebuf));
-  c->bin_r1 = (bytebuf*)calloc((size_t)c->total, sizeof(bytebuf));
-  c->off2 = (uint64_t*)calloc((size_t)c->total * 4, sizeof(uint64_t));
-  c->len2 = c->off2 + c->total;
-  c->off1 = c->len2 + c->total;
-  c->len1 = c->off1 + c->total;
+  c->n_slots = cfg->n_slots < 1 ? 1 : (cfg->n_slots > 8 ? 8 : cfg->n_slots);
+  c->slots = (struct oslot*)calloc((size_t)c->n_slots, sizeof(struct oslot));
+  for (int k = 0; k < c->n_slots; ++k) {
+    struct oslot* s = &c->slots[k];
+    s->bin_r2 = (bytebuf*)calloc((size_t)c->total, sizeof(bytebuf));
+    s->bin_r1 = (bytebuf*)calloc((size_t)c->total, sizeof(bytebuf));
+    s->off2 = (uint64_t*)calloc((size_t)c->total * 4, sizeof(uint64_t));
+    s->len2 = s->off2 + c->total;
+    s->off1 = s->len2 + c->total;
+    s->len1 = s->off1 + c->total;
+  }
   *out = c;
   return MGK_OK;
 }
@@ -272,16 +283,20 @@ void orc_destroy(orc_ctx* c) {
     dict_free(&c->tpl[t].d7);
     dict_free(&c->tpl[t].d5);
   }
-  for (int b = 0; b < c->total; ++b) {
-    free(c->bin_r2[b].p);
-    free(c->bin_r1[b].p);
+  for (int k = 0; k < c->n_slots; ++k) {
+    struct oslot* s = &c->slots[k];
+    for (int b = 0; b < c->total; ++b) {
+      free(s->bin_r2[b].p);
+      free(s->bin_r1[b].p);
+    }
+    free(s->bin_r2);
+    free(s->bin_r1);
+    free(s->out_r2.p);
+    free(s->out_r1.p);
+    free(s->off2);
+    free(s->unassigned);
   }
-  free(c->bin_r2);
-  free(c->bin_r1);
-  free(c->out_r2.p);
-  free(c->out_r1.p);
-  free(c->off2);
-  free(c->unassigned);
+  free(c->slots);
   free(c->tpl);
   free(c->stats);
   free(c->mism);
@@ -513,8 +528,11 @@ int orc_match_barcodes(orc_ctx* c, const uint8_t* barcodes, uint64_t n, int32_t*
 int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, const uint8_t* r1,
                uint64_t r1_len, uint32_t flags) {
   (void)flags;
-  if (c->have_result) {
-    snprintf(c->err, sizeof c->err, "orc_submit: previous chunk not released");
+  struct oslot* S = NULL;
+  for (int k = 0; k < c->n_slots && !S; ++k)
+    if (c->slots[k].state == 0) S = &c->slots[k];
+  if (!S) {
+    snprintf(c->err, sizeof c->err, "orc_submit: all slots are in flight; collect and release first");
     return MGK_ERR_STATE;
   }
   const mgk_config* cfg = &c->cfg;
@@ -527,9 +545,9 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
   const int illumina = cfg->out_mode == MGK_OUT_ILLUMINA;
   const int full_hdr = cfg->out_mode == MGK_OUT_MGI_FULL_HEADER;
 
-  for (int b = 0; b < total; ++b) c->bin_r2[b].n = c->bin_r1[b].n = 0;
-  c->n_unassigned = 0;
-  memset(&c->res, 0, sizeof c->res);
+  for (int b = 0; b < total; ++b) S->bin_r2[b].n = S->bin_r1[b].n = 0;
+  S->n_unassigned = 0;
+  memset(&S->res, 0, sizeof S->res);
 
   uint32_t *nl2 = NULL, *nl1 = NULL;
   size_t n2 = memchr_all(r2, (size_t)r2_len, &nl2); /* src/lib.rs:1526 */
@@ -604,11 +622,11 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
     if (sample_id == und || sample_id == amb) {
       /* :1048-1088: the label is rebuilt on the host from this offset */
       if (cfg->report_level > 1) {
-        if (c->n_unassigned == c->cap_unassigned) {
-          c->cap_unassigned = c->cap_unassigned ? c->cap_unassigned * 2 : 1024;
-          c->unassigned = (uint32_t*)realloc(c->unassigned, c->cap_unassigned * sizeof(uint32_t));
+        if (S->n_unassigned == S->cap_unassigned) {
+          S->cap_unassigned = S->cap_unassigned ? S->cap_unassigned * 2 : 1024;
+          S->unassigned = (uint32_t*)realloc(S->unassigned, S->cap_unassigned * sizeof(uint32_t));
         }
-        c->unassigned[c->n_unassigned++] =
+        S->unassigned[S->n_unassigned++] =
             (uint32_t)(plus_start - 1 - BL) | (sample_id == amb ? 0x80000000u : 0u);
       }
     }
@@ -629,8 +647,8 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
         v = check_read_content(r2 + header_start, read_end - header_start, seq_start - header_start,
                                plus_start - header_start, qual_start - header_start);
       if (v) {
-        c->res.validate_error = v;
-        c->res.validate_record = i;
+        S->res.validate_error = v;
+        S->res.validate_record = i;
         break;
       }
     }
@@ -654,11 +672,11 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
 
     const int w = c->writing[sample_id]; /* :1214 */
     if (sample_id >= und) {              /* :1225-1235 */
-      bb_add(&c->bin_r2[sample_id], r2 + header_start, read_end + 1 - header_start);
-      if (paired) bb_add(&c->bin_r1[sample_id], r1 + header_start_pr, read_end_pr + 1 - header_start_pr);
+      bb_add(&S->bin_r2[sample_id], r2 + header_start, read_end + 1 - header_start);
+      if (paired) bb_add(&S->bin_r1[sample_id], r1 + header_start_pr, read_end_pr + 1 - header_start_pr);
     } else {
-      bytebuf* B2 = cfg->read2_has_sequence ? &c->bin_r2[w] : NULL; /* src/sample_data.rs:35-44, :683 */
-      bytebuf* B1 = paired ? &c->bin_r1[w] : NULL;
+      bytebuf* B2 = cfg->read2_has_sequence ? &S->bin_r2[w] : NULL; /* src/sample_data.rs:35-44, :683 */
+      bytebuf* B1 = paired ? &S->bin_r1[w] : NULL;
       if (illumina) { /* :1240-1293 */
         size_t e = c->prefix_len;
         memcpy(hdr, c->prefix, e); /* src/sample_data.rs:256 */
@@ -716,50 +734,56 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
   if (rc != MGK_OK) return rc;
 
   /* lay the bins out back to back, like the GPU result */
-  c->out_r2.n = c->out_r1.n = 0;
+  S->out_r2.n = S->out_r1.n = 0;
   for (int b = 0; b < total; ++b) {
-    c->off2[b] = c->out_r2.n;
-    c->len2[b] = c->bin_r2[b].n;
-    if (c->bin_r2[b].n) bb_add(&c->out_r2, c->bin_r2[b].p, c->bin_r2[b].n);
-    c->off1[b] = c->out_r1.n;
-    c->len1[b] = c->bin_r1[b].n;
-    if (c->bin_r1[b].n) bb_add(&c->out_r1, c->bin_r1[b].p, c->bin_r1[b].n);
+    S->off2[b] = S->out_r2.n;
+    S->len2[b] = S->bin_r2[b].n;
+    if (S->bin_r2[b].n) bb_add(&S->out_r2, S->bin_r2[b].p, S->bin_r2[b].n);
+    S->off1[b] = S->out_r1.n;
+    S->len1[b] = S->bin_r1[b].n;
+    if (S->bin_r1[b].n) bb_add(&S->out_r1, S->bin_r1[b].p, S->bin_r1[b].n);
   }
-  c->res.seq = seq;
-  c->res.n_records = read_cntr;
-  c->res.consumed_r2 = header_start;
-  c->res.consumed_r1 = header_start_pr;
-  c->res.out_r2 = c->out_r2.p;
-  c->res.out_r1 = paired ? c->out_r1.p : NULL;
-  c->res.out_r2_bytes = c->out_r2.n;
-  c->res.out_r1_bytes = c->out_r1.n;
-  c->res.seg_off_r2 = c->off2;
-  c->res.seg_len_r2 = c->len2;
-  c->res.seg_off_r1 = c->off1;
-  c->res.seg_len_r1 = c->len1;
-  c->res.unassigned = c->unassigned;
-  c->res.n_unassigned = c->n_unassigned;
-  c->seq = seq;
-  c->have_result = 1;
+  S->res.seq = seq;
+  S->res.n_records = read_cntr;
+  S->res.consumed_r2 = header_start;
+  S->res.consumed_r1 = header_start_pr;
+  S->res.out_r2 = S->out_r2.p;
+  S->res.out_r1 = paired ? S->out_r1.p : NULL;
+  S->res.out_r2_bytes = S->out_r2.n;
+  S->res.out_r1_bytes = S->out_r1.n;
+  S->res.seg_off_r2 = S->off2;
+  S->res.seg_len_r2 = S->len2;
+  S->res.seg_off_r1 = S->off1;
+  S->res.seg_len_r1 = S->len1;
+  S->res.unassigned = S->unassigned;
+  S->res.n_unassigned = S->n_unassigned;
+  S->seq = seq;
+  S->order = c->submit_clock++;
+  S->state = 1;
   return MGK_OK;
 }
 
 int orc_collect(orc_ctx* c, mgk_result* res) {
-  if (!c->have_result) {
-    snprintf(c->err, sizeof c->err, "orc_collect: nothing submitted");
+  struct oslot* S = NULL;
+  for (int k = 0; k < c->n_slots; ++k)
+    if (c->slots[k].state == 1 && (!S || c->slots[k].order < S->order)) S = &c->slots[k];
+  if (!S) {
+    snprintf(c->err, sizeof c->err, "orc_collect: nothing in flight");
     return MGK_ERR_STATE;
   }
-  *res = c->res;
+  S->state = 2;
+  *res = S->res;
   return MGK_OK;
 }
 
 int orc_release(orc_ctx* c, uint64_t seq) {
-  if (!c->have_result || seq != c->seq) {
-    snprintf(c->err, sizeof c->err, "orc_release: unknown chunk");
-    return MGK_ERR_STATE;
-  }
-  c->have_result = 0;
-  return MGK_OK;
+  for (int k = 0; k < c->n_slots; ++k)
+    if (c->slots[k].state == 2 && c->slots[k].seq == seq) {
+      c->slots[k].state = 0;
+      return MGK_OK;
+    }
+  snprintf(c->err, sizeof c->err, "orc_release: unknown chunk");
+  return MGK_ERR_STATE;
 }
 
 int orc_counters(orc_ctx* c, uint64_t* stats, uint64_t* mism) {

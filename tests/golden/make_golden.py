@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/ from the reference (run in the build container only).
+
+ 1. copies the INPUT fixtures of the reference's demultiplex tests
+    (/root/reference/testing_data/input/*, sample sheets) so the GPU box, which
+    has no /root/reference, can replay them;
+ 2. records, per case of tests/ref_matrix.py, the digest of every file under
+    the reference's testing_data/expected (sha256 of the DECOMPRESSED text for
+    .gz — the comparison the reference's tests make — and of the raw bytes for
+    reports)  -> reference_matrix.json;
+ 3. runs the reference's own binary (oracle/_ref/mgikit, v2.2.0) on seeded
+    synthetic lanes shaped like BASELINE.json configs 2-5 and records the same
+    digests -> synthetic_reference.json.
+"""
+import dataclasses
+import hashlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import lanes  # noqa: E402
+import ref_matrix as M  # noqa: E402
+from mgikit_b200 import synth  # noqa: E402
+
+REF = "/root/reference/testing_data"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "mgikit")
+DST = os.path.join(HERE, "testing_data")
+
+
+def synthetic_variants():
+    small = dataclasses.replace(synth.CONFIG2, frac_random=0.5, frac_n=0.1, n_samples=8)
+    return [("cfg2", synth.CONFIG2, [], 20000), ("cfg3", synth.CONFIG3, [], 20000), ("cfg4", synth.CONFIG4, [], 20000),
+            ("cfg5", synth.CONFIG5, [], 20000), ("cfg2-mgi", synth.CONFIG2, ["--disable-illumina"], 5000),
+            ("cfg3-fullhdr", synth.CONFIG3, ["--disable-illumina", "--mgi-full-header"], 5000),
+            ("cfg2-keep", synth.CONFIG2, ["--keep-barcode"], 5000),
+            ("cfg3-perindex", synth.CONFIG3, ["--per-index-error"], 5000),
+            ("cfg2-report1", synth.CONFIG2, ["--report-level", "1"], 5000),
+            ("cfg2-noisy", small, ["--report-limit", "7"], 5000)]
+
+
+def main():
+    cases = M.all_cases()
+    needed = set()
+    for c in cases:
+        it = iter(c.args)
+        for a in it:
+            if a in M.PATH_FLAGS:
+                v = next(it)
+                if v:
+                    needed.add(v)
+    if os.path.isdir(DST):
+        shutil.rmtree(DST)
+    for rel in sorted(needed):
+        src = os.path.join(REF, rel)
+        if os.path.isdir(src):
+            for name in os.listdir(src):
+                os.makedirs(os.path.join(DST, rel), exist_ok=True)
+                shutil.copy(os.path.join(src, name), os.path.join(DST, rel, name))
+        else:
+            os.makedirs(os.path.dirname(os.path.join(DST, rel)), exist_ok=True)
+            shutil.copy(src, os.path.join(DST, rel))
+    matrix = {}
+    for c in cases:
+        entry = {"files": M.expected_listing(c, REF)}
+        if c.stats_override:
+            with open(os.path.join(REF, "expected", c.stats_override), "rb") as f:
+                entry["stats_override"] = hashlib.sha256(f.read()).hexdigest()
+        matrix[c.name] = entry
+    with open(os.path.join(HERE, "reference_matrix.json"), "w") as f:
+        json.dump(matrix, f, indent=0, sort_keys=True)
+
+    syn = {}
+    for name, lane, extra, n in synthetic_variants():
+        d = tempfile.mkdtemp(prefix="golden_")
+        r1, r2, sheet = lanes.write_lane(lane, n, d)
+        out = os.path.join(d, "out")
+        lanes.run_binary(REF_BIN, lanes.demux_args(lane, r1, r2, sheet, out, extra))
+        inputs = {}
+        for p in (r1, r2):
+            if p:
+                import gzip
+                with gzip.open(p, "rb") as f:
+                    inputs[os.path.basename(p)] = hashlib.sha256(f.read()).hexdigest()
+        syn[name] = {"n_pairs": n, "extra": extra, "inputs": inputs, "files": lanes.digest_dir(out)}
+        shutil.rmtree(d)
+    with open(os.path.join(HERE, "synthetic_reference.json"), "w") as f:
+        json.dump(syn, f, indent=0, sort_keys=True)
+    print(f"{len(matrix)} fixture cases, {len(syn)} synthetic lanes")
+
+
+if __name__ == "__main__":
+    main()
