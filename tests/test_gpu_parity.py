@@ -123,7 +123,7 @@ def test_full_size_properties(gpu_lib):
     und = spec_total - 2
     seg = res.segment(1, und)
     heads = [l for l in seg.split(b"\n")[0::4] if l]
-    nums = [int(h[19:27]) for h in heads]
+    nums = [int(h[21:29]) for h in heads]
     assert nums == sorted(nums) and len(set(nums)) == len(nums)
     seg0 = res.segment(1, 0)
     ids = [int(l.split(b":")[4]) for l in seg0.split(b"\n")[0::4] if l]
