@@ -47,7 +47,7 @@ oracle/_ref/mgikit_oracle: oracle/oracle_cli.cpp oracle/_ref/mgikit_oracle.o $(H
 	$(CXX) $(CXXFLAGS) -o $@ oracle/oracle_cli.cpp $(HOST_SRC) oracle/_ref/mgikit_oracle.o -lz
 
 # CPU emulation of the device logic (tests only): device_logic.cuh compiled by g++
-EMU_DEP := tests/emu/emu.cpp mgikit_b200/csrc/gpu/device_logic.cuh mgikit_b200/csrc/gpu/params_build.hpp include/mgikit_gpu.h
+EMU_DEP := tests/emu/emu.cpp mgikit_b200/csrc/gpu/device_logic.cuh mgikit_b200/csrc/gpu/emit_logic.cuh mgikit_b200/csrc/gpu/params_build.hpp include/mgikit_gpu.h
 oracle/_ref/libemu.so: $(EMU_DEP)
 	@mkdir -p oracle/_ref
 	$(CXX) $(CXXFLAGS) -shared -o $@ tests/emu/emu.cpp

@@ -19,7 +19,7 @@
 
 #include <cuda_runtime.h>
 
-#include "device_logic.cuh"
+#include "emit_logic.cuh"
 
 namespace mgk {
 
@@ -33,7 +33,9 @@ enum : uint32_t {
   ERR_NL_CAPACITY = 1u,    // more newlines than the record table holds
   ERR_REC_CAPACITY = 2u,   // more records than max_chunk_records
   ERR_OUT_CAPACITY = 4u,   // output larger than the output buffer
-  ERR_PANIC = 8u           // a read hit the reference's stale-dictionary panic
+  ERR_PANIC = 8u,          // a read hit the reference's stale-dictionary panic
+  ERR_REC_TOO_LONG = 16u,  // one read pair does not fit a shared-memory stage
+  ERR_HDR_TOO_LONG = 32u   // a rewritten header exceeds HDR_STAGE_MAX bytes
 };
 
 struct __align__(16) RecMeta {
@@ -62,7 +64,8 @@ struct ChunkDev {
   uint32_t* tickets;           // [2] dynamic tile ids
   uint32_t* counts;            // [2] newline totals
   RecMeta* meta;
-  uint32_t* tile_bins;         // [tiles][2*total]: bytes, then absolute offsets
+  uint32_t* tile_bins;         // [tiles][bins_stride]: bytes, then absolute offsets (rows 16-byte aligned)
+  uint32_t bins_stride, pad0;
   uint32_t* group_sums;        // [groups][2*total]
   unsigned long long* seg;     // [4][total]: off2, len2, off1, len1
   uint8_t* out2;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __res
       __syncthreads();
     }
     if (active) c.meta[rec] = mt;
-    uint32_t* row = c.tile_bins + (size_t)tile * B2;
+    uint32_t* row = c.tile_bins + (size_t)tile * c.bins_stride;
     for (int i = threadIdx.x; i < B2; i += blockDim.x) row[i] = bin_acc[i];
   }
 }
@@ -370,7 +373,7 @@ __global__ void k_scan_groups(const Params* __restrict__ Pg, ChunkDev c) {
   const uint32_t t0 = g * GROUP_TILES, t1 = min(n_tiles, t0 + GROUP_TILES);
   uint32_t sum = 0;
 #pragma unroll 8
-  for (uint32_t t = t0; t < t1; ++t) sum += c.tile_bins[(size_t)t * B2 + b];
+  for (uint32_t t = t0; t < t1; ++t) sum += c.tile_bins[(size_t)t * c.bins_stride + b];
   c.group_sums[(size_t)g * B2 + b] = sum;
 }
 
@@ -424,94 +427,262 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
   const uint32_t t0 = g * GROUP_TILES, t1 = min(n_tiles, t0 + GROUP_TILES);
   uint32_t run = c.group_sums[(size_t)g * B2 + b] + (uint32_t)c.seg[(b < (uint32_t)total ? 0 : 2) * total + (b % total)];
   for (uint32_t t = t0; t < t1; ++t) {
-    const uint32_t v = c.tile_bins[(size_t)t * B2 + b];
-    c.tile_bins[(size_t)t * B2 + b] = run;
+    const uint32_t v = c.tile_bins[(size_t)t * c.bins_stride + b];
+    c.tile_bins[(size_t)t * c.bins_stride + b] = run;
     run += v;
   }
 }
 
 // ------------------------------------------------------------------ K4
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+// Persistent, one CTA per SM.  Each CTA owns a contiguous run of plan tiles and
+// streams its records through two shared-memory stages: while the warps emit
+// the records of stage s, the TMA engine (cp.async.bulk, completion on an
+// mbarrier) fills stage s^1 with the next tile's bytes of both reads, its
+// newline positions, its RecMeta rows and its row of bin offsets.  Every byte
+// of the input therefore crosses HBM->SM exactly once in this kernel, as
+// full-width bulk copies, and every output byte leaves as part of a 16-byte
+// store aligned on its destination (emit3, emit_logic.cuh).
+constexpr int EMIT_THREADS = 512;
+constexpr int EMIT_WARPS = EMIT_THREADS / 32;
+constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
+constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
 
-__global__ void __launch_bounds__(TILE_RECORDS) k_scatter(const Params* __restrict__ Pg, ChunkDev c) {
+struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 16-byte aligned
+  uint32_t consts;        // prefix + literals (+ slack)
+  uint32_t stats;         // [total][QC_SLOTS] u32
+  uint32_t hdr;           // [EMIT_WARPS][HDR_STAGE_BYTES]
+  uint32_t stage0, stage_stride;   // two stages, each: nl2 | nl1 | meta | bins | bytes
+  uint32_t nl1, meta, bins, bytes;   // offsets inside a stage (nl2 at 0)
+  uint32_t cap;           // bytes of text one stage holds (both reads)
+  uint32_t total_bytes;
+};
+
+struct StageDesc {
+  uint32_t n;             // records in the stage (0: no more tiles)
+  uint32_t r0;            // first record
+  uint32_t base2, base1;  // chunk offset of the first staged byte of either read (16-byte aligned)
+  uint32_t off1;          // where the paired read starts inside the stage's byte area
+  uint32_t pad[3];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map): 16-byte aligned both sides, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WarpDev {
+  int lane;
+  template <class F> __device__ __forceinline__ void each(F f) const { f(lane); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <class F> __device__ __forceinline__ uint32_t ballot(F f) const { return __ballot_sync(0xffffffffu, f(lane)); }
+  template <class F> __device__ __forceinline__ uint32_t sum(F f) const { return __reduce_add_sync(0xffffffffu, (uint32_t)f(lane)); }
+  template <class F> __device__ __forceinline__ U4 sum4(F f) const {
+    const U4 v = f(lane);
+    U4 r;
+    r.a = __reduce_add_sync(0xffffffffu, v.a);
+    r.b = __reduce_add_sync(0xffffffffu, v.b);
+    r.c = __reduce_add_sync(0xffffffffu, v.c);
+    r.d = __reduce_add_sync(0xffffffffu, v.d);
+    return r;
+  }
+  template <class F> __device__ __forceinline__ int min(F f) const { return __reduce_min_sync(0xffffffffu, (int)f(lane)); }
+};
+
+__global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restrict__ Pg, ChunkDev c, EmitLayout lay) {
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Params P;
-  copy_params_to_smem(&P, Pg);
-  __syncthreads();
-  const int total = P.total, B2 = 2 * total;
-  const uint32_t n_rec = device_n_records(c, P);
-  const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t BL = (uint32_t)P.BL, wbl = P.keep_barcode ? 0u : BL;
-  if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY)) return;  // nothing safe to write
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ StageDesc s_desc[2];
+  __shared__ uint32_t s_claim[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t* tb = c.tile_bins + (size_t)tile * B2;
-    const uint32_t rec0 = tile * TILE_RECORDS + warp * 32;
-    for (uint32_t r = 0; r < 32; ++r) {
-      const uint32_t rec = rec0 + r;
-      if (rec >= n_rec) break;
-      const RecMeta mt = c.meta[rec];
-      if (mt.flags & 1) continue;  // layout error: reported through status, nothing emitted
-      const RecGeom G = load_geom(c, P, rec);
-      const int sample = mt.sample, bin = mt.bin;
-      const RecPlan pl = record_plan(P, c.r2, G, sample, mt.bar_t, mt.umi_t);
-      uint8_t* d2 = c.out2 + tb[bin] + mt.off2;
-      uint8_t* d1 = P.paired ? c.out1 + tb[total + bin] + mt.off1 : nullptr;
-      if (!pl.matched) {
-        copy_span(d2, c.r2 + G.h2, G.e2 + 1u - G.h2, lane, 32);
-        if (P.paired) copy_span(d1, c.r1 + G.h1, G.e1 + 1u - G.h1, lane, 32);
-      } else {
-        const bool rewrite = P.out_mode != MGK_OUT_MGI;
-        if (P.read2_has_sequence) {
-          uint32_t n = 0;
-          if (rewrite) {
-            SegList s;
-            header_segments(P, c.r2, c.r1, G, pl, mt.bar_t, mt.umi_t, 2, s);
-            n = emit_segments(d2, s, lane, 32);
-          }
-          const uint32_t a0 = rewrite ? G.s2 - 1u : G.h2;         // src/lib.rs:1293 / unchanged header_start
-          const uint32_t na = G.p2 - wbl - 1u - a0;               // :1321-1323
-          copy_span(d2 + n, c.r2 + a0, na, lane, 32);
-          const uint32_t nb = G.e2 - wbl - (G.p2 - 1u);           // :1324-1326
-          copy_span(d2 + n + na, c.r2 + G.p2 - 1u, nb, lane, 32);
-          if (lane == 0) d2[n + na + nb] = '\n';                  // :1327
-        }
-        if (P.paired) {
-          uint32_t n = 0;
-          if (rewrite) {
-            SegList s;
-            header_segments(P, c.r2, c.r1, G, pl, mt.bar_t, mt.umi_t, 1, s);
-            n = emit_segments(d1, s, lane, 32);
-          }
-          const uint32_t a0 = rewrite ? G.s1 - 1u : G.h1;
-          copy_span(d1 + n, c.r1 + a0, G.e1 + 1u - a0, lane, 32);  // :1328-1331
-        }
-      }
-      if (P.report_level > 0) {  // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
-        Qc qa, qb, qc;
-        qa.sum = qa.high = 0;
-        if (P.paired) qa = qc_partial(c.r1 + G.q1, G.e1 - G.q1, lane, 32);
-        qb = qc_partial(c.r2 + G.e2 - BL, BL, lane, 32);
-        qc = qc_partial(c.r2 + G.q2, G.e2 - BL - G.q2, lane, 32);
-        const uint32_t v0 = warp_sum(qa.high), v1 = warp_sum(qa.sum), v2 = warp_sum(qb.high), v3 = warp_sum(qb.sum),
-                       v4 = warp_sum(qc.high), v5 = warp_sum(qc.sum);
-        const int shift = P.paired ? 1 : 0;
-        unsigned long long* st = c.stats + (size_t)sample * MGK_N_STATS;
-        if (lane == 0 && P.paired) atomicAdd(st + 0, (unsigned long long)v0);
-        if (lane == 1 && P.paired) atomicAdd(st + 6, (unsigned long long)v1);
-        if (lane == 2) atomicAdd(st + 2, (unsigned long long)v2);
-        if (lane == 3) atomicAdd(st + 8, (unsigned long long)v3);
-        if (lane == 4) atomicAdd(st + shift, (unsigned long long)v4);
-        if (lane == 5) atomicAdd(st + 6 + shift, (unsigned long long)v5);
-      }
-      if (P.validate) {
-        int v = validate_partial(P, c.r2, c.r1, G, lane, 32);
-        v = v ? v : 15;
-        v = __reduce_min_sync(0xffffffffu, v);
-        if (v != 15 && lane == 0) atomicMin(&c.status->validate_key, ((unsigned long long)rec << 4) | (unsigned)v);
+  copy_params_to_smem(&P, Pg);
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int total = P.total, paired = P.paired;
+  {  // constants and QC accumulators
+    const uint32_t nconst = (uint32_t)P.prefix_len + LIT_BYTES;
+    for (uint32_t i = tid; i < nconst; i += EMIT_THREADS) smem[lay.consts + i] = P.consts[i];
+    uint32_t* st = reinterpret_cast<uint32_t*>(smem + lay.stats);
+    for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) st[i] = 0;
+  }
+  const uint32_t n_rec = device_n_records(c, P);
+  if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY)) return;  // nothing safe to write
+  // this CTA's run of plan tiles
+  const uint32_t n_pt = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t pt0 = (uint32_t)(((unsigned long long)n_pt * blockIdx.x) / gridDim.x);
+  const uint32_t pt1 = (uint32_t)(((unsigned long long)n_pt * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t R0 = pt0 * TILE_RECORDS, R1 = min(pt1 * TILE_RECORDS, n_rec);
+  if (R0 >= R1) return;
+  const uint32_t bins_stride = (2u * (uint32_t)total + 3u) & ~3u;
+
+  // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are halved below)
+  uint32_t n_tile;
+  {
+    const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
+    const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
+    n_tile = (lay.cap - 192u) / (mean + mean / 32u + 1u);
+    n_tile = max(1u, min(n_tile, (uint32_t)EMIT_NMAX));
+  }
+
+  // producer state (warp 0, lane 0)
+  uint32_t next_rec = R0, start2 = 0, start1 = 0;
+  if (warp == 0 && lane == 0) {
+    start2 = c.nl2[(long long)4 * R0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
+    start1 = paired ? c.nl1[(long long)4 * R0 - 1] + 1u : 0u;
+  }
+  auto produce = [&](int s) {   // lane 0 of warp 0
+    StageDesc& d = s_desc[s];
+    if (next_rec >= R1) {
+      d.n = 0;
+      return;
+    }
+    const uint32_t r0 = next_rec;
+    uint32_t lim = min(min(r0 + n_tile, R1), (r0 / TILE_RECORDS + 1u) * TILE_RECORDS);
+    const uint32_t base2 = start2 & ~15u, base1 = start1 & ~15u;
+    uint32_t e2, e1, len2, len1, off1;
+    for (;;) {
+      e2 = c.nl2[4u * lim - 1u] + 1u;
+      e1 = paired ? c.nl1[4u * lim - 1u] + 1u : 0u;
+      len2 = ((e2 + 15u) & ~15u) - base2;
+      len1 = paired ? ((e1 + 15u) & ~15u) - base1 : 0u;
+      off1 = (len2 + 127u) & ~127u;
+      if (off1 + len1 + 32u <= lay.cap || lim == r0 + 1u) break;
+      lim = r0 + (lim - r0) / 2u;
+    }
+    if (off1 + len1 + 32u > lay.cap) {   // one read pair larger than a stage
+      atomicOr(&c.status->error, ERR_REC_TOO_LONG);
+      d.n = 0;
+      next_rec = R1;
+      return;
+    }
+    const uint32_t n = lim - r0;
+    d.n = n;
+    d.r0 = r0;
+    d.base2 = base2;
+    d.base1 = base1;
+    d.off1 = off1;
+    s_claim[s] = 0;
+    unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
+    const uint32_t nl_bytes = 16u * (n + 1u), meta_bytes = 16u * n, bins_bytes = 4u * bins_stride;
+    mbar_expect_tx(&s_bar[s], len2 + len1 + (paired ? 2u : 1u) * nl_bytes + meta_bytes + bins_bytes);
+    bulk_g2s(st + lay.bytes, c.r2 + base2, len2, &s_bar[s]);
+    if (paired) bulk_g2s(st + lay.bytes + off1, c.r1 + base1, len1, &s_bar[s]);
+    bulk_g2s(st, c.nl2 + ((long long)4 * r0 - 4), nl_bytes, &s_bar[s]);
+    if (paired) bulk_g2s(st + lay.nl1, c.nl1 + ((long long)4 * r0 - 4), nl_bytes, &s_bar[s]);
+    bulk_g2s(st + lay.meta, c.meta + r0, meta_bytes, &s_bar[s]);
+    bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / TILE_RECORDS) * bins_stride, bins_bytes, &s_bar[s]);
+    next_rec = lim;
+    start2 = e2;
+    start1 = e1;
+  };
+  if (warp == 0 && lane == 0) produce(0);
+  __syncthreads();
+
+  const WarpDev w{lane};
+  const uint32_t hs = lay.hdr + (uint32_t)warp * HDR_STAGE_BYTES;
+  uint32_t* s_stats = reinterpret_cast<uint32_t*>(smem + lay.stats);
+  auto flush_stats = [&]() {   // all threads; s_stats quiescent
+    for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) {
+      const uint32_t v = s_stats[i];
+      if (v) {
+        const int k = i % QC_SLOTS;
+        atomicAdd(c.stats + (size_t)(i / QC_SLOTS) * MGK_N_STATS + qc_stat_column(k, paired), (unsigned long long)v);
+        s_stats[i] = 0;
       }
     }
+  };
+
+  for (uint32_t k = 0;; ++k) {
+    const int s = (int)(k & 1u);
+    if (warp == 0 && lane == 0) produce(s ^ 1);
+    const StageDesc d = s_desc[s];
+    if (d.n == 0) break;
+    mbar_wait(&s_bar[s], (k >> 1) & 1u);
+    unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
+    const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
+    const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
+    const RecMeta* metas = reinterpret_cast<const RecMeta*>(st + lay.meta);
+    const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
+    // S offsets of chunk byte 0 of either read
+    const uint32_t o2 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes - d.base2;
+    const uint32_t o1 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes + d.off1 - d.base1;
+    for (;;) {
+      uint32_t i = 0;
+      if (lane == 0) i = atomicAdd(&s_claim[s], 1u);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= d.n) break;
+      const RecMeta mt = metas[i];
+      if (mt.flags & 1) continue;   // layout error: reported through status, nothing emitted
+      RecGeom G;
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
+        G.h2 = nl2s[4u * i + 3u] + 1u + o2;
+        G.s2 = a.x + 1u + o2;
+        G.p2 = a.y + 1u + o2;
+        G.q2 = a.z + 1u + o2;
+        G.e2 = a.w + o2;
+        G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
+        if (paired) {
+          const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
+          G.h1 = nl1s[4u * i + 3u] + 1u + o1;
+          G.s1 = b.x + 1u + o1;
+          G.p1 = b.y + 1u + o1;
+          G.q1 = b.z + 1u + o1;
+          G.e1 = b.w + o1;
+        }
+      }
+      const int sample = mt.sample, bin = mt.bin;
+      uint8_t* d2 = c.out2 + bins[bin] + mt.off2;
+      uint8_t* d1 = paired ? c.out1 + bins[total + bin] + mt.off1 : nullptr;
+      const PairOut po = emit_pair(w, P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, d2, d1);
+      if (po.hdr_overflow) {
+        if (lane == 0) atomicOr(&c.status->error, ERR_HDR_TOO_LONG);
+        continue;
+      }
+      if (P.report_level > 0 && lane < QC_SLOTS) {
+        uint32_t v = po.qc.v[0];
+#pragma unroll
+        for (int q = 1; q < QC_SLOTS; ++q) v = lane == q ? po.qc.v[q] : v;
+        if (v) atomicAdd(&s_stats[sample * QC_SLOTS + lane], v);
+      }
+      if (P.validate && po.validate && lane == 0)
+        atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)po.validate);
+    }
+    __syncthreads();   // stage s is free again; desc[s^1] is published
+    if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {
+      flush_stats();
+      __syncthreads();
+    }
   }
+  __syncthreads();
+  if (P.report_level > 0) flush_stats();
 }
 
 // ------------------------------------------------------------------ stage kernels (parity tests)

@@ -61,7 +61,9 @@ struct mgk_ctx {
   uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
   uint32_t scan_tiles_max = 0, tiles_max = 0, groups_max = 0;
   size_t match_smem = 0;
-  int grid_match = 0, grid_scatter = 0, n_sm = 0;
+  int grid_match = 0, grid_emit = 0, n_sm = 0;
+  uint32_t bins_stride = 0;
+  EmitLayout lay{};
   std::vector<Slot> slots;
   std::deque<int> fifo;     // submitted slots, oldest first
   uint64_t launches = 0;
@@ -256,11 +258,44 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   if (ctx->match_smem > 200 * 1024) BAD("mgk_create: index tables (%zu B) do not fit the shared-memory staging area", ctx->match_smem);
   CUC(cudaFuncSetAttribute(k_match_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
   CUC(cudaFuncSetAttribute(k_match_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
-  int occ_m = 1, occ_s = 1;
+  int occ_m = 1;
   CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, k_match_plan, TILE_RECORDS, ctx->match_smem));
-  CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_scatter, TILE_RECORDS, 0));
   ctx->grid_match = ctx->n_sm * (occ_m > 0 ? occ_m : 1);
-  ctx->grid_scatter = ctx->n_sm * (occ_s > 0 ? occ_s : 1);
+  ctx->bins_stride = (2u * (uint32_t)P.total + 3u) & ~3u;
+  {  // shared-memory plan of the emit kernel: everything that is not a stage is fixed, the two stages share the rest
+    cudaFuncAttributes fa;
+    CUC(cudaFuncGetAttributes(&fa, k_emit));
+    int max_optin = 0;
+    CUC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    auto up = [](uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; };
+    EmitLayout& L = ctx->lay;
+    uint32_t at = 0;
+    L.consts = at;
+    at += up((uint32_t)P.prefix_len + LIT_BYTES + 48u, 16u);
+    L.stats = at;
+    at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
+    at += 32u;                                   // slack in front of the header staging areas (gather16 reads around them)
+    L.hdr = at;
+    at += EMIT_WARPS * HDR_STAGE_BYTES + 32u;
+    at = up(at, 128u);
+    const uint32_t nl_bytes = 16u * (EMIT_NMAX + 1u);
+    L.nl1 = up(nl_bytes, 16u);
+    L.meta = L.nl1 + up(nl_bytes, 16u);
+    L.bins = L.meta + 16u * EMIT_NMAX;
+    L.bytes = up(L.bins + 4u * ctx->bins_stride + 16u, 128u);
+    const int64_t avail = (int64_t)max_optin - (int64_t)fa.sharedSizeBytes - (int64_t)at - 256;
+    const int64_t cap = (avail / 2 - (int64_t)L.bytes) / 128 * 128;
+    if (cap < 4096) BAD("mgk_create: %d samples leave no shared memory for the record stages", P.S);
+    L.cap = (uint32_t)cap;
+    L.stage0 = at;
+    L.stage_stride = L.bytes + L.cap;
+    L.total_bytes = L.stage0 + 2u * L.stage_stride;
+    CUC(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
+    int occ_e = 0;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_emit, EMIT_THREADS, L.total_bytes));
+    if (occ_e < 1) BAD("mgk_create: the emit kernel does not fit an SM (%u bytes of shared memory)", L.total_bytes);
+    ctx->grid_emit = ctx->n_sm;
+  }
 
   CUC(cudaEventCreate(&ctx->span_begin));
   CUC(cudaEventCreate(&ctx->span_end));
@@ -272,6 +307,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   const int n_slots = cfg->n_slots < 1 ? 1 : (cfg->n_slots > 8 ? 8 : cfg->n_slots);
   ctx->slots.resize((size_t)n_slots);
   const size_t B2 = (size_t)2 * P.total;
+  const uint32_t nl_sentinel[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
   for (auto& s : ctx->slots) {
     CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (auto& e : s.ev) CUC(cudaEventCreate(&e));
@@ -280,13 +316,19 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     if (P.paired) CUC(dalloc(&s.d_r1, ctx->cap_bytes + 256));
     CUC(dalloc(&s.out2, ctx->out_cap + 256));
     if (P.paired) CUC(dalloc(&s.out1, ctx->out_cap + 256));
-    CUC(dalloc(&s.nl2, ctx->cap_records * 4 + 8));
-    if (P.paired) CUC(dalloc(&s.nl1, ctx->cap_records * 4 + 8));
+    // newline tables: 4 sentinel entries (-1: "a newline just before byte 0") in front of entry 0, so that
+    // record r's previous newline is always nl[4r-1] and the rows stay 16-byte aligned for the bulk copies
+    CUC(dalloc(&s.nl2, ctx->cap_records * 4 + 16));
+    CUC(cudaMemcpy(s.nl2, nl_sentinel, sizeof nl_sentinel, cudaMemcpyHostToDevice));
+    if (P.paired) {
+      CUC(dalloc(&s.nl1, ctx->cap_records * 4 + 16));
+      CUC(cudaMemcpy(s.nl1, nl_sentinel, sizeof nl_sentinel, cudaMemcpyHostToDevice));
+    }
     CUC(dalloc(&s.look2, (size_t)ctx->scan_tiles_max));
     CUC(dalloc(&s.look1, (size_t)ctx->scan_tiles_max));
     CUC(dalloc(&s.ctrl, 8));
     CUC(dalloc(&s.meta, ctx->cap_records + 1));
-    CUC(dalloc(&s.tile_bins, (size_t)ctx->tiles_max * B2));
+    CUC(dalloc(&s.tile_bins, (size_t)ctx->tiles_max * ctx->bins_stride));
     CUC(dalloc(&s.group_sums, (size_t)ctx->groups_max * B2));
     CUC(dalloc(&s.seg, (size_t)4 * P.total));
     CUC(dalloc(&s.unassigned, ctx->cap_records + 1));
@@ -298,7 +340,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     CUC(cudaHostAlloc(reinterpret_cast<void**>(&s.h_unassigned), (ctx->cap_records + 1) * 4, cudaHostAllocDefault));
     s.off2.resize((size_t)P.total); s.len2v.resize((size_t)P.total); s.off1.resize((size_t)P.total); s.len1v.resize((size_t)P.total);
     ChunkDev& c = s.cd;
-    c.nl2 = s.nl2; c.nl1 = s.nl1;
+    c.nl2 = s.nl2 + 4; c.nl1 = s.nl1 ? s.nl1 + 4 : nullptr;
+    c.bins_stride = ctx->bins_stride;
     c.nl_cap = (uint32_t)(ctx->cap_records * 4 + 4);
     c.max_records = (uint32_t)ctx->cap_records;
     c.look2 = s.look2; c.look1 = s.look1;
@@ -384,7 +427,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   k_scan_bins<<<1, 1024, 0, st>>>(ctx->d_params, c);
   k_scan_tiles<<<(scan_threads + 255) / 256, 256, 0, st>>>(ctx->d_params, c);
   CU(cudaEventRecord(s.ev[4], st));
-  k_scatter<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_scatter), TILE_RECORDS, 0, st>>>(ctx->d_params, c);
+  k_emit<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_emit), EMIT_THREADS, ctx->lay.total_bytes, st>>>(ctx->d_params, c, ctx->lay);
   ctx->launches += 5;
   CU(cudaEventRecord(s.ev[5], st));
   CU(cudaEventRecord(ctx->span_end, st));
@@ -418,6 +461,10 @@ extern "C" int mgk_collect(mgk_ctx* ctx, mgk_result* res) {
     return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu holds more records than max_chunk_records = %llu", (unsigned long long)s.seq,
                 (unsigned long long)ctx->cap_records);
   if (hs.error & ERR_OUT_CAPACITY) return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: output does not fit the output buffer", (unsigned long long)s.seq);
+  if (hs.error & ERR_REC_TOO_LONG)
+    return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: a read pair is longer than the %u bytes one shared-memory stage holds", (unsigned long long)s.seq, ctx->lay.cap);
+  if (hs.error & ERR_HDR_TOO_LONG)
+    return fail(ctx, MGK_ERR_FORMAT, "chunk %llu: a rewritten read header is longer than %u bytes", (unsigned long long)s.seq, HDR_STAGE_MAX);
   if (hs.fmt_record != ~0ull)
     return fail(ctx, MGK_ERR_FORMAT, "chunk %llu, read %llu: lines shorter than the barcode/header layout", (unsigned long long)s.seq, hs.fmt_record);
   const int total = P.total;

@@ -10,9 +10,24 @@
 #include <string>
 #include <vector>
 
+#include "../../mgikit_b200/csrc/gpu/emit_logic.cuh"
 #include "../../mgikit_b200/csrc/gpu/params_build.hpp"
 
 using namespace mgk;
+
+// the 32 lanes of a warp, looped
+struct WarpEmu {
+  template <class F> void each(F f) const { for (int l = 0; l < 32; ++l) f(l); }
+  void sync() const {}
+  template <class F> uint32_t ballot(F f) const { uint32_t m = 0; for (int l = 0; l < 32; ++l) m |= (f(l) ? 1u : 0u) << l; return m; }
+  template <class F> uint32_t sum(F f) const { uint32_t s = 0; for (int l = 0; l < 32; ++l) s += (uint32_t)f(l); return s; }
+  template <class F> U4 sum4(F f) const {
+    U4 s{0, 0, 0, 0};
+    for (int l = 0; l < 32; ++l) { const U4 v = f(l); s.a += v.a; s.b += v.b; s.c += v.c; s.d += v.d; }
+    return s;
+  }
+  template <class F> int min(F f) const { int m = 0x7fffffff; for (int l = 0; l < 32; ++l) { const int v = f(l); if (v < m) m = v; } return m; }
+};
 
 struct emu_ctx {
   Params P;
@@ -125,69 +140,41 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   uint8_t* o2 = c->out2.data();
   uint8_t* o1 = c->out1.data();
   memset(&c->res, 0, sizeof c->res);
-  const uint32_t BL = (uint32_t)P.BL, wbl = P.keep_barcode ? 0u : BL;
+  // the staged tile: the whole chunk as ONE tile, laid out like the kernel's shared memory
+  //   [slack | prefix + literals | header staging | barcode read bytes | paired read bytes | slack]
+  const uint32_t cs0 = 64;
+  const uint32_t hs = (cs0 + (uint32_t)c->tb.consts.size() + 31u) / 16u * 16u + 16u;
+  const uint32_t b2 = hs + HDR_STAGE_BYTES + 16u;
+  const uint32_t b1 = (b2 + (uint32_t)r2_len + 15u) / 16u * 16u + 16u + (uint32_t)(seq % 3) * 16u;
+  const size_t s_bytes = (size_t)b1 + r1_len + 128;
+  uint8_t* S = (uint8_t*)aligned_alloc(64, (s_bytes + 63) / 64 * 64);
+  memset(S, 0x5a, s_bytes);
+  memcpy(S + cs0, c->tb.consts.data(), c->tb.consts.size());
+  memcpy(S + b2, r2, r2_len);
+  if (r1_len) memcpy(S + b1, r1, r1_len);
+  const WarpEmu w;
   unsigned long long vkey = ~0ull;
   for (uint32_t i = 0; i < n_rec; ++i) {
     const Rec& R = recs[i];
-    const RecGeom& G = R.G;
-    const RecPlan pl = record_plan(P, r2, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t);
+    RecGeom G = R.G;   // into S offsets
+    G.h2 += b2; G.s2 += b2; G.p2 += b2; G.q2 += b2; G.e2 += b2;
+    G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
     uint8_t* d2 = o2 + c->off2[(size_t)R.bin] + R.d2;
     uint8_t* d1 = o1 + c->off1[(size_t)R.bin] + R.d1;
-    Qc qa{0, 0}, qb{0, 0}, qc{0, 0};
-    int vworst = 0;
-    for (int lane = 0; lane < 32; ++lane) {  // one warp, lanes looped
-      if (!pl.matched) {
-        copy_span(d2, r2 + G.h2, G.e2 + 1u - G.h2, lane, 32);
-        if (P.paired) copy_span(d1, r1 + G.h1, G.e1 + 1u - G.h1, lane, 32);
-      } else {
-        const bool rewrite = P.out_mode != MGK_OUT_MGI;
-        if (P.read2_has_sequence) {
-          uint32_t n = 0;
-          if (rewrite) {
-            SegList s;
-            header_segments(P, r2, r1, G, pl, R.mo.bar_t, R.mo.umi_t, 2, s);
-            n = emit_segments(d2, s, lane, 32);
-          }
-          const uint32_t a0 = rewrite ? G.s2 - 1u : G.h2;
-          const uint32_t na = G.p2 - wbl - 1u - a0;
-          copy_span(d2 + n, r2 + a0, na, lane, 32);
-          const uint32_t nb = G.e2 - wbl - (G.p2 - 1u);
-          copy_span(d2 + n + na, r2 + G.p2 - 1u, nb, lane, 32);
-          if (lane == 0) d2[n + na + nb] = '\n';
-        }
-        if (P.paired) {
-          uint32_t n = 0;
-          if (rewrite) {
-            SegList s;
-            header_segments(P, r2, r1, G, pl, R.mo.bar_t, R.mo.umi_t, 1, s);
-            n = emit_segments(d1, s, lane, 32);
-          }
-          const uint32_t a0 = rewrite ? G.s1 - 1u : G.h1;
-          copy_span(d1 + n, r1 + a0, G.e1 + 1u - a0, lane, 32);
-        }
-      }
-      if (P.report_level > 0) {
-        if (P.paired) { Qc q = qc_partial(r1 + G.q1, G.e1 - G.q1, lane, 32); qa.sum += q.sum; qa.high += q.high; }
-        { Qc q = qc_partial(r2 + G.e2 - BL, BL, lane, 32); qb.sum += q.sum; qb.high += q.high; }
-        { Qc q = qc_partial(r2 + G.q2, G.e2 - BL - G.q2, lane, 32); qc.sum += q.sum; qc.high += q.high; }
-      }
-      if (P.validate) {
-        const int v = validate_partial(P, r2, r1, G, lane, 32);
-        if (v && (vworst == 0 || v < vworst)) vworst = v;
-      }
-    }
+    const PairOut po = emit_pair(w, P, S, hs, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, d1);
+    if (po.hdr_overflow) { rc = MGK_ERR_FORMAT; c->err = "header too long"; break; }
     if (P.report_level > 0) {
       uint64_t* st = c->stats.data() + (size_t)R.mo.sample * MGK_N_STATS;
-      const int shift = P.paired ? 1 : 0;
-      if (P.paired) { st[0] += qa.high; st[6] += qa.sum; }
-      st[2] += qb.high; st[8] += qb.sum;
-      st[shift] += qc.high; st[6 + shift] += qc.sum;
+      for (int k = 0; k < QC_SLOTS; ++k)
+        if (P.paired || k >= 2) st[qc_stat_column(k, P.paired)] += po.qc.v[k];
     }
-    if (vworst) {
-      const unsigned long long k = ((unsigned long long)i << 4) | (unsigned)vworst;
+    if (po.validate) {
+      const unsigned long long k = ((unsigned long long)i << 4) | (unsigned)po.validate;
       if (k < vkey) vkey = k;
     }
   }
+  free(S);
+  if (rc != MGK_OK) { free(r2); free(r1); return rc; }
   free(r2);
   free(r1);
   c->res.seq = seq;
