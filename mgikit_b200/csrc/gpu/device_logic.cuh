@@ -33,6 +33,9 @@ MGK_HD uint4 ldg_v4(const uint4* p) { return __ldg(p); }
 struct uint4 {
   uint32_t x, y, z, w;
 };
+struct uint2 {
+  uint32_t x, y;
+};
 #endif
 MGK_HD int popc32(uint32_t x) { return __builtin_popcount(x); }
 MGK_HD int popc64(uint64_t x) { return __builtin_popcountll(x); }

@@ -3,14 +3,14 @@
 // fast byte array `S` (shared memory on the B200, a host array in the CPU
 // emulation that the `-m "not gpu"` tests check against the oracle).
 //
-// Everything is written against a tiny warp interface `W`:
-//     w.each(f)        run f(lane) for the 32 lanes          (device: this lane)
-//     w.sync()         order the lanes' writes to S          (device: __syncwarp)
-//     w.ballot(f)      bit l = f(l)                          (device: __ballot_sync)
-//     w.sum(f)         sum of f(l) over the lanes            (device: __reduce_add_sync)
-//     w.min(f)         min of f(l) over the lanes            (device: __reduce_min_sync)
-//     w.lane0(f)       run f() once
-// so that the byte-exact logic below is ONE piece of source for both targets.
+// ONE THREAD PER (record, role): the control-heavy part of a record (where the
+// header digits start, which bytes survive the trim) is scalar work, so every
+// lane of a warp carries a different record and runs the same straight-line
+// code; nothing here needs a warp collective, which is also why the CPU
+// emulation can call these functions as they are.
+//   role A  emit_read2()   barcode read: new header, trimmed sequence and qualities
+//   role B  emit_read1()   paired read: copy of the header, rest of the record verbatim
+//   role C  qc_pair() / validate_pair()
 //
 // What it restates (reference = /root/reference):
 //   write_illumina_header        src/sample_data.rs:569-654, call site src/lib.rs:1240-1293
@@ -89,204 +89,382 @@ MGK_HD void put_byte16(uint4& o, int i, uint32_t v) {
   o.w = put_byte(o.w, i - 12, v);
 }
 
-// ---------------------------------------------------------------- three-segment emit
+// ---------------------------------------------------------------- three-segment copy
 // An output record is the concatenation of up to three byte ranges of S
-// (rewritten header | sequence part | quality part) with at most one byte
-// overridden (the closing '\n' after a trimmed quality line, or the read-number
-// digit of the paired read's copy of the header).
+// (rewritten header | sequence part | quality part).
 struct Seg3 {
   uint32_t s0, n0, s1, n1, s2, n2;  // S offsets and lengths
-  uint32_t patch_at, patch_val;     // output index to override (>= len: none)
 };
 
-MGK_HD uint32_t seg3_len(const Seg3& g) { return g.n0 + g.n1 + g.n2; }
+MGK_HD void st_v4(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
-// Lane `lane` writes its share of dst[0..len).  The bulk moves as 16-byte stores
-// ALIGNED ON THE DESTINATION; each takes its bytes from the segment holding its
-// first byte and, where it straddles a boundary, merges in the next segment(s).
-// The < 16 bytes in front of the first aligned unit go one per lane (lanes 0-15),
-// those after the last unit likewise (lanes 16-31).
-MGK_HD void emit3(uint8_t* dst, const uint8_t* S, const Seg3& g, int lane) {
-  const uint32_t len = seg3_len(g);
+// lo, hi = two consecutive aligned vectors; the 16 bytes starting `sh` bytes into lo
+MGK_HD uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
+  const bool s2 = (sh & 8u) != 0u, s1 = (sh & 4u) != 0u;
+  const uint32_t t0 = s2 ? a.z : a.x, t1 = s2 ? a.w : a.y, t2 = s2 ? b.x : a.z, t3 = s2 ? b.y : a.w, t4 = s2 ? b.z : b.x,
+                 t5 = s2 ? b.w : b.y;
+  const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
+  const uint32_t bs = (sh & 3u) * 8u;
+  uint4 o;
+  o.x = funnel_r(u0, u1, bs);
+  o.y = funnel_r(u1, u2, bs);
+  o.z = funnel_r(u2, u3, bs);
+  o.w = funnel_r(u3, u4, bs);
+  return o;
+}
+
+// the LAST n (< 16) bytes of v go to [end - n, end), `end` 16-byte aligned: 8 + 4 + 2 + 1 ladder
+MGK_HD void store_before(uint8_t* end, const uint4& v, uint32_t n) {
+  uint32_t cur = v.w, prev = v.z;
+  uint8_t* p = end;
+  if (n & 8u) {
+    p -= 8;
+    uint2 t;
+    t.x = v.z;
+    t.y = v.w;
+    *reinterpret_cast<uint2*>(p) = t;
+    cur = v.y;
+    prev = v.x;
+  }
+  if (n & 4u) {
+    p -= 4;
+    *reinterpret_cast<uint32_t*>(p) = cur;
+    cur = prev;
+  }
+  if (n & 2u) {
+    p -= 2;
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)(cur >> 16);
+    cur <<= 16;
+  }
+  if (n & 1u) {
+    p -= 1;
+    *p = (uint8_t)(cur >> 24);
+  }
+}
+// the FIRST n (< 16) bytes of v go to [p, p + n), p 16-byte aligned
+MGK_HD void store_after(uint8_t* p, const uint4& v, uint32_t n) {
+  uint32_t c0 = v.x, c1 = v.y;
+  if (n & 8u) {
+    uint2 t;
+    t.x = v.x;
+    t.y = v.y;
+    *reinterpret_cast<uint2*>(p) = t;
+    p += 8;
+    c0 = v.z;
+    c1 = v.w;
+  }
+  if (n & 4u) {
+    *reinterpret_cast<uint32_t*>(p) = c0;
+    p += 4;
+    c0 = c1;
+  }
+  if (n & 2u) {
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)(c0 & 0xffffu);
+    p += 2;
+    c0 >>= 16;
+  }
+  if (n & 1u) *p = (uint8_t)(c0 & 0xffu);
+}
+
+// This thread writes dst[0 .. n0+n1+n2).  The bulk moves as 16-byte stores ALIGNED
+// ON THE DESTINATION; inside a segment the source is read as a sliding window of
+// aligned 16-byte vectors (one shared-memory load per store).  A unit that
+// straddles a segment boundary is assembled from both sides; the < 16 bytes in
+// front of the first / after the last aligned unit go out as an 8+4+2+1 ladder.
+MGK_HD void copy3(uint8_t* dst, const uint8_t* S, const Seg3& g) {
+  const uint32_t len = g.n0 + g.n1 + g.n2;
+  if (len == 0) return;
   const uint32_t o1 = g.n0, o2 = g.n0 + g.n1;
   const uint32_t b0 = g.s0, b1 = g.s1 - o1, b2 = g.s2 - o2;  // source offset of output byte y in segment j: bj + y
   uint32_t hb = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
   if (hb > len) hb = len;
   const uint32_t nfull = (len - hb) >> 4;
-  const uint32_t tail0 = hb + (nfull << 4);
-  {
-    const uint32_t y = lane < 16 ? (uint32_t)lane : tail0 + (uint32_t)(lane - 16);
-    const bool on = lane < 16 ? (uint32_t)lane < hb : y < len;
-    if (on) {
-      const uint32_t base = y >= o2 ? b2 : (y >= o1 ? b1 : b0);
-      uint32_t v = s_u8(S, base + y);
-      if (y == g.patch_at) v = g.patch_val;
-      dst[y] = (uint8_t)v;
+  const uint32_t tail0 = hb + (nfull << 4), nt = len - tail0;
+  // 16 output bytes starting at ANY output offset x (may hang over either end of the record)
+  auto unit_at = [&](uint32_t x) {
+    const uint32_t xe = x + 16u;
+    int j = ((int)x >= (int)o2 && g.n2) ? 2 : (((int)x >= (int)o1 && g.n1) ? 1 : 0);   // never an empty segment:
+    if (j == 0 && g.n0 == 0) j = g.n1 ? 1 : 2;                                            // its base offset is meaningless
+    uint4 w = gather16(S, (j == 2 ? b2 : (j == 1 ? b1 : b0)) + x);
+    if (j < 1 && (int)o1 < (int)xe && g.n1) w = merge16(w, gather16(S, b1 + x), (int)(o1 - x));
+    if (j < 2 && (int)o2 < (int)xe && g.n2) w = merge16(w, gather16(S, b2 + x), (int)(o2 - x));
+    return w;
+  };
+  if (hb) {
+    if (nfull == 0 && nt == 0) {   // the whole record sits in front of the first aligned boundary
+      for (uint32_t y = 0; y < len; ++y) dst[y] = (uint8_t)s_u8(S, (y >= o2 ? b2 : (y >= o1 ? b1 : b0)) + y);
+      return;
+    }
+    store_before(dst + hb, unit_at(hb - 16u), hb);
+  }
+  uint32_t x = hb;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 3; ++j) {
+    const uint32_t bj = j == 0 ? b0 : (j == 1 ? b1 : b2);
+    uint32_t end = j == 0 ? o1 : (j == 1 ? o2 : len);
+    if (end > tail0) end = tail0;       // only whole units here
+    if (x + 16u <= end) {
+      const uint32_t addr = bj + x, sh = addr & 15u;
+      uint32_t al = addr - sh;
+      uint4 lo = s_v4(S, al);
+      do {
+        al += 16u;
+        const uint4 hi = s_v4(S, al);
+        st_v4(dst + x, shift16(lo, hi, sh));
+        lo = hi;
+        x += 16u;
+      } while (x + 16u <= end);
+    }
+    if (x < end) {                      // whole unit that leaves segment j
+      st_v4(dst + x, unit_at(x));
+      x += 16u;
     }
   }
-  for (uint32_t u = (uint32_t)lane; u < nfull; u += 32u) {
-    const uint32_t x = hb + (u << 4), xe = x + 16u;
-    const int j = (x >= o1 ? 1 : 0) + (x >= o2 ? 1 : 0);
-    uint4 w = gather16(S, (j == 2 ? b2 : (j == 1 ? b1 : b0)) + x);
-    if (j < 1 && o1 < xe && g.n1) w = merge16(w, gather16(S, b1 + x), (int)(o1 - x));
-    if (j < 2 && o2 < xe && g.n2) w = merge16(w, gather16(S, b2 + x), (int)(o2 - x));
-    if (g.patch_at >= x && g.patch_at < xe) put_byte16(w, (int)(g.patch_at - x), g.patch_val);
-    *reinterpret_cast<uint4*>(dst + x) = w;
-  }
+  if (nt) store_after(dst + tail0, unit_at(tail0), nt);
 }
 
-// ---------------------------------------------------------------- record geometry inside S
-// RecGeom (device_logic.cuh) with every position an offset into S.
-
-// Illumina header rewrite: where the kept digits start (src/sample_data.rs:584-626).
+// ---------------------------------------------------------------- header rewrite
+// Positions are offsets into S.  Illumina: where the kept digits start
+// (src/sample_data.rs:584-626): leading zeros of the read number are dropped (all
+// zeros: nothing is left), the two 3-digit fields keep at least their last digit.
 struct HdrInfo {
-  uint32_t z, f1, f2;  // S offsets: first kept byte of the read number (== sep if none), of the two 3-digit fields
-  uint32_t sep;        // S offset of the '/' (header length - 3, src/lib.rs:1007)
+  uint32_t z, f1, f2;  // first kept byte of the read number (== sep if none), of the two 3-digit fields
+  uint32_t sep;        // the '/' (header length - 3, src/lib.rs:1007)
 };
 
-template <class W>
-MGK_HD HdrInfo hdr_info(const W& w, const Params& P, const uint8_t* S, const RecGeom& G) {
+MGK_HD HdrInfo hdr_info(const Params& P, const uint8_t* S, const RecGeom& G) {
   HdrInfo h;
   const uint32_t L = (uint32_t)P.L, H = G.h2;
   h.sep = G.s2 - 3u;
-  // one ballot covers the two 3-digit fields (bits 0-2, 4-6) and the first 25 digits of the read number
-  const uint32_t w0 = H + L + 3u;
-  uint32_t nz = w.ballot([&](int lane) {
-    const uint32_t at = w0 + (uint32_t)lane;
-    return (lane < 7 || at < h.sep) && s_u8(S, at) != '0';   // the two 3-digit fields are read unconditionally
-  });
-  h.f1 = (nz & 1u) ? H + L + 3u : ((nz & 2u) ? H + L + 4u : H + L + 5u);
-  h.f2 = (nz & 0x10u) ? H + L + 7u : ((nz & 0x20u) ? H + L + 8u : H + L + 9u);
-  uint32_t rest = nz >> 7;
-  uint32_t base = H + L + 10u;
-  h.z = h.sep;
-  for (;;) {
-    if (rest) {
-      h.z = base + (uint32_t)ctz32(rest);
-      break;
-    }
-    base += (base == H + L + 10u) ? 25u : 32u;
-    if (base >= h.sep) break;
-    const uint32_t bb = base;
-    rest = w.ballot([&](int lane) {
-      const uint32_t at = bb + (uint32_t)lane;
-      return at < h.sep && s_u8(S, at) != '0';
-    });
-  }
+  h.f1 = s_u8(S, H + L + 3u) != '0' ? H + L + 3u : (s_u8(S, H + L + 4u) != '0' ? H + L + 4u : H + L + 5u);
+  h.f2 = s_u8(S, H + L + 7u) != '0' ? H + L + 7u : (s_u8(S, H + L + 8u) != '0' ? H + L + 8u : H + L + 9u);
+  uint32_t z = H + L + 10u;
+  while (z < h.sep && s_u8(S, z) == '0') ++z;
+  h.z = z < h.sep ? z : h.sep;
   return h;
 }
 
-// Source of byte k of the text that follows the original/new header fields:
+// What follows the header fields:
 //   illumina : [":" umi] " " n ":N:0:" barcode            (src/sample_data.rs:627-653)
 //   mgi full : " " [umi " "] n ":N:0:" barcode            (src/lib.rs:1294-1319)
-// `cs` = S offset of the literals (LIT_*), `bar` = S offset of the BL barcode bytes,
-// `nsrc` = S offset of the read-number digit.
 struct TailSpec {
-  uint32_t cs, bar, nsrc;
   uint32_t umi_off, umi_len;   // S offset / length of the UMI (0 length: none)
   uint32_t i7_off, i7_len, i5_off, i5_len, has_i5, has_bar;
-  int full;                    // 1: mgi full header flavour
 };
-MGK_HD uint32_t tail_len(const TailSpec& t) {
+MGK_HD uint32_t barcode_len(const TailSpec& t) { return t.has_bar ? t.i7_len + (t.has_i5 ? 1u + t.i5_len : 0u) : 0u; }
+MGK_HD uint32_t tail_len(const TailSpec& t, int full) {
   const uint32_t u = t.umi_len ? 1u + t.umi_len : 0u;
-  const uint32_t b = t.has_bar ? t.i7_len + (t.has_i5 ? 1u + t.i5_len : 0u) : 0u;
-  return (t.full ? 1u : 0u) + u + (t.full ? 0u : 1u) + 1u + 5u + b;
+  (void)full;
+  return u + 7u + barcode_len(t);   // both flavours: one separator more than the umi, n, ":N:0:"
 }
-MGK_HD uint32_t tail_src(const TailSpec& t, uint32_t k) {
-  uint32_t u0;
-  if (t.full) {  // " " [umi " "]
-    if (k == 0) return t.cs + LIT_SPACE;
-    u0 = 1u;
-    if (t.umi_len) {
-      if (k < 1u + t.umi_len) return t.umi_off + (k - 1u);
-      if (k == 1u + t.umi_len) return t.cs + LIT_SPACE;
-      u0 = 2u + t.umi_len;
-    }
-  } else {       // [":" umi] " "
-    u0 = 0u;
-    if (t.umi_len) {
-      if (k == 0) return t.cs + LIT_COLON;
-      if (k < 1u + t.umi_len) return t.umi_off + (k - 1u);
-      u0 = 1u + t.umi_len;
-    }
-    if (k == u0) return t.cs + LIT_SPACE;
-    u0 += 1u;
-  }
-  if (k == u0) return t.nsrc;
-  if (k < u0 + 6u) return t.cs + LIT_TAIL + (k - u0 - 1u);
-  const uint32_t b0 = u0 + 6u;
-  if (k < b0 + t.i7_len) return t.i7_off + (k - b0);
-  if (k == b0 + t.i7_len) return t.cs + LIT_PLUS;
-  return t.i5_off + (k - b0 - t.i7_len - 1u);
-}
-
-MGK_HD TailSpec make_tail(const Params& P, const RecGeom& G, int bar_t, int umi_t, uint32_t cs, uint32_t nsrc, int full) {
+MGK_HD TailSpec make_tail(const Params& P, const RecGeom& G, int bar_t, int umi_t) {
   TailSpec t;
-  t.cs = cs;
-  t.bar = G.p2 - 1u - (uint32_t)P.BL;
-  t.nsrc = nsrc;
-  t.full = full;
+  const uint32_t bar = G.p2 - 1u - (uint32_t)P.BL;
   t.umi_off = t.umi_len = 0;
   if (umi_t >= 0) {
-    t.umi_off = t.bar + (uint32_t)(P.BL - P.tpl[umi_t].g[8]);
+    t.umi_off = bar + (uint32_t)(P.BL - P.tpl[umi_t].g[8]);
     t.umi_len = (uint32_t)P.tpl[umi_t].g[7];
   }
   t.has_bar = bar_t >= 0 ? 1u : 0u;
-  t.i7_off = t.i5_off = t.bar;
+  t.i7_off = t.i5_off = bar;
   t.i7_len = t.i5_len = t.has_i5 = 0;
   if (bar_t >= 0) {
     const TemplateDev& T = P.tpl[bar_t];
-    t.i7_off = t.bar + (uint32_t)(P.BL - T.g[2]);
+    t.i7_off = bar + (uint32_t)(P.BL - T.g[2]);
     t.i7_len = (uint32_t)T.g[1];
     t.has_i5 = T.has_i5 ? 1u : 0u;
     if (T.has_i5) {
-      t.i5_off = t.bar + (uint32_t)(P.BL - T.g[5]);
+      t.i5_off = bar + (uint32_t)(P.BL - T.g[5]);
       t.i5_len = (uint32_t)T.g[4];
     }
   }
   return t;
 }
 
-// Illumina header into the staging area S[hs..): prefix lane ":" readno ":" ccc ":" rrr tail.
-// Returns its length.  `cs0` = S offset of the prefix (the literals follow it).
-template <class W>
-MGK_HD uint32_t build_illumina_header(const W& w, const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G,
-                                      const HdrInfo& hi, const TailSpec& t) {
-  const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len, lit = cs0 + Pn;
-  const uint32_t nr = hi.sep - hi.z, n1 = H + L + 6u - hi.f1, n2 = H + L + 10u - hi.f2;
-  const uint32_t t1 = 2u + nr, t2 = t1 + 1u + n1, t3 = t2 + 1u + n2, tl = tail_len(t);
-  const uint32_t total = Pn + t3 + tl;
-  w.each([&](int lane) {
-    for (uint32_t k = (uint32_t)lane; k < total; k += 32u) {
-      uint32_t src;
-      if (k < Pn) {
-        src = cs0 + k;
-      } else {
-        const uint32_t q = k - Pn;
-        if (q >= t3) src = tail_src(t, q - t3);
-        else if (q == 0) src = H + L + 1u;
-        else if (q == 1 || q == t1 || q == t2) src = lit + LIT_COLON;
-        else if (q < t1) src = hi.z + (q - 2u);
-        else if (q < t2) src = hi.f1 + (q - t1 - 1u);
-        else src = hi.f2 + (q - t2 - 1u);
-      }
-      S[hs + k] = (uint8_t)s_u8(S, src);
+// A header is written front to back through a cursor.  `Sink` is either the
+// per-thread staging slot in S or, for headers too long for the slot, the
+// destination itself (byte stores; correct for any length, just slower).
+struct SlotSink {
+  uint8_t* p;
+  MGK_HD void put(uint32_t v) { *p++ = (uint8_t)v; }
+};
+template <class Sink>
+MGK_HD void put_span(Sink& o, const uint8_t* S, uint32_t src, uint32_t n) {
+  for (uint32_t k = 0; k < n; ++k) o.put(s_u8(S, src + k));
+}
+template <class Sink>
+MGK_HD void put_tail(Sink& o, const uint8_t* S, const TailSpec& t, uint32_t n_digit, int full) {
+  if (full) {
+    o.put(' ');
+    if (t.umi_len) {
+      put_span(o, S, t.umi_off, t.umi_len);
+      o.put(' ');
     }
-  });
-  return total;
+  } else {
+    if (t.umi_len) {
+      o.put(':');
+      put_span(o, S, t.umi_off, t.umi_len);
+    }
+    o.put(' ');
+  }
+  o.put(n_digit);
+  o.put(':');
+  o.put('N');
+  o.put(':');
+  o.put('0');
+  o.put(':');
+  if (t.has_bar) {
+    put_span(o, S, t.i7_off, t.i7_len);
+    if (t.has_i5) {
+      o.put('+');
+      put_span(o, S, t.i5_off, t.i5_len);
+    }
+  }
+}
+MGK_HD uint32_t illumina_header_len(const Params& P, const RecGeom& G, const HdrInfo& hi, const TailSpec& t) {
+  const uint32_t L = (uint32_t)P.L, H = G.h2;
+  return (uint32_t)P.prefix_len + 2u + (hi.sep - hi.z) + 1u + (H + L + 6u - hi.f1) + 1u + (H + L + 10u - hi.f2) + tail_len(t, 0);
+}
+// prefix lane ":" readno ":" ccc ":" rrr tail.  `cs0` = S offset of the prefix.
+template <class Sink>
+MGK_HD void put_illumina_header(Sink& o, const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G, const HdrInfo& hi,
+                                const TailSpec& t, uint32_t n_digit) {
+  const uint32_t L = (uint32_t)P.L, H = G.h2;
+  put_span(o, S, cs0, (uint32_t)P.prefix_len);
+  o.put(s_u8(S, H + L + 1u));
+  o.put(':');
+  put_span(o, S, hi.z, hi.sep - hi.z);
+  o.put(':');
+  put_span(o, S, hi.f1, H + L + 6u - hi.f1);
+  o.put(':');
+  put_span(o, S, hi.f2, H + L + 10u - hi.f2);
+  put_tail(o, S, t, n_digit, 0);
 }
 
-// MGI full header of one read: its own header line without the '\n', then the tail.
-template <class W>
-MGK_HD uint32_t build_full_header(const W& w, uint8_t* S, uint32_t hs, uint32_t h, uint32_t hl1, const TailSpec& t) {
-  const uint32_t total = hl1 + tail_len(t);
-  w.each([&](int lane) {
-    for (uint32_t k = (uint32_t)lane; k < total; k += 32u) {
-      const uint32_t src = k < hl1 ? h + k : tail_src(t, k - hl1);
-      S[hs + k] = (uint8_t)s_u8(S, src);
+// ---------------------------------------------------------------- the two emit roles
+constexpr uint32_t HDR_SLOT_BYTES = 96;     // per (record, read) staging slot; longer headers take the byte-store path
+struct GlobalSink {
+  uint8_t* p;
+  MGK_HD void put(uint32_t v) { *p++ = (uint8_t)v; }
+};
+
+// Barcode read of one pair -> d2.  `hs` = this thread's staging slot (S offset, 16-byte aligned).
+MGK_HD void emit_read2(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int sample, int bar_t, int umi_t,
+                       uint8_t* d2) {
+  Seg3 g;
+  g.s1 = g.n1 = g.s2 = g.n2 = 0;
+  if (sample >= P.S) {  // verbatim, src/lib.rs:1225-1235
+    g.s0 = G.h2;
+    g.n0 = G.e2 + 1u - G.h2;
+    copy3(d2, S, g);
+    return;
+  }
+  if (!P.read2_has_sequence) return;   // samples get no barcode-read file, src/sample_data.rs:35-44
+  const uint32_t wbl = P.keep_barcode ? 0u : (uint32_t)P.BL;
+  // "\n+\n" qual[..-wbl]; the closing '\n' (src/lib.rs:1324-1327) is stored on its own below
+  const uint32_t qs = G.p2 - 1u, qn = G.e2 - wbl - (G.p2 - 1u);
+  uint32_t len;
+  if (P.out_mode == MGK_OUT_MGI) {
+    g.s0 = G.h2;
+    g.n0 = G.p2 - wbl - 1u - G.h2;   // header line and trimmed sequence are contiguous
+    g.s1 = qs;
+    g.n1 = qn;
+    len = g.n0 + g.n1;
+    copy3(d2, S, g);
+  } else {
+    const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
+    const TailSpec t = make_tail(P, G, bar_t, umi_t);
+    const uint32_t n_digit = s_u8(S, G.s2 - 2u);          // src/lib.rs:1275,1302
+    HdrInfo hi;
+    uint32_t hl;
+    if (full) {
+      hi.z = hi.f1 = hi.f2 = hi.sep = 0;
+      hl = G.s2 - G.h2 - 1u + tail_len(t, 1);
+    } else {
+      hi = hdr_info(P, S, G);
+      hl = illumina_header_len(P, G, hi, t);
     }
-  });
-  return total;
+    g.s1 = G.s2 - 1u;
+    g.n1 = G.p2 - wbl - 1u - (G.s2 - 1u);                // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
+    g.s2 = qs;
+    g.n2 = qn;
+    if (hl <= HDR_SLOT_BYTES) {
+      SlotSink o{S + hs};
+      if (full) {
+        put_span(o, S, G.h2, G.s2 - G.h2 - 1u);
+        put_tail(o, S, t, n_digit, 1);
+      } else {
+        put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
+      }
+      g.s0 = hs;
+      g.n0 = hl;
+      copy3(d2, S, g);
+    } else {
+      GlobalSink o{d2};
+      if (full) {
+        put_span(o, S, G.h2, G.s2 - G.h2 - 1u);
+        put_tail(o, S, t, n_digit, 1);
+      } else {
+        put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
+      }
+      g.s0 = g.n0 = 0;
+      copy3(d2 + hl, S, g);
+    }
+    len = hl + g.n1 + g.n2;
+  }
+  d2[len] = '\n';
+}
+
+// Paired read of one pair -> d1.  In illumina mode its header is the barcode read's new
+// header with its own read-number digit (src/sample_data.rs:302-328, src/lib.rs:1288).
+MGK_HD void emit_read1(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int sample, int bar_t, int umi_t,
+                       uint8_t* d1) {
+  Seg3 g;
+  g.s1 = g.n1 = g.s2 = g.n2 = 0;
+  if (sample >= P.S || P.out_mode == MGK_OUT_MGI) {  // verbatim
+    g.s0 = G.h1;
+    g.n0 = G.e1 + 1u - G.h1;
+    copy3(d1, S, g);
+    return;
+  }
+  const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
+  const TailSpec t = make_tail(P, G, bar_t, umi_t);
+  const uint32_t n_digit = s_u8(S, G.s1 - 2u);           // src/lib.rs:1288,1314
+  HdrInfo hi;
+  uint32_t hl;
+  if (full) {
+    hi.z = hi.f1 = hi.f2 = hi.sep = 0;
+    hl = G.s1 - G.h1 - 1u + tail_len(t, 1);              // the paired read keeps ITS OWN header line, src/lib.rs:1306-1318
+  } else {
+    hi = hdr_info(P, S, G);
+    hl = illumina_header_len(P, G, hi, t);
+  }
+  g.s1 = G.s1 - 1u;
+  g.n1 = G.e1 + 1u - (G.s1 - 1u);                         // src/lib.rs:1328-1331
+  if (hl <= HDR_SLOT_BYTES) {
+    SlotSink o{S + hs};
+    if (full) {
+      put_span(o, S, G.h1, G.s1 - G.h1 - 1u);
+      put_tail(o, S, t, n_digit, 1);
+    } else {
+      put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
+    }
+    g.s0 = hs;
+    g.n0 = hl;
+    copy3(d1, S, g);
+  } else {
+    GlobalSink o{d1};
+    if (full) {
+      put_span(o, S, G.h1, G.s1 - G.h1 - 1u);
+      put_tail(o, S, t, n_digit, 1);
+    } else {
+      put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
+    }
+    g.s0 = g.n0 = 0;
+    copy3(d1 + hl, S, g);
+  }
 }
 
 // ---------------------------------------------------------------- QC sums out of S
@@ -298,25 +476,28 @@ MGK_HD uint32_t keep_range(uint32_t wd, int lo, int hi) {  // keep bytes [lo,hi)
   if (lo) mask &= ~((1u << (8 * lo)) - 1u);
   return wd & mask;
 }
-// this sub-lane's share of sum_qc over S[start .. start+n): aligned vectors, edges masked
-MGK_HD Qc qc_span(const uint8_t* S, uint32_t start, uint32_t n, uint32_t sub, uint32_t nsub) {
+MGK_HD void qc_add(Qc& q, const uint4& a) {
+  q.sum += byte_sum(a.x) + byte_sum(a.y) + byte_sum(a.z) + byte_sum(a.w);
+  q.high += (uint32_t)(popc32(bytes_ge63(a.x)) + popc32(bytes_ge63(a.y)) + popc32(bytes_ge63(a.z)) + popc32(bytes_ge63(a.w)));
+}
+MGK_HD uint4 keep16(uint4 a, int lo, int hi) {
+  a.x = keep_range(a.x, lo, hi);
+  a.y = keep_range(a.y, lo - 4, hi - 4);
+  a.z = keep_range(a.z, lo - 8, hi - 8);
+  a.w = keep_range(a.w, lo - 12, hi - 12);
+  return a;
+}
+// sum_qc (src/lib.rs:458-474) over S[start .. start+n): aligned vectors, the two edge vectors masked
+MGK_HD Qc qc_line(const uint8_t* S, uint32_t start, uint32_t n) {
   Qc q;
   q.sum = q.high = 0;
   if (n == 0) return q;
   const uint32_t sh = start & 15u, al = start - sh;
   const uint32_t nvec = (sh + n + 15u) >> 4;
-  for (uint32_t v = sub; v < nvec; v += nsub) {
-    uint4 a = s_v4(S, al + (v << 4));
-    const int lo = (int)sh - (int)(v << 4), hi = (int)(sh + n) - (int)(v << 4);
-    if (lo > 0 || hi < 16) {
-      a.x = keep_range(a.x, lo, hi);
-      a.y = keep_range(a.y, lo - 4, hi - 4);
-      a.z = keep_range(a.z, lo - 8, hi - 8);
-      a.w = keep_range(a.w, lo - 12, hi - 12);
-    }
-    q.sum += byte_sum(a.x) + byte_sum(a.y) + byte_sum(a.z) + byte_sum(a.w);
-    q.high += (uint32_t)(popc32(bytes_ge63(a.x)) + popc32(bytes_ge63(a.y)) + popc32(bytes_ge63(a.z)) + popc32(bytes_ge63(a.w)));
-  }
+  const int end = (int)(sh + n);
+  qc_add(q, keep16(s_v4(S, al), (int)sh, end));
+  for (uint32_t v = 1; v + 1u < nvec; ++v) qc_add(q, s_v4(S, al + (v << 4)));
+  if (nvec > 1u) qc_add(q, keep16(s_v4(S, al + ((nvec - 1u) << 4)), 0, end - (int)((nvec - 1u) << 4)));
   return q;
 }
 
@@ -339,197 +520,58 @@ MGK_HD int qc_stat_column(int k, int paired) {
   }
 }
 
-struct U4 {
-  uint32_t a, b, c, d;
-};
-
-template <class W>
-MGK_HD QcSix qc_pair(const W& w, const Params& P, const uint8_t* S, const RecGeom& G) {
+MGK_HD QcSix qc_pair(const Params& P, const uint8_t* S, const RecGeom& G) {
   QcSix r;
   const uint32_t BL = (uint32_t)P.BL;
-  const uint32_t n2 = G.e2 - G.q2, n1 = P.paired ? G.e1 - G.q1 : 0u;
-  const int paired = P.paired;
-  // whole quality lines: lanes 0-15 the paired read, lanes 16-31 the barcode read (all 32 when single-end)
-  const U4 t = w.sum4([&](int lane) {
-    U4 v;
-    Qc q;
-    if (!paired) q = qc_span(S, G.q2, n2, (uint32_t)lane, 32u);
-    else if (lane < 16) q = qc_span(S, G.q1, n1, (uint32_t)lane, 16u);
-    else q = qc_span(S, G.q2, n2, (uint32_t)lane - 16u, 16u);
-    v.a = q.sum;
-    v.b = q.high;
-    v.c = (paired && lane < 16) ? q.sum : 0u;
-    v.d = (paired && lane < 16) ? q.high : 0u;
-    return v;
-  });
-  // the barcode's own qualities, one byte per lane: sum in the low half, count >= Q30 in the high half
-  // (BL <= 255, so neither half overflows)
-  const uint32_t bq = G.e2 - BL;
-  const uint32_t pb = w.sum([&](int lane) {
-    uint32_t s = 0;
-    for (uint32_t k = (uint32_t)lane; k < BL; k += 32u) {
-      const uint32_t q = s_u8(S, bq + k);
-      s += q + (q >= 63u ? 0x10000u : 0u);
-    }
-    return s;
-  });
-  const uint32_t sum_b = pb & 0xffffu, high_b = pb >> 16;
-  r.v[0] = t.d;
-  r.v[1] = t.c;
-  r.v[2] = high_b;
-  r.v[3] = sum_b;
-  r.v[4] = t.b - t.d - high_b;
-  r.v[5] = t.a - t.c - sum_b;
+  Qc q1;
+  q1.sum = q1.high = 0;
+  if (P.paired) q1 = qc_line(S, G.q1, G.e1 - G.q1);
+  const Qc q2 = qc_line(S, G.q2, G.e2 - G.q2);
+  uint32_t sb = 0, hb = 0;
+  for (uint32_t k = 0; k < BL; ++k) {   // the barcode's own qualities
+    const uint32_t q = s_u8(S, G.e2 - BL + k);
+    sb += q;
+    hb += q >= 63u ? 1u : 0u;
+  }
+  r.v[0] = q1.high;
+  r.v[1] = q1.sum;
+  r.v[2] = hb;
+  r.v[3] = sb;
+  r.v[4] = q2.high - hb;
+  r.v[5] = q2.sum - sb;
   return r;
 }
 
 // ---------------------------------------------------------------- --validate out of S
 // Lowest failing priority (1..7) of one pair, 0 if clean:
 //   1..3 paired read ('@', base, quality)  4 header mismatch  5..7 barcode read
-MGK_HD int validate_lane(const Params& P, const uint8_t* S, const RecGeom& G, int lane) {
-  int worst = 0;
-  auto note = [&](int p) {
-    if (worst == 0 || p < worst) worst = p;
-  };
+MGK_HD int validate_pair(const Params& P, const uint8_t* S, const RecGeom& G) {
   auto base_ok = [](uint32_t n) {
     return n == 'A' || n == 'C' || n == 'G' || n == 'T' || n == 'N' || n == 'a' || n == 'c' || n == 'g' || n == 't' || n == 'n';
   };
   if (P.paired) {
-    if (lane == 0 && s_u8(S, G.h1) != '@') note(1);
-    for (uint32_t i = G.s1 + (uint32_t)lane; i + 1u < G.p1; i += 32u)
-      if (!base_ok(s_u8(S, i))) note(2);
-    for (uint32_t i = G.q1 + (uint32_t)lane; i < G.e1; i += 32u) {
+    if (s_u8(S, G.h1) != '@') return 1;
+    for (uint32_t i = G.s1; i + 1u < G.p1; ++i)
+      if (!base_ok(s_u8(S, i))) return 2;
+    for (uint32_t i = G.q1; i < G.e1; ++i) {
       const uint32_t q = s_u8(S, i);
-      if (q > 73u || q < 33u) note(3);
+      if (q > 73u || q < 33u) return 3;
     }
     if (P.mgi_data) {
       const uint32_t l1 = G.s1 - 2u - G.h1, l2 = G.s2 - 2u - G.h2;
-      if (l1 != l2) {
-        if (lane == 0) note(4);
-      } else {
-        for (uint32_t i = (uint32_t)lane; i < l1; i += 32u)
-          if (s_u8(S, G.h1 + i) != s_u8(S, G.h2 + i)) note(4);
-      }
+      if (l1 != l2) return 4;
+      for (uint32_t i = 0; i < l1; ++i)
+        if (s_u8(S, G.h1 + i) != s_u8(S, G.h2 + i)) return 4;
     }
   }
-  if (lane == 0 && s_u8(S, G.h2) != '@') note(5);
-  for (uint32_t i = G.s2 + (uint32_t)lane; i + 1u < G.p2; i += 32u)
-    if (!base_ok(s_u8(S, i))) note(6);
-  for (uint32_t i = G.q2 + (uint32_t)lane; i < G.e2; i += 32u) {
+  if (s_u8(S, G.h2) != '@') return 5;
+  for (uint32_t i = G.s2; i + 1u < G.p2; ++i)
+    if (!base_ok(s_u8(S, i))) return 6;
+  for (uint32_t i = G.q2; i < G.e2; ++i) {
     const uint32_t q = s_u8(S, i);
-    if (q > 73u || q < 33u) note(7);
+    if (q > 73u || q < 33u) return 7;
   }
-  return worst;
-}
-
-// ---------------------------------------------------------------- one read pair
-struct PairOut {
-  int validate;   // lowest failing priority, 0 = clean (only when P.validate)
-  int hdr_overflow;
-  QcSix qc;       // only when P.report_level > 0
-};
-
-constexpr uint32_t HDR_STAGE_BYTES = 256;   // per warp; rewritten headers longer than this are refused
-constexpr uint32_t HDR_STAGE_MAX = HDR_STAGE_BYTES - 16;
-
-// `S` holds the tile (both reads), the constants (prefix + literals at S[cs0..))
-// and this warp's header staging area S[hs .. hs+HDR_STAGE_BYTES).  `G` is in S
-// offsets.  d2 / d1 = where this pair's two output records start.
-template <class W>
-MGK_HD PairOut emit_pair(const W& w, const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int sample,
-                         int bar_t, int umi_t, uint8_t* d2, uint8_t* d1) {
-  PairOut out;
-  out.validate = 0;
-  out.hdr_overflow = 0;
-  const uint32_t BL = (uint32_t)P.BL, wbl = P.keep_barcode ? 0u : BL;
-  const uint32_t lit = cs0 + (uint32_t)P.prefix_len;
-  const bool matched = sample < P.S;
-  Seg3 g2, g1;
-  g2.patch_at = g1.patch_at = 0xffffffffu;
-  g2.patch_val = g1.patch_val = '\n';
-  g2.s2 = g2.n2 = g1.s2 = g1.n2 = 0;
-  if (!matched) {  // verbatim, src/lib.rs:1225-1235
-    g2.s0 = G.h2; g2.n0 = G.e2 + 1u - G.h2; g2.s1 = g2.n1 = 0;
-    g1.s0 = G.h1; g1.n0 = P.paired ? G.e1 + 1u - G.h1 : 0u; g1.s1 = g1.n1 = 0;
-    w.each([&](int lane) {
-      emit3(d2, S, g2, lane);
-      if (P.paired) emit3(d1, S, g1, lane);
-    });
-  } else {
-    // quality part "\n+\n" qual[..-wbl] and the closing '\n' (src/lib.rs:1324-1327): one extra byte, overridden
-    const uint32_t qs = G.p2 - 1u, qn = G.e2 - wbl - (G.p2 - 1u) + 1u;
-    if (P.out_mode == MGK_OUT_MGI) {
-      if (P.read2_has_sequence) {
-        g2.s0 = G.h2; g2.n0 = G.p2 - wbl - 1u - G.h2;     // header and trimmed sequence are contiguous
-        g2.s1 = qs; g2.n1 = qn;
-        g2.patch_at = g2.n0 + g2.n1 - 1u;
-      }
-      g1.s0 = G.h1; g1.n0 = P.paired ? G.e1 + 1u - G.h1 : 0u; g1.s1 = g1.n1 = 0;
-      w.each([&](int lane) {
-        if (P.read2_has_sequence) emit3(d2, S, g2, lane);
-        if (P.paired) emit3(d1, S, g1, lane);
-      });
-    } else {
-      const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
-      uint32_t hl;
-      TailSpec t = make_tail(P, G, bar_t, umi_t, lit, G.s2 - 2u, full);  // n of the barcode read, src/lib.rs:1275,1302
-      if (!full) {
-        const HdrInfo hi = hdr_info(w, P, S, G);
-        const uint32_t nr = hi.sep - hi.z;
-        if ((uint32_t)P.prefix_len + nr + tail_len(t) + 16u > HDR_STAGE_MAX) {
-          out.hdr_overflow = 1;
-          return out;
-        }
-        hl = build_illumina_header(w, P, S, hs, cs0, G, hi, t);
-      } else {
-        const uint32_t hl1 = G.s2 - G.h2 - 1u;
-        if (hl1 + tail_len(t) > HDR_STAGE_MAX || (P.paired && G.s1 - G.h1 - 1u + tail_len(t) > HDR_STAGE_MAX)) {
-          out.hdr_overflow = 1;
-          return out;
-        }
-        hl = build_full_header(w, S, hs, G.h2, hl1, t);
-      }
-      w.sync();
-      if (P.read2_has_sequence) {
-        g2.s0 = hs; g2.n0 = hl;
-        g2.s1 = G.s2 - 1u; g2.n1 = G.p2 - wbl - 1u - (G.s2 - 1u);   // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
-        g2.s2 = qs; g2.n2 = qn;
-        g2.patch_at = g2.n0 + g2.n1 + g2.n2 - 1u;
-      } else {
-        g2.s0 = g2.n0 = g2.s1 = g2.n1 = 0;
-      }
-      if (P.paired && !full) {   // copy of the new header with the read-number digit of the paired read
-        g1.s0 = hs; g1.n0 = hl;                                     // src/sample_data.rs:302-328
-        g1.s1 = G.s1 - 1u; g1.n1 = G.e1 + 1u - (G.s1 - 1u);         // src/lib.rs:1328-1331
-        g1.patch_at = hl - 6u - (t.has_bar ? t.i7_len + (t.has_i5 ? 1u + t.i5_len : 0u) : 0u);
-        g1.patch_val = s_u8(S, G.s1 - 2u);                          // src/lib.rs:1288
-      }
-      w.each([&](int lane) {
-        if (P.read2_has_sequence) emit3(d2, S, g2, lane);
-        if (P.paired && !full) emit3(d1, S, g1, lane);
-      });
-      if (P.paired && full) {    // the paired read keeps ITS OWN header line (src/lib.rs:1306-1318)
-        w.sync();
-        t.nsrc = G.s1 - 2u;
-        const uint32_t hl1 = G.s1 - G.h1 - 1u;
-        const uint32_t hlp = build_full_header(w, S, hs, G.h1, hl1, t);
-        w.sync();
-        g1.s0 = hs; g1.n0 = hlp;
-        g1.s1 = G.s1 - 1u; g1.n1 = G.e1 + 1u - (G.s1 - 1u);
-        w.each([&](int lane) { emit3(d1, S, g1, lane); });
-      }
-      w.sync();  // the staging area is free again
-    }
-  }
-  if (P.report_level > 0) out.qc = qc_pair(w, P, S, G);
-  if (P.validate) {
-    const int v = w.min([&](int lane) {
-      const int x = validate_lane(P, S, G, lane);
-      return x ? x : 15;
-    });
-    out.validate = v == 15 ? 0 : v;
-  }
-  return out;
+  return 0;
 }
 
 }  // namespace mgk

@@ -34,8 +34,7 @@ enum : uint32_t {
   ERR_REC_CAPACITY = 2u,   // more records than max_chunk_records
   ERR_OUT_CAPACITY = 4u,   // output larger than the output buffer
   ERR_PANIC = 8u,          // a read hit the reference's stale-dictionary panic
-  ERR_REC_TOO_LONG = 16u,  // one read pair does not fit a shared-memory stage
-  ERR_HDR_TOO_LONG = 32u   // a rewritten header exceeds HDR_STAGE_MAX bytes
+  ERR_REC_TOO_LONG = 16u   // one read pair does not fit a shared-memory stage
 };
 
 struct __align__(16) RecMeta {
@@ -442,15 +441,24 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
 // of the input therefore crosses HBM->SM exactly once in this kernel, as
 // full-width bulk copies, and every output byte leaves as part of a 16-byte
 // store aligned on its destination (emit3, emit_logic.cuh).
-constexpr int EMIT_THREADS = 512;
-constexpr int EMIT_WARPS = EMIT_THREADS / 32;
 constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
+constexpr int EMIT_ROLES = 3;                // A barcode read, B paired read, C QC + validate: one thread per (record, role)
+constexpr int EMIT_WORKERS = EMIT_ROLES * EMIT_NMAX;
+constexpr int EMIT_THREADS = EMIT_WORKERS + 32;   // + the producer warp (bulk copies of the next tile)
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
+// staging slot of (role, record): inside a warp's 32 slots, rows of 8 are skewed by 16 bytes so that the lanes spread
+// over all banks
+constexpr uint32_t HDR_WARP_BYTES = 32u * HDR_SLOT_BYTES + 64u;
+constexpr uint32_t HDR_ROLE_BYTES = (EMIT_NMAX / 32) * HDR_WARP_BYTES;
+constexpr uint32_t HDR_AREA_BYTES = 2u * HDR_ROLE_BYTES;
+__host__ __device__ inline uint32_t hdr_slot(uint32_t role, uint32_t i) {
+  return role * HDR_ROLE_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 16u * ((i >> 3) & 3u);
+}
 
 struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 16-byte aligned
   uint32_t consts;        // prefix + literals (+ slack)
   uint32_t stats;         // [total][QC_SLOTS] u32
-  uint32_t hdr;           // [EMIT_WARPS][HDR_STAGE_BYTES]
+  uint32_t hdr;           // header staging slots, hdr_slot()
   uint32_t stage0, stage_stride;   // two stages, each: nl2 | nl1 | meta | bins | bytes
   uint32_t nl1, meta, bins, bytes;   // offsets inside a stage (nl2 at 0)
   uint32_t cap;           // bytes of text one stage holds (both reads)
@@ -492,31 +500,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-struct WarpDev {
-  int lane;
-  template <class F> __device__ __forceinline__ void each(F f) const { f(lane); }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
-  template <class F> __device__ __forceinline__ uint32_t ballot(F f) const { return __ballot_sync(0xffffffffu, f(lane)); }
-  template <class F> __device__ __forceinline__ uint32_t sum(F f) const { return __reduce_add_sync(0xffffffffu, (uint32_t)f(lane)); }
-  template <class F> __device__ __forceinline__ U4 sum4(F f) const {
-    const U4 v = f(lane);
-    U4 r;
-    r.a = __reduce_add_sync(0xffffffffu, v.a);
-    r.b = __reduce_add_sync(0xffffffffu, v.b);
-    r.c = __reduce_add_sync(0xffffffffu, v.c);
-    r.d = __reduce_add_sync(0xffffffffu, v.d);
-    return r;
-  }
-  template <class F> __device__ __forceinline__ int min(F f) const { return __reduce_min_sync(0xffffffffu, (int)f(lane)); }
-};
-
 __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restrict__ Pg, ChunkDev c, EmitLayout lay) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Params P;
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ StageDesc s_desc[2];
-  __shared__ uint32_t s_claim[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PRODUCER_WARP = EMIT_WORKERS / 32;
 
   copy_params_to_smem(&P, Pg);
   if (tid == 0) {
@@ -547,17 +537,16 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   {
     const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
     const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
-    n_tile = (lay.cap - 192u) / (mean + mean / 32u + 1u);
-    n_tile = max(1u, min(n_tile, (uint32_t)EMIT_NMAX));
+    n_tile = max(1u, min((lay.cap - 256u) / mean, (uint32_t)EMIT_NMAX));
   }
 
-  // producer state (warp 0, lane 0)
+  // producer state (lane 0 of the producer warp)
   uint32_t next_rec = R0, start2 = 0, start1 = 0;
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     start2 = c.nl2[(long long)4 * R0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
     start1 = paired ? c.nl1[(long long)4 * R0 - 1] + 1u : 0u;
   }
-  auto produce = [&](int s) {   // lane 0 of warp 0
+  auto produce = [&](int s) {   // lane 0 of the producer warp
     StageDesc& d = s_desc[s];
     if (next_rec >= R1) {
       d.n = 0;
@@ -574,7 +563,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       len1 = paired ? ((e1 + 15u) & ~15u) - base1 : 0u;
       off1 = (len2 + 127u) & ~127u;
       if (off1 + len1 + 32u <= lay.cap || lim == r0 + 1u) break;
-      lim = r0 + (lim - r0) / 2u;
+      lim = r0 + max(1u, (lim - r0) * 15u / 16u);   // rare: records much longer than the chunk's mean
     }
     if (off1 + len1 + 32u > lay.cap) {   // one read pair larger than a stage
       atomicOr(&c.status->error, ERR_REC_TOO_LONG);
@@ -588,7 +577,6 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     d.base2 = base2;
     d.base1 = base1;
     d.off1 = off1;
-    s_claim[s] = 0;
     unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
     const uint32_t nl_bytes = 16u * (n + 1u), meta_bytes = 16u * n, bins_bytes = 4u * bins_stride;
     mbar_expect_tx(&s_bar[s], len2 + len1 + (paired ? 2u : 1u) * nl_bytes + meta_bytes + bins_bytes);
@@ -602,11 +590,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     start2 = e2;
     start1 = e1;
   };
-  if (warp == 0 && lane == 0) produce(0);
+  if (warp == PRODUCER_WARP && lane == 0) produce(0);
   __syncthreads();
 
-  const WarpDev w{lane};
-  const uint32_t hs = lay.hdr + (uint32_t)warp * HDR_STAGE_BYTES;
   uint32_t* s_stats = reinterpret_cast<uint32_t*>(smem + lay.stats);
   auto flush_stats = [&]() {   // all threads; s_stats quiescent
     for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) {
@@ -618,62 +604,62 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       }
     }
   };
+  const int role = tid / EMIT_NMAX;            // warp-uniform: 0 A, 1 B, 2 C, 3 producer
+  const uint32_t i = (uint32_t)(tid % EMIT_NMAX);
+  const uint32_t hs = lay.hdr + hdr_slot(role == 1 ? 1u : 0u, i);
 
   for (uint32_t k = 0;; ++k) {
     const int s = (int)(k & 1u);
-    if (warp == 0 && lane == 0) produce(s ^ 1);
+    if (warp == PRODUCER_WARP && lane == 0) produce(s ^ 1);
     const StageDesc d = s_desc[s];
     if (d.n == 0) break;
-    mbar_wait(&s_bar[s], (k >> 1) & 1u);
-    unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
-    const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
-    const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
-    const RecMeta* metas = reinterpret_cast<const RecMeta*>(st + lay.meta);
-    const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
-    // S offsets of chunk byte 0 of either read
-    const uint32_t o2 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes - d.base2;
-    const uint32_t o1 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes + d.off1 - d.base1;
-    for (;;) {
-      uint32_t i = 0;
-      if (lane == 0) i = atomicAdd(&s_claim[s], 1u);
-      i = __shfl_sync(0xffffffffu, i, 0);
-      if (i >= d.n) break;
-      const RecMeta mt = metas[i];
-      if (mt.flags & 1) continue;   // layout error: reported through status, nothing emitted
-      RecGeom G;
-      {
-        const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
-        G.h2 = nl2s[4u * i + 3u] + 1u + o2;
-        G.s2 = a.x + 1u + o2;
-        G.p2 = a.y + 1u + o2;
-        G.q2 = a.z + 1u + o2;
-        G.e2 = a.w + o2;
-        G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
-        if (paired) {
-          const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
-          G.h1 = nl1s[4u * i + 3u] + 1u + o1;
-          G.s1 = b.x + 1u + o1;
-          G.p1 = b.y + 1u + o1;
-          G.q1 = b.z + 1u + o1;
-          G.e1 = b.w + o1;
+    if (role < EMIT_ROLES && i < d.n && !(role == 1 && !paired)) {
+      mbar_wait(&s_bar[s], (k >> 1) & 1u);
+      unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
+      const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
+      const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
+      const RecMeta mt = reinterpret_cast<const RecMeta*>(st + lay.meta)[i];
+      const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
+      if (!(mt.flags & 1)) {   // layout errors are reported through status, nothing is emitted
+        // S offsets of chunk byte 0 of either read
+        const uint32_t o2 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes - d.base2;
+        const uint32_t o1 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes + d.off1 - d.base1;
+        RecGeom G;
+        {
+          const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
+          G.h2 = nl2s[4u * i + 3u] + 1u + o2;
+          G.s2 = a.x + 1u + o2;
+          G.p2 = a.y + 1u + o2;
+          G.q2 = a.z + 1u + o2;
+          G.e2 = a.w + o2;
+          G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
+          if (paired) {
+            const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
+            G.h1 = nl1s[4u * i + 3u] + 1u + o1;
+            G.s1 = b.x + 1u + o1;
+            G.p1 = b.y + 1u + o1;
+            G.q1 = b.z + 1u + o1;
+            G.e1 = b.w + o1;
+          }
+        }
+        const int sample = mt.sample, bin = mt.bin;
+        if (role == 0) {
+          emit_read2(P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, c.out2 + bins[bin] + mt.off2);
+        } else if (role == 1) {
+          emit_read1(P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, c.out1 + bins[total + bin] + mt.off1);
+        } else {
+          if (P.report_level > 0) {   // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
+            const QcSix q = qc_pair(P, smem, G);
+#pragma unroll
+            for (int j = 0; j < QC_SLOTS; ++j)
+              if (q.v[j]) atomicAdd(&s_stats[sample * QC_SLOTS + j], q.v[j]);   // slots 0,1 stay 0 when single-end
+          }
+          if (P.validate) {
+            const int v = validate_pair(P, smem, G);
+            if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)v);
+          }
         }
       }
-      const int sample = mt.sample, bin = mt.bin;
-      uint8_t* d2 = c.out2 + bins[bin] + mt.off2;
-      uint8_t* d1 = paired ? c.out1 + bins[total + bin] + mt.off1 : nullptr;
-      const PairOut po = emit_pair(w, P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, d2, d1);
-      if (po.hdr_overflow) {
-        if (lane == 0) atomicOr(&c.status->error, ERR_HDR_TOO_LONG);
-        continue;
-      }
-      if (P.report_level > 0 && lane < QC_SLOTS) {
-        uint32_t v = po.qc.v[0];
-#pragma unroll
-        for (int q = 1; q < QC_SLOTS; ++q) v = lane == q ? po.qc.v[q] : v;
-        if (v) atomicAdd(&s_stats[sample * QC_SLOTS + lane], v);
-      }
-      if (P.validate && po.validate && lane == 0)
-        atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)po.validate);
     }
     __syncthreads();   // stage s is free again; desc[s^1] is published
     if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {

@@ -276,7 +276,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
     at += 32u;                                   // slack in front of the header staging areas (gather16 reads around them)
     L.hdr = at;
-    at += EMIT_WARPS * HDR_STAGE_BYTES + 32u;
+    at += HDR_AREA_BYTES + 32u;
     at = up(at, 128u);
     const uint32_t nl_bytes = 16u * (EMIT_NMAX + 1u);
     L.nl1 = up(nl_bytes, 16u);
@@ -463,8 +463,6 @@ extern "C" int mgk_collect(mgk_ctx* ctx, mgk_result* res) {
   if (hs.error & ERR_OUT_CAPACITY) return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: output does not fit the output buffer", (unsigned long long)s.seq);
   if (hs.error & ERR_REC_TOO_LONG)
     return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: a read pair is longer than the %u bytes one shared-memory stage holds", (unsigned long long)s.seq, ctx->lay.cap);
-  if (hs.error & ERR_HDR_TOO_LONG)
-    return fail(ctx, MGK_ERR_FORMAT, "chunk %llu: a rewritten read header is longer than %u bytes", (unsigned long long)s.seq, HDR_STAGE_MAX);
   if (hs.fmt_record != ~0ull)
     return fail(ctx, MGK_ERR_FORMAT, "chunk %llu, read %llu: lines shorter than the barcode/header layout", (unsigned long long)s.seq, hs.fmt_record);
   const int total = P.total;

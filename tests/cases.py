@@ -91,6 +91,11 @@ def edge_cases():
             "@FC01L1C001R001", "@FC01L1C100R0909", "@FC01L1C010R0010000000000000000000000000007"]
     hp = [pair(i, "AAAAAAAACCCCCCCC", hdr=h) for i, h in enumerate(hdrs)]
     cases.append(("header-zero-stripping", RunSpec(samples=samples, **kw), [chunk(hp)]))
+    # rewritten headers longer than a staging slot take the byte-store path; mixed with normal ones
+    long_hdrs = [f"@FC01L1C{i % 7:03d}R{i % 5:03d}" + "0" * (i % 4) + "1234567890" * (3 + i % 9) for i in range(40)]
+    lp = [pair(i, bars[i % len(bars)], hdr=h) for i, h in enumerate(long_hdrs)]
+    cases.append(("header-longer-than-slot", RunSpec(samples=samples, **kw), [chunk(lp + pairs[:9] + lp[:7])]))
+    cases.append(("header-longer-than-slot-full", RunSpec(samples=samples, out_mode=2, **kw), [chunk(lp + pairs[:9])]))
     # ragged records: every read its own lengths
     rng = np.random.default_rng(5)
     rag = []

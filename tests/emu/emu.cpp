@@ -15,20 +15,6 @@
 
 using namespace mgk;
 
-// the 32 lanes of a warp, looped
-struct WarpEmu {
-  template <class F> void each(F f) const { for (int l = 0; l < 32; ++l) f(l); }
-  void sync() const {}
-  template <class F> uint32_t ballot(F f) const { uint32_t m = 0; for (int l = 0; l < 32; ++l) m |= (f(l) ? 1u : 0u) << l; return m; }
-  template <class F> uint32_t sum(F f) const { uint32_t s = 0; for (int l = 0; l < 32; ++l) s += (uint32_t)f(l); return s; }
-  template <class F> U4 sum4(F f) const {
-    U4 s{0, 0, 0, 0};
-    for (int l = 0; l < 32; ++l) { const U4 v = f(l); s.a += v.a; s.b += v.b; s.c += v.c; s.d += v.d; }
-    return s;
-  }
-  template <class F> int min(F f) const { int m = 0x7fffffff; for (int l = 0; l < 32; ++l) { const int v = f(l); if (v < m) m = v; } return m; }
-};
-
 struct emu_ctx {
   Params P;
   HostTables tb;
@@ -143,8 +129,8 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   // the staged tile: the whole chunk as ONE tile, laid out like the kernel's shared memory
   //   [slack | prefix + literals | header staging | barcode read bytes | paired read bytes | slack]
   const uint32_t cs0 = 64;
-  const uint32_t hs = (cs0 + (uint32_t)c->tb.consts.size() + 31u) / 16u * 16u + 16u;
-  const uint32_t b2 = hs + HDR_STAGE_BYTES + 16u;
+  const uint32_t hs = (cs0 + (uint32_t)c->tb.consts.size() + 31u) / 16u * 16u + 16u;   // two slots: barcode read, paired read
+  const uint32_t b2 = hs + 2u * HDR_SLOT_BYTES + 16u;
   const uint32_t b1 = (b2 + (uint32_t)r2_len + 15u) / 16u * 16u + 16u + (uint32_t)(seq % 3) * 16u;
   const size_t s_bytes = (size_t)b1 + r1_len + 128;
   uint8_t* S = (uint8_t*)aligned_alloc(64, (s_bytes + 63) / 64 * 64);
@@ -152,7 +138,6 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   memcpy(S + cs0, c->tb.consts.data(), c->tb.consts.size());
   memcpy(S + b2, r2, r2_len);
   if (r1_len) memcpy(S + b1, r1, r1_len);
-  const WarpEmu w;
   unsigned long long vkey = ~0ull;
   for (uint32_t i = 0; i < n_rec; ++i) {
     const Rec& R = recs[i];
@@ -161,16 +146,20 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
     uint8_t* d2 = o2 + c->off2[(size_t)R.bin] + R.d2;
     uint8_t* d1 = o1 + c->off1[(size_t)R.bin] + R.d1;
-    const PairOut po = emit_pair(w, P, S, hs, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, d1);
-    if (po.hdr_overflow) { rc = MGK_ERR_FORMAT; c->err = "header too long"; break; }
+    // the three per-record roles of k_emit, one after the other
+    emit_read2(P, S, hs, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2);
+    if (P.paired) emit_read1(P, S, hs + HDR_SLOT_BYTES, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1);
     if (P.report_level > 0) {
+      const QcSix q = qc_pair(P, S, G);
       uint64_t* st = c->stats.data() + (size_t)R.mo.sample * MGK_N_STATS;
-      for (int k = 0; k < QC_SLOTS; ++k)
-        if (P.paired || k >= 2) st[qc_stat_column(k, P.paired)] += po.qc.v[k];
+      for (int k = P.paired ? 0 : 2; k < QC_SLOTS; ++k) st[qc_stat_column(k, P.paired)] += q.v[k];
     }
-    if (po.validate) {
-      const unsigned long long k = ((unsigned long long)i << 4) | (unsigned)po.validate;
-      if (k < vkey) vkey = k;
+    if (P.validate) {
+      const int v = validate_pair(P, S, G);
+      if (v) {
+        const unsigned long long k = ((unsigned long long)i << 4) | (unsigned)v;
+        if (k < vkey) vkey = k;
+      }
     }
   }
   free(S);
