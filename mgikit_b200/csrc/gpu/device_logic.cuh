@@ -17,8 +17,12 @@
 
 #if defined(__CUDACC__)
 #define MGK_HD __host__ __device__ __forceinline__
+#define MGK_HD_NOINLINE __host__ __device__ __noinline__
+#define MGK_LOOP_ROLLED _Pragma("unroll 1")
 #else
 #define MGK_HD inline
+#define MGK_HD_NOINLINE inline
+#define MGK_LOOP_ROLLED
 #endif
 
 namespace mgk {

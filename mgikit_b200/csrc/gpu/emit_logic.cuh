@@ -113,10 +113,28 @@ MGK_HD uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
   return o;
 }
 
-// the LAST n (< 16) bytes of v go to [end - n, end), `end` 16-byte aligned: 8 + 4 + 2 + 1 ladder
-MGK_HD void store_before(uint8_t* end, const uint4& v, uint32_t n) {
-  uint32_t cur = v.w, prev = v.z;
+// 32 bytes to a 32-byte aligned global address: one full DRAM sector per lane per store
+MGK_HD void st_v8(uint8_t* p, const uint4& a, const uint4& b) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+#else
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 16) = b;
+#endif
+}
+
+// the LAST n (< 32) bytes of the 32-byte value (a, b) go to [end - n, end), `end` 32-byte aligned: 16 + 8 + 4 + 2 + 1 ladder
+MGK_HD void store_before(uint8_t* end, const uint4& a, const uint4& b, uint32_t n) {
+  uint4 v = b;
   uint8_t* p = end;
+  if (n & 16u) {
+    p -= 16;
+    st_v4(p, b);
+    v = a;
+  }
+  uint32_t cur = v.w, prev = v.z;
   if (n & 8u) {
     p -= 8;
     uint2 t;
@@ -141,8 +159,14 @@ MGK_HD void store_before(uint8_t* end, const uint4& v, uint32_t n) {
     *p = (uint8_t)(cur >> 24);
   }
 }
-// the FIRST n (< 16) bytes of v go to [p, p + n), p 16-byte aligned
-MGK_HD void store_after(uint8_t* p, const uint4& v, uint32_t n) {
+// the FIRST n (< 32) bytes of (a, b) go to [p, p + n), p 32-byte aligned
+MGK_HD void store_after(uint8_t* p, const uint4& a, const uint4& b, uint32_t n) {
+  uint4 v = a;
+  if (n & 16u) {
+    st_v4(p, a);
+    p += 16;
+    v = b;
+  }
   uint32_t c0 = v.x, c1 = v.y;
   if (n & 8u) {
     uint2 t;
@@ -166,63 +190,100 @@ MGK_HD void store_after(uint8_t* p, const uint4& v, uint32_t n) {
   if (n & 1u) *p = (uint8_t)(c0 & 0xffu);
 }
 
-// This thread writes dst[0 .. n0+n1+n2).  The bulk moves as 16-byte stores ALIGNED
-// ON THE DESTINATION; inside a segment the source is read as a sliding window of
-// aligned 16-byte vectors (one shared-memory load per store).  A unit that
-// straddles a segment boundary is assembled from both sides; the < 16 bytes in
-// front of the first / after the last aligned unit go out as an 8+4+2+1 ladder.
-MGK_HD void copy3(uint8_t* dst, const uint8_t* S, const Seg3& g) {
+// A record's output may be shared by two threads: PART_HEAD takes the bytes in front of the
+// first aligned unit and the first `split` units, PART_TAIL the rest.  Both compute the same
+// split from the same inputs; `own0` leading output bytes (the staged header, which only the
+// head thread can see) are guaranteed to stay in the head part.
+enum { PART_HEAD = 0, PART_TAIL = 1, PART_ALL = 2 };
+
+// This thread writes its part of dst[0 .. n0+n1+n2).  The bulk moves as 32-byte stores ALIGNED
+// ON THE DESTINATION (one whole DRAM sector per store); inside a segment the source is read
+// as a sliding window of aligned 16-byte vectors (two shared-memory loads per store).  The at
+// most four "special" pieces — the < 32 bytes in front of the first aligned unit, the two
+// units that straddle a segment boundary, the < 32 bytes after the last unit — are assembled
+// from both sides of the boundary by ONE copy of the gather-and-merge code (instruction-cache
+// footprint matters: every lane of every emit warp runs this function).
+MGK_HD void copy3(uint8_t* dst, const uint8_t* S, const Seg3& g, int part, uint32_t own0) {
   const uint32_t len = g.n0 + g.n1 + g.n2;
   if (len == 0) return;
   const uint32_t o1 = g.n0, o2 = g.n0 + g.n1;
   const uint32_t b0 = g.s0, b1 = g.s1 - o1, b2 = g.s2 - o2;  // source offset of output byte y in segment j: bj + y
-  uint32_t hb = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  uint32_t hb = (32u - (uint32_t)((uintptr_t)dst & 31u)) & 31u;
   if (hb > len) hb = len;
-  const uint32_t nfull = (len - hb) >> 4;
-  const uint32_t tail0 = hb + (nfull << 4), nt = len - tail0;
-  // 16 output bytes starting at ANY output offset x (may hang over either end of the record)
-  auto unit_at = [&](uint32_t x) {
-    const uint32_t xe = x + 16u;
-    int j = ((int)x >= (int)o2 && g.n2) ? 2 : (((int)x >= (int)o1 && g.n1) ? 1 : 0);   // never an empty segment:
-    if (j == 0 && g.n0 == 0) j = g.n1 ? 1 : 2;                                            // its base offset is meaningless
-    uint4 w = gather16(S, (j == 2 ? b2 : (j == 1 ? b1 : b0)) + x);
-    if (j < 1 && (int)o1 < (int)xe && g.n1) w = merge16(w, gather16(S, b1 + x), (int)(o1 - x));
-    if (j < 2 && (int)o2 < (int)xe && g.n2) w = merge16(w, gather16(S, b2 + x), (int)(o2 - x));
-    return w;
-  };
-  if (hb) {
-    if (nfull == 0 && nt == 0) {   // the whole record sits in front of the first aligned boundary
+  const uint32_t nfull = (len - hb) >> 5;
+  const uint32_t tail0 = hb + (nfull << 5), nt = len - tail0;
+  uint32_t split = (nfull * 3u) >> 3;
+  if (own0 > hb && ((own0 - hb + 31u) >> 5) > split) split = (own0 - hb + 31u) >> 5;
+  if (split > nfull) split = nfull;
+  const uint32_t x_lo = part == PART_TAIL ? hb + (split << 5) : hb;   // whole units of this part: [x_lo, x_hi)
+  const uint32_t x_hi = part == PART_HEAD ? hb + (split << 5) : tail0;
+  if (nfull == 0 && nt == 0) {   // the whole record sits in front of the first aligned boundary
+    if (part != PART_TAIL)
       for (uint32_t y = 0; y < len; ++y) dst[y] = (uint8_t)s_u8(S, (y >= o2 ? b2 : (y >= o1 ? b1 : b0)) + y);
-      return;
-    }
-    store_before(dst + hb, unit_at(hb - 16u), hb);
+    return;
   }
-  uint32_t x = hb;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+  // ---- whole units that lie inside one segment
+  MGK_LOOP_ROLLED
   for (int j = 0; j < 3; ++j) {
     const uint32_t bj = j == 0 ? b0 : (j == 1 ? b1 : b2);
+    const uint32_t beg = j == 0 ? 0u : (j == 1 ? o1 : o2);
     uint32_t end = j == 0 ? o1 : (j == 1 ? o2 : len);
-    if (end > tail0) end = tail0;       // only whole units here
-    if (x + 16u <= end) {
+    if (end > x_hi) end = x_hi;
+    uint32_t x = beg <= hb ? hb : hb + (((beg - hb) + 31u) & ~31u);   // first unit that starts inside the segment
+    if (x < x_lo) x = x_lo;
+    if (x + 32u <= end) {
       const uint32_t addr = bj + x, sh = addr & 15u;
       uint32_t al = addr - sh;
       uint4 lo = s_v4(S, al);
       do {
-        al += 16u;
-        const uint4 hi = s_v4(S, al);
-        st_v4(dst + x, shift16(lo, hi, sh));
+        const uint4 mid = s_v4(S, al + 16u), hi = s_v4(S, al + 32u);
+        al += 32u;
+        st_v8(dst + x, shift16(lo, mid, sh), shift16(mid, hi, sh));
         lo = hi;
-        x += 16u;
-      } while (x + 16u <= end);
-    }
-    if (x < end) {                      // whole unit that leaves segment j
-      st_v4(dst + x, unit_at(x));
-      x += 16u;
+        x += 32u;
+      } while (x + 32u <= end);
     }
   }
-  if (nt) store_after(dst + tail0, unit_at(tail0), nt);
+  // ---- the special pieces: 0 head fragment, 1 / 2 unit across the boundary at o1 / o2, 3 tail fragment
+  const int tail_owner = own0 > tail0 ? PART_HEAD : PART_TAIL;   // a staged header reaching into the tail keeps it in the head part
+  uint32_t done_unit = 0xffffffffu;
+  MGK_LOOP_ROLLED
+  for (int k = 0; k < 4; ++k) {
+    uint32_t x;
+    bool on;
+    if (k == 0) {
+      x = hb - 32u;
+      on = hb != 0u && part != PART_TAIL;
+    } else if (k == 3) {
+      x = tail0;
+      on = nt != 0u && (part == PART_ALL || part == tail_owner);
+    } else {
+      const uint32_t o = k == 1 ? o1 : o2;
+      x = hb + ((o - hb) & ~31u);                       // unit holding output byte o, if o is past the head fragment
+      on = o > hb && o < tail0 && x != o && x >= x_lo && x + 32u <= x_hi && x != done_unit && (k == 1 ? g.n1 + g.n2 : g.n2) != 0u;
+      if (on) done_unit = x;
+    }
+    if (!on) continue;
+    // 2 x 16 output bytes starting at output offset x (may hang over either end of the record)
+    uint4 wa, wb;
+    wa.x = wa.y = wa.z = wa.w = 0;
+    wb = wa;
+    MGK_LOOP_ROLLED
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t xh = x + 16u * (uint32_t)h, xe = xh + 16u;
+      if ((int)xe <= 0 || (int)xh >= (int)len) continue;   // half entirely outside the record
+      int j = ((int)xh >= (int)o2 && g.n2) ? 2 : (((int)xh >= (int)o1 && g.n1) ? 1 : 0);   // never an empty segment:
+      if (j == 0 && g.n0 == 0) j = g.n1 ? 1 : 2;                                             // its base offset is meaningless
+      uint4 w = gather16(S, (j == 2 ? b2 : (j == 1 ? b1 : b0)) + xh);
+      if (j < 1 && (int)o1 < (int)xe && g.n1) w = merge16(w, gather16(S, b1 + xh), (int)(o1 - xh));
+      if (j < 2 && (int)o2 < (int)xe && g.n2) w = merge16(w, gather16(S, b2 + xh), (int)(o2 - xh));
+      if (h == 0) wa = w;
+      else wb = w;
+    }
+    if (k == 0) store_before(dst + hb, wa, wb, hb);
+    else if (k == 3) store_after(dst + tail0, wa, wb, nt);
+    else st_v8(dst + x, wa, wb);
+  }
 }
 
 // ---------------------------------------------------------------- header rewrite
@@ -283,188 +344,144 @@ MGK_HD TailSpec make_tail(const Params& P, const RecGeom& G, int bar_t, int umi_
   return t;
 }
 
-// A header is written front to back through a cursor.  `Sink` is either the
-// per-thread staging slot in S or, for headers too long for the slot, the
-// destination itself (byte stores; correct for any length, just slower).
-struct SlotSink {
-  uint8_t* p;
-  MGK_HD void put(uint32_t v) { *p++ = (uint8_t)v; }
-};
-template <class Sink>
-MGK_HD void put_span(Sink& o, const uint8_t* S, uint32_t src, uint32_t n) {
-  for (uint32_t k = 0; k < n; ++k) o.put(s_u8(S, src + k));
+// A header is written front to back through a cursor `o`: into the (record, read)'s staging
+// slot in S or, for headers too long for the slot, straight to the destination (byte stores;
+// correct for any length, just slower).  ONE out-of-line copy of the byte loop serves every
+// piece: the emit code runs in every warp of the kernel and has to stay small.
+MGK_HD_NOINLINE uint8_t* put_span(uint8_t* o, const uint8_t* S, uint32_t src, uint32_t n) {
+  uint32_t k = 0;
+  MGK_LOOP_ROLLED
+  for (; k + 4u <= n; k += 4u) {   // loads first: the cursor may alias S as far as the compiler knows
+    const uint32_t a = s_u8(S, src + k), b = s_u8(S, src + k + 1u), c = s_u8(S, src + k + 2u), d = s_u8(S, src + k + 3u);
+    o[0] = (uint8_t)a;
+    o[1] = (uint8_t)b;
+    o[2] = (uint8_t)c;
+    o[3] = (uint8_t)d;
+    o += 4;
+  }
+  MGK_LOOP_ROLLED
+  for (; k < n; ++k) *o++ = (uint8_t)s_u8(S, src + k);
+  return o;
 }
-template <class Sink>
-MGK_HD void put_tail(Sink& o, const uint8_t* S, const TailSpec& t, uint32_t n_digit, int full) {
+MGK_HD uint8_t* put_tail(uint8_t* o, const uint8_t* S, const TailSpec& t, uint32_t n_digit, int full) {
   if (full) {
-    o.put(' ');
+    *o++ = ' ';
     if (t.umi_len) {
-      put_span(o, S, t.umi_off, t.umi_len);
-      o.put(' ');
+      o = put_span(o, S, t.umi_off, t.umi_len);
+      *o++ = ' ';
     }
   } else {
     if (t.umi_len) {
-      o.put(':');
-      put_span(o, S, t.umi_off, t.umi_len);
+      *o++ = ':';
+      o = put_span(o, S, t.umi_off, t.umi_len);
     }
-    o.put(' ');
+    *o++ = ' ';
   }
-  o.put(n_digit);
-  o.put(':');
-  o.put('N');
-  o.put(':');
-  o.put('0');
-  o.put(':');
+  *o++ = (uint8_t)n_digit;
+  *o++ = ':';
+  *o++ = 'N';
+  *o++ = ':';
+  *o++ = '0';
+  *o++ = ':';
   if (t.has_bar) {
-    put_span(o, S, t.i7_off, t.i7_len);
+    o = put_span(o, S, t.i7_off, t.i7_len);
     if (t.has_i5) {
-      o.put('+');
-      put_span(o, S, t.i5_off, t.i5_len);
+      *o++ = '+';
+      o = put_span(o, S, t.i5_off, t.i5_len);
     }
   }
+  return o;
 }
 MGK_HD uint32_t illumina_header_len(const Params& P, const RecGeom& G, const HdrInfo& hi, const TailSpec& t) {
   const uint32_t L = (uint32_t)P.L, H = G.h2;
   return (uint32_t)P.prefix_len + 2u + (hi.sep - hi.z) + 1u + (H + L + 6u - hi.f1) + 1u + (H + L + 10u - hi.f2) + tail_len(t, 0);
 }
-// prefix lane ":" readno ":" ccc ":" rrr tail.  `cs0` = S offset of the prefix.
-template <class Sink>
-MGK_HD void put_illumina_header(Sink& o, const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G, const HdrInfo& hi,
-                                const TailSpec& t, uint32_t n_digit) {
-  const uint32_t L = (uint32_t)P.L, H = G.h2;
-  put_span(o, S, cs0, (uint32_t)P.prefix_len);
-  o.put(s_u8(S, H + L + 1u));
-  o.put(':');
-  put_span(o, S, hi.z, hi.sep - hi.z);
-  o.put(':');
-  put_span(o, S, hi.f1, H + L + 6u - hi.f1);
-  o.put(':');
-  put_span(o, S, hi.f2, H + L + 10u - hi.f2);
-  put_tail(o, S, t, n_digit, 0);
+// prefix lane ":" readno ":" ccc ":" rrr tail.  `cs0` = S offset of the prefix; `vec`: the cursor is
+// a 16-byte aligned staging slot, so the constant prefix goes in as whole vectors.
+MGK_HD uint8_t* put_illumina_header(uint8_t* o, bool vec, const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G,
+                                    const HdrInfo& hi, const TailSpec& t, uint32_t n_digit) {
+  const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len;
+  if (vec) {
+    MGK_LOOP_ROLLED
+    for (uint32_t k = 0; k < Pn; k += 16u) *reinterpret_cast<uint4*>(o + k) = s_v4(S, cs0 + k);
+    o += Pn;
+  } else {
+    o = put_span(o, S, cs0, Pn);
+  }
+  *o++ = (uint8_t)s_u8(S, H + L + 1u);
+  *o++ = ':';
+  o = put_span(o, S, hi.z, hi.sep - hi.z);
+  *o++ = ':';
+  o = put_span(o, S, hi.f1, H + L + 6u - hi.f1);
+  *o++ = ':';
+  o = put_span(o, S, hi.f2, H + L + 10u - hi.f2);
+  return put_tail(o, S, t, n_digit, 0);
 }
 
-// ---------------------------------------------------------------- the two emit roles
+// ---------------------------------------------------------------- the emit roles
 constexpr uint32_t HDR_SLOT_BYTES = 96;     // per (record, read) staging slot; longer headers take the byte-store path
-struct GlobalSink {
-  uint8_t* p;
-  MGK_HD void put(uint32_t v) { *p++ = (uint8_t)v; }
-};
-
-// Barcode read of one pair -> d2.  `hs` = this thread's staging slot (S offset, 16-byte aligned).
-MGK_HD void emit_read2(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int sample, int bar_t, int umi_t,
-                       uint8_t* d2) {
+// Every record, matched or not, is cut into the SAME three pieces (header line | sequence
+// line | "+" and quality lines) so that the lanes of a warp, each on its own record, run the
+// copy loops of copy3() in step whatever their records look like; and both reads go through
+// the SAME function so that the four emit roles of the kernel share one set of instructions.
+//
+// which = 2: barcode read -> new header, barcode trimmed off sequence and qualities
+//            (src/lib.rs:1240-1327); unmatched reads verbatim (:1225-1235)
+// which = 1: paired read  -> in illumina mode the barcode read's new header with its own
+//            read-number digit (src/sample_data.rs:302-328, src/lib.rs:1288), the rest of the
+//            record verbatim (:1328-1331); with --mgi-full-header ITS OWN header line (:1306-1318)
+// `hs` = this (record, read)'s staging slot (S offset, 16-byte aligned), written by the
+// PART_HEAD thread only.
+MGK_HD void emit_read(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int which, int sample, int bar_t,
+                      int umi_t, uint8_t* d, int part) {
+  const bool br = which == 2;
+  const uint32_t h = br ? G.h2 : G.h1, s = br ? G.s2 : G.s1, p = br ? G.p2 : G.p1, e = br ? G.e2 : G.e1;
+  const bool matched = sample < P.S;
+  if (br && matched && !P.read2_has_sequence) return;   // samples get no barcode-read file, src/sample_data.rs:35-44
+  const bool trim = br && matched;
+  const uint32_t wbl = (trim && !P.keep_barcode) ? (uint32_t)P.BL : 0u;
   Seg3 g;
-  g.s1 = g.n1 = g.s2 = g.n2 = 0;
-  if (sample >= P.S) {  // verbatim, src/lib.rs:1225-1235
-    g.s0 = G.h2;
-    g.n0 = G.e2 + 1u - G.h2;
-    copy3(d2, S, g);
-    return;
-  }
-  if (!P.read2_has_sequence) return;   // samples get no barcode-read file, src/sample_data.rs:35-44
-  const uint32_t wbl = P.keep_barcode ? 0u : (uint32_t)P.BL;
-  // "\n+\n" qual[..-wbl]; the closing '\n' (src/lib.rs:1324-1327) is stored on its own below
-  const uint32_t qs = G.p2 - 1u, qn = G.e2 - wbl - (G.p2 - 1u);
-  uint32_t len;
-  if (P.out_mode == MGK_OUT_MGI) {
-    g.s0 = G.h2;
-    g.n0 = G.p2 - wbl - 1u - G.h2;   // header line and trimmed sequence are contiguous
-    g.s1 = qs;
-    g.n1 = qn;
-    len = g.n0 + g.n1;
-    copy3(d2, S, g);
-  } else {
+  g.s1 = s - 1u;
+  g.n1 = p - wbl - s;                                   // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
+  g.s2 = p - 1u;
+  g.n2 = trim ? e - wbl - (p - 1u) : e + 2u - p;        // "\n+\n" qual[..-wbl]; a trimmed read's closing '\n' is stored on its own
+  g.s0 = h;
+  g.n0 = s - 1u - h;                                    // the header line as it is
+  uint32_t own0 = 0, skip = 0;
+  if (matched && P.out_mode != MGK_OUT_MGI) {
     const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
     const TailSpec t = make_tail(P, G, bar_t, umi_t);
-    const uint32_t n_digit = s_u8(S, G.s2 - 2u);          // src/lib.rs:1275,1302
+    const uint32_t n_digit = s_u8(S, s - 2u);           // src/lib.rs:1275,1288,1302,1314
     HdrInfo hi;
     uint32_t hl;
     if (full) {
       hi.z = hi.f1 = hi.f2 = hi.sep = 0;
-      hl = G.s2 - G.h2 - 1u + tail_len(t, 1);
+      hl = s - h - 1u + tail_len(t, 1);
     } else {
       hi = hdr_info(P, S, G);
       hl = illumina_header_len(P, G, hi, t);
     }
-    g.s1 = G.s2 - 1u;
-    g.n1 = G.p2 - wbl - 1u - (G.s2 - 1u);                // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
-    g.s2 = qs;
-    g.n2 = qn;
-    if (hl <= HDR_SLOT_BYTES) {
-      SlotSink o{S + hs};
+    const bool slot = hl <= HDR_SLOT_BYTES;
+    if (part != PART_TAIL) {   // too long for the slot: bytes straight to the destination
+      uint8_t* o = slot ? S + hs : d;
       if (full) {
-        put_span(o, S, G.h2, G.s2 - G.h2 - 1u);
+        o = put_span(o, S, h, s - h - 1u);
         put_tail(o, S, t, n_digit, 1);
       } else {
-        put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
+        put_illumina_header(o, slot, P, S, cs0, G, hi, t, n_digit);
       }
+    }
+    if (slot) {
       g.s0 = hs;
       g.n0 = hl;
-      copy3(d2, S, g);
+      own0 = hl;
     } else {
-      GlobalSink o{d2};
-      if (full) {
-        put_span(o, S, G.h2, G.s2 - G.h2 - 1u);
-        put_tail(o, S, t, n_digit, 1);
-      } else {
-        put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
-      }
       g.s0 = g.n0 = 0;
-      copy3(d2 + hl, S, g);
+      skip = hl;
     }
-    len = hl + g.n1 + g.n2;
   }
-  d2[len] = '\n';
-}
-
-// Paired read of one pair -> d1.  In illumina mode its header is the barcode read's new
-// header with its own read-number digit (src/sample_data.rs:302-328, src/lib.rs:1288).
-MGK_HD void emit_read1(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int sample, int bar_t, int umi_t,
-                       uint8_t* d1) {
-  Seg3 g;
-  g.s1 = g.n1 = g.s2 = g.n2 = 0;
-  if (sample >= P.S || P.out_mode == MGK_OUT_MGI) {  // verbatim
-    g.s0 = G.h1;
-    g.n0 = G.e1 + 1u - G.h1;
-    copy3(d1, S, g);
-    return;
-  }
-  const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
-  const TailSpec t = make_tail(P, G, bar_t, umi_t);
-  const uint32_t n_digit = s_u8(S, G.s1 - 2u);           // src/lib.rs:1288,1314
-  HdrInfo hi;
-  uint32_t hl;
-  if (full) {
-    hi.z = hi.f1 = hi.f2 = hi.sep = 0;
-    hl = G.s1 - G.h1 - 1u + tail_len(t, 1);              // the paired read keeps ITS OWN header line, src/lib.rs:1306-1318
-  } else {
-    hi = hdr_info(P, S, G);
-    hl = illumina_header_len(P, G, hi, t);
-  }
-  g.s1 = G.s1 - 1u;
-  g.n1 = G.e1 + 1u - (G.s1 - 1u);                         // src/lib.rs:1328-1331
-  if (hl <= HDR_SLOT_BYTES) {
-    SlotSink o{S + hs};
-    if (full) {
-      put_span(o, S, G.h1, G.s1 - G.h1 - 1u);
-      put_tail(o, S, t, n_digit, 1);
-    } else {
-      put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
-    }
-    g.s0 = hs;
-    g.n0 = hl;
-    copy3(d1, S, g);
-  } else {
-    GlobalSink o{d1};
-    if (full) {
-      put_span(o, S, G.h1, G.s1 - G.h1 - 1u);
-      put_tail(o, S, t, n_digit, 1);
-    } else {
-      put_illumina_header(o, P, S, cs0, G, hi, t, n_digit);
-    }
-    g.s0 = g.n0 = 0;
-    copy3(d1 + hl, S, g);
-  }
+  copy3(d + skip, S, g, part, own0);
+  if (trim && part != PART_HEAD) d[skip + g.n0 + g.n1 + g.n2] = '\n';   // src/lib.rs:1327
 }
 
 // ---------------------------------------------------------------- QC sums out of S
@@ -496,6 +513,7 @@ MGK_HD Qc qc_line(const uint8_t* S, uint32_t start, uint32_t n) {
   const uint32_t nvec = (sh + n + 15u) >> 4;
   const int end = (int)(sh + n);
   qc_add(q, keep16(s_v4(S, al), (int)sh, end));
+  MGK_LOOP_ROLLED
   for (uint32_t v = 1; v + 1u < nvec; ++v) qc_add(q, s_v4(S, al + (v << 4)));
   if (nvec > 1u) qc_add(q, keep16(s_v4(S, al + ((nvec - 1u) << 4)), 0, end - (int)((nvec - 1u) << 4)));
   return q;
@@ -520,21 +538,25 @@ MGK_HD int qc_stat_column(int k, int paired) {
   }
 }
 
-MGK_HD QcSix qc_pair(const Params& P, const uint8_t* S, const RecGeom& G) {
+// which: bit 0 the paired read's slots (0,1), bit 1 the barcode read's (2..5); the others are left 0
+MGK_HD QcSix qc_pair(const Params& P, const uint8_t* S, const RecGeom& G, int which) {
   QcSix r;
   const uint32_t BL = (uint32_t)P.BL;
   Qc q1;
   q1.sum = q1.high = 0;
-  if (P.paired) q1 = qc_line(S, G.q1, G.e1 - G.q1);
+  if (P.paired && (which & 1)) q1 = qc_line(S, G.q1, G.e1 - G.q1);
+  r.v[0] = q1.high;
+  r.v[1] = q1.sum;
+  r.v[2] = r.v[3] = r.v[4] = r.v[5] = 0;
+  if (!(which & 2)) return r;
   const Qc q2 = qc_line(S, G.q2, G.e2 - G.q2);
   uint32_t sb = 0, hb = 0;
+  MGK_LOOP_ROLLED
   for (uint32_t k = 0; k < BL; ++k) {   // the barcode's own qualities
     const uint32_t q = s_u8(S, G.e2 - BL + k);
     sb += q;
     hb += q >= 63u ? 1u : 0u;
   }
-  r.v[0] = q1.high;
-  r.v[1] = q1.sum;
   r.v[2] = hb;
   r.v[3] = sb;
   r.v[4] = q2.high - hb;

@@ -74,6 +74,7 @@ struct ChunkDev {
   Status* status;
   unsigned long long* stats;   // [total][10]   running totals of the context
   unsigned long long* mism;    // [total][2m+2]
+  unsigned long long* prof;    // optional [grid][warps][4] cycle counters of k_emit (MGK_PROFILE=1), else null
 };
 
 // ------------------------------------------------------------------ helpers
@@ -442,7 +443,9 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
 // full-width bulk copies, and every output byte leaves as part of a 16-byte
 // store aligned on its destination (emit3, emit_logic.cuh).
 constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
-constexpr int EMIT_ROLES = 3;                // A barcode read, B paired read, C QC + validate: one thread per (record, role)
+// one thread per (record, role): 0/1 head and tail part of the barcode read, 2/3 of the paired read,
+// 4 QC of the paired read (+ validate), 5 QC of the barcode read
+constexpr int EMIT_ROLES = 6;
 constexpr int EMIT_WORKERS = EMIT_ROLES * EMIT_NMAX;
 constexpr int EMIT_THREADS = EMIT_WORKERS + 32;   // + the producer warp (bulk copies of the next tile)
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
@@ -562,10 +565,10 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       len2 = ((e2 + 15u) & ~15u) - base2;
       len1 = paired ? ((e1 + 15u) & ~15u) - base1 : 0u;
       off1 = (len2 + 127u) & ~127u;
-      if (off1 + len1 + 32u <= lay.cap || lim == r0 + 1u) break;
+      if (off1 + len1 + 64u <= lay.cap || lim == r0 + 1u) break;
       lim = r0 + max(1u, (lim - r0) * 15u / 16u);   // rare: records much longer than the chunk's mean
     }
-    if (off1 + len1 + 32u > lay.cap) {   // one read pair larger than a stage
+    if (off1 + len1 + 64u > lay.cap) {   // one read pair larger than a stage
       atomicOr(&c.status->error, ERR_REC_TOO_LONG);
       d.n = 0;
       next_rec = R1;
@@ -604,17 +607,27 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       }
     }
   };
-  const int role = tid / EMIT_NMAX;            // warp-uniform: 0 A, 1 B, 2 C, 3 producer
+  const int role = tid / EMIT_NMAX;            // warp-uniform; EMIT_ROLES = the producer warp
   const uint32_t i = (uint32_t)(tid % EMIT_NMAX);
-  const uint32_t hs = lay.hdr + hdr_slot(role == 1 ? 1u : 0u, i);
+  const uint32_t hs = lay.hdr + hdr_slot(role >= 2 ? 1u : 0u, i);
 
+  unsigned long long t_wait = 0, t_work = 0, t_bar = 0, t_prod = 0;
   for (uint32_t k = 0;; ++k) {
     const int s = (int)(k & 1u);
+    const long long c0 = c.prof ? clock64() : 0;
     if (warp == PRODUCER_WARP && lane == 0) produce(s ^ 1);
+    const long long c1 = c.prof ? clock64() : 0;
+    t_prod += (unsigned long long)(c1 - c0);
     const StageDesc d = s_desc[s];
     if (d.n == 0) break;
-    if (role < EMIT_ROLES && i < d.n && !(role == 1 && !paired)) {
+    const int val_role = paired ? 4 : 5;   // --validate goes to the QC thread every record has
+    const bool idle = role >= EMIT_ROLES || i >= d.n || (!paired && role >= 2 && role <= 4) ||
+                      (role >= 4 && P.report_level == 0 && !(P.validate && role == val_role));
+    long long c2 = c1;
+    if (!idle) {
       mbar_wait(&s_bar[s], (k >> 1) & 1u);
+      c2 = c.prof ? clock64() : 0;
+      t_wait += (unsigned long long)(c2 - c1);
       unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
       const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
       const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
@@ -643,25 +656,28 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
           }
         }
         const int sample = mt.sample, bin = mt.bin;
-        if (role == 0) {
-          emit_read2(P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, c.out2 + bins[bin] + mt.off2);
-        } else if (role == 1) {
-          emit_read1(P, smem, hs, lay.consts, G, sample, mt.bar_t, mt.umi_t, c.out1 + bins[total + bin] + mt.off1);
+        if (role < 4) {
+          const bool br = role < 2;
+          uint8_t* dst = br ? c.out2 + bins[bin] + mt.off2 : c.out1 + bins[total + bin] + mt.off1;
+          emit_read(P, smem, hs, lay.consts, G, br ? 2 : 1, sample, mt.bar_t, mt.umi_t, dst, role & 1);
         } else {
           if (P.report_level > 0) {   // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
-            const QcSix q = qc_pair(P, smem, G);
+            const QcSix q = qc_pair(P, smem, G, role == 4 ? 1 : 2);
 #pragma unroll
             for (int j = 0; j < QC_SLOTS; ++j)
-              if (q.v[j]) atomicAdd(&s_stats[sample * QC_SLOTS + j], q.v[j]);   // slots 0,1 stay 0 when single-end
+              if (q.v[j]) atomicAdd(&s_stats[sample * QC_SLOTS + j], q.v[j]);
           }
-          if (P.validate) {
+          if (P.validate && role == val_role) {
             const int v = validate_pair(P, smem, G);
             if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)v);
           }
         }
       }
     }
+    const long long c3 = c.prof ? clock64() : 0;
+    t_work += (unsigned long long)(c3 - c2);
     __syncthreads();   // stage s is free again; desc[s^1] is published
+    if (c.prof) t_bar += (unsigned long long)(clock64() - c3);
     if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {
       flush_stats();
       __syncthreads();
@@ -669,6 +685,13 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
   __syncthreads();
   if (P.report_level > 0) flush_stats();
+  if (c.prof && lane == 0) {
+    unsigned long long* o = c.prof + ((size_t)blockIdx.x * (EMIT_THREADS / 32) + warp) * 4;
+    o[0] = t_wait;
+    o[1] = t_work;
+    o[2] = t_bar;
+    o[3] = t_prod;
+  }
 }
 
 // ------------------------------------------------------------------ stage kernels (parity tests)

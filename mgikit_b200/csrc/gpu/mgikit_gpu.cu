@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -55,7 +56,7 @@ struct mgk_ctx {
   uint64_t* d_codes = nullptr;
   int32_t *d_pairs = nullptr, *d_xlat = nullptr, *d_writing = nullptr;
   uint8_t* d_consts = nullptr;
-  unsigned long long *d_stats = nullptr, *d_mism = nullptr;
+  unsigned long long *d_stats = nullptr, *d_mism = nullptr, *d_prof = nullptr;
   Status* h_status_init = nullptr;
   int total = 0, mism_w = 0;
   uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
@@ -157,6 +158,18 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->d_prof) {   // last k_emit launch: mean cycles per warp index over the CTAs
+    const int nw = EMIT_THREADS / 32;
+    std::vector<unsigned long long> h((size_t)ctx->n_sm * nw * 4);
+    cudaMemcpy(h.data(), ctx->d_prof, h.size() * 8, cudaMemcpyDeviceToHost);
+    for (int w = 0; w < nw; ++w) {
+      double a[4] = {0, 0, 0, 0};
+      for (int b = 0; b < ctx->n_sm; ++b)
+        for (int k = 0; k < 4; ++k) a[k] += (double)h[((size_t)b * nw + w) * 4 + k] / ctx->n_sm;
+      fprintf(stderr, "[mgk profile] k_emit warp %2d: wait %.0f work %.0f barrier %.0f produce %.0f cycles\n", w, a[0], a[1], a[2], a[3]);
+    }
+    cudaFree(ctx->d_prof);
+  }
   for (auto& s : ctx->slots) free_slot(s);
   cudaFree(ctx->d_params); cudaFree(ctx->d_codes); cudaFree(ctx->d_pairs); cudaFree(ctx->d_xlat);
   cudaFree(ctx->d_writing); cudaFree(ctx->d_consts); cudaFree(ctx->d_stats); cudaFree(ctx->d_mism);
@@ -297,6 +310,10 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     ctx->grid_emit = ctx->n_sm;
   }
 
+  if (getenv("MGK_PROFILE")) {   // developer aid: per-warp cycle counters of k_emit, dumped at destroy
+    CUC(dalloc(&ctx->d_prof, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 4));
+    CUC(cudaMemset(ctx->d_prof, 0, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 4 * 8));
+  }
   CUC(cudaEventCreate(&ctx->span_begin));
   CUC(cudaEventCreate(&ctx->span_end));
   CUC(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status_init), sizeof(Status), cudaHostAllocDefault));
@@ -351,6 +368,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     c.out_cap2 = ctx->out_cap; c.out_cap1 = ctx->out_cap;
     c.unassigned = s.unassigned; c.status = s.status;
     c.stats = ctx->d_stats; c.mism = ctx->d_mism;
+    c.prof = ctx->d_prof;
   }
 #undef CUC
 #undef BAD

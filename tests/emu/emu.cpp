@@ -146,11 +146,22 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
     uint8_t* d2 = o2 + c->off2[(size_t)R.bin] + R.d2;
     uint8_t* d1 = o1 + c->off1[(size_t)R.bin] + R.d1;
-    // the three per-record roles of k_emit, one after the other
-    emit_read2(P, S, hs, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2);
-    if (P.paired) emit_read1(P, S, hs + HDR_SLOT_BYTES, cs0, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1);
+    // the per-record roles of k_emit, one after the other: every third record in one piece, the others
+    // head part and tail part like the two threads that share a record on the GPU
+    if (i % 3 == 2) {
+      emit_read(P, S, hs, cs0, G, 2, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, PART_ALL);
+      if (P.paired) emit_read(P, S, hs + HDR_SLOT_BYTES, cs0, G, 1, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1, PART_ALL);
+    } else {
+      const int first = i % 3 == 0 ? PART_HEAD : PART_TAIL;   // the two parts are independent: either order
+      for (int part : {first, 1 - first}) {
+        emit_read(P, S, hs, cs0, G, 2, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, part);
+        if (P.paired) emit_read(P, S, hs + HDR_SLOT_BYTES, cs0, G, 1, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1, part);
+      }
+    }
     if (P.report_level > 0) {
-      const QcSix q = qc_pair(P, S, G);
+      QcSix q = qc_pair(P, S, G, 1);
+      const QcSix qb = qc_pair(P, S, G, 2);
+      for (int k = 2; k < QC_SLOTS; ++k) q.v[k] = qb.v[k];
       uint64_t* st = c->stats.data() + (size_t)R.mo.sample * MGK_N_STATS;
       for (int k = P.paired ? 0 : 2; k < QC_SLOTS; ++k) st[qc_stat_column(k, P.paired)] += q.v[k];
     }
