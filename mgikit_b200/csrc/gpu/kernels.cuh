@@ -24,8 +24,9 @@
 namespace mgk {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_BYTES_PER_THREAD = 64;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_BYTES_PER_THREAD;  // 16 KiB of text per CTA
+constexpr int SCAN_ROWS = 4;                                      // 16-byte vectors per thread and tile
+constexpr int SCAN_TILE = SCAN_THREADS * 16 * SCAN_ROWS;         // 16 KiB of text per stage
+constexpr int SCAN_STAGES = 6;                                    // bulk copies in flight per CTA
 constexpr int TILE_RECORDS = 256;                                // read pairs per K2/K4 tile
 constexpr int GROUP_TILES = 64;                                  // tiles per scan group
 
@@ -58,9 +59,10 @@ struct ChunkDev {
   uint32_t* nl2;
   uint32_t* nl1;
   uint32_t nl_cap, max_records;
-  unsigned long long* look2;   // decoupled look-back state per scan tile
-  unsigned long long* look1;
-  uint32_t* tickets;           // [2] dynamic tile ids
+  uint32_t* stg2;              // newline positions as found, one run per scan CTA (scan_cap entries each)
+  uint32_t* stg1;
+  uint32_t* range_counts;      // [2][scan_grid] newlines found by each scan CTA
+  uint32_t scan_grid, scan_cap;
   uint32_t* counts;            // [2] newline totals
   RecMeta* meta;
   uint32_t* tile_bins;         // [tiles][bins_stride]: bytes, then absolute offsets (rows 16-byte aligned)
@@ -105,117 +107,173 @@ __device__ __forceinline__ void copy_params_to_smem(T* dst, const T* src) {
   for (uint32_t i = threadIdx.x; i < sizeof(T) / 4; i += blockDim.x) d[i] = s[i];
 }
 
+// ------------------------------------------------------------------ TMA / mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map): 16-byte aligned both sides, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+
 // ------------------------------------------------------------------ K1
-// grid = (tiles of the longer stream, 2 streams).  Tile ids are taken from a
-// ticket so that look-back only ever waits on CTAs that are already running.
+// Newline scan without any inter-CTA dependency.  grid = (scan_grid, files), every CTA
+// owns ONE contiguous range of its stream and walks it through a ring of shared-memory
+// stages that the TMA engine keeps full (cp.async.bulk + mbarrier), so the bytes in
+// flight per SM are set by the ring depth, not by registers or by how long a CTA waits.
+// The index of a newline inside its range needs only the CTA's own running count; the
+// positions go to a per-range run of a staging array and k_gather_newlines then packs
+// the runs into the final table (32 B per read pair, L2-resident) once the per-range
+// totals are known.  Order inside a warp's 2 KiB: (row, lane), lane l = bytes 16l..16l+15.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int n_files) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_full[SCAN_STAGES];
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const int file = blockIdx.y;
   if (file >= n_files) return;
   const uint8_t* __restrict__ buf = file == 0 ? c.r2 : c.r1;
   const uint32_t len = file == 0 ? c.len2 : c.len1;
-  uint32_t* __restrict__ nl = file == 0 ? c.nl2 : c.nl1;
-  unsigned long long* look = file == 0 ? c.look2 : c.look1;
+  uint32_t* __restrict__ out = (file == 0 ? c.stg2 : c.stg1) + (size_t)blockIdx.x * c.scan_cap;
   const uint32_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
-  if (blockIdx.x >= ntiles) return;
-
-  __shared__ uint32_t s_tile, s_excl;
-  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-  if (threadIdx.x == 0) s_tile = atomicAdd(&c.tickets[file], 1u);
+  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t0 = min(blockIdx.x * per, ntiles), t1 = min(t0 + per, ntiles);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_BYTES_PER_THREAD;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto issue = [&](uint32_t t) {   // thread 0: tile t -> stage (t - t0) % SCAN_STAGES
+    const int s = (int)((t - t0) % SCAN_STAGES);
+    const uint32_t off = t * SCAN_TILE;
+    const uint32_t bytes = (min(len - off, (uint32_t)SCAN_TILE) + 15u) & ~15u;   // chunk buffers are padded
+    mbar_expect_tx(&s_full[s], bytes);
+    bulk_g2s(smem + (size_t)s * SCAN_TILE, buf + off, bytes, &s_full[s]);
+  };
+  if (tid == 0)
+    for (uint32_t t = t0; t < t1 && t < t0 + SCAN_STAGES; ++t) issue(t);
 
-  uint32_t f[16];
-  uint32_t cnt = 0;
+  uint32_t run = 0;   // newlines of this range so far
+  bool overflow = false;
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint32_t it = t - t0;
+    const int s = (int)(it % SCAN_STAGES);
+    mbar_wait(&s_full[s], (it / SCAN_STAGES) & 1u);
+    const unsigned char* st = smem + (size_t)s * SCAN_TILE;
+    const uint32_t wbase = t * SCAN_TILE + (uint32_t)warp * (512u * SCAN_ROWS) + 16u * (uint32_t)lane;
+    uint32_t m[SCAN_ROWS];   // one bit per byte of the lane's vector
+    uint32_t cp[SCAN_ROWS / 2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t off = base + 16u * j;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (off < len) v = __ldg(reinterpret_cast<const uint4*>(buf + off));
-    uint32_t w[4] = {nl_flags(v.x), nl_flags(v.y), nl_flags(v.z), nl_flags(v.w)};
-    if (off >= len) {
-      w[0] = w[1] = w[2] = w[3] = 0;
-    } else if (off + 16u > len) {  // last, partial vector of the stream
+    for (int j = 0; j < SCAN_ROWS; ++j) {
+      const uint32_t off = wbase + 512u * j;
+      const uint4 v = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE));
+      uint32_t f0 = nl_flags(v.x), f1 = nl_flags(v.y), f2 = nl_flags(v.z), f3 = nl_flags(v.w);
+      // 0x80 flags of a word -> 4 bits
+      uint32_t mm = (((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | ((((f1 >> 7) * 0x00204081u) >> 21 & 0xfu) << 4) |
+                    ((((f2 >> 7) * 0x00204081u) >> 21 & 0xfu) << 8) | ((((f3 >> 7) * 0x00204081u) >> 21 & 0xfu) << 12);
+      if (off + 16u > len) mm = off >= len ? 0u : mm & ((1u << (len - off)) - 1u);   // bytes beyond the stream
+      m[j] = mm;
+      const uint32_t n = (uint32_t)__popc(mm);
+      if ((j & 1) == 0) cp[j / 2] = n;
+      else cp[j / 2] += n << 16;
+    }
+    uint32_t ip[SCAN_ROWS / 2];   // inclusive scan over the lanes, two rows per register (a row holds at most 512)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int nb = (int)(len - off) - 4 * k;
-        if (nb <= 0) w[k] = 0;
-        else if (nb < 4) w[k] &= (1u << (8 * nb)) - 1u;
+    for (int h = 0; h < SCAN_ROWS / 2; ++h) ip[h] = cp[h];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int h = 0; h < SCAN_ROWS / 2; ++h) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, ip[h], d);
+        if (lane >= d) ip[h] += x;
       }
     }
+    uint32_t rowbase[SCAN_ROWS];  // newlines of this warp in the rows before row j
+    uint32_t wtotal = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      f[4 * j + k] = w[k];
-      cnt += __popc(w[k]);
+    for (int h = 0; h < SCAN_ROWS / 2; ++h) {
+      const uint32_t x = __shfl_sync(0xffffffffu, ip[h], 31);
+      rowbase[2 * h] = wtotal;
+      wtotal += x & 0xffffu;
+      rowbase[2 * h + 1] = wtotal;
+      wtotal += x >> 16;
     }
-  }
-  // block exclusive scan of cnt
-  uint32_t incl = cnt;
+    if (lane == 0) s_warp[warp] = wtotal;
+    __syncthreads();   // every thread has read its part of stage s; s_warp is complete
+    uint32_t warp_off = 0, agg = 0;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  uint32_t warp_off = 0, agg = 0;
-#pragma unroll
-  for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) {
-    const uint32_t t = s_warp[wi];
-    if (wi < warp) warp_off += t;
-    agg += t;
-  }
-  // decoupled look-back: status word = flag << 32 | value; flag 1 aggregate, 2 inclusive prefix
-  if (warp == 0) {
-    uint32_t excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_relaxed(&look[0], (2ull << 32) | agg);
-    } else {
-      if (lane == 0) st_relaxed(&look[tile], (1ull << 32) | agg);
-      int look_at = (int)tile - 1;
-      for (;;) {
-        const int idx = look_at - lane;
-        unsigned long long st = (2ull << 32);  // before the first tile: prefix 0
-        if (idx >= 0) {
-          do {
-            st = ld_relaxed(&look[idx]);
-          } while ((st >> 32) == 0);
-        }
-        const uint32_t flag = (uint32_t)(st >> 32), val = (uint32_t)st;
-        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
-        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest tile that already has its prefix
-        uint32_t contrib = lane <= stop ? val : 0u;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-        excl += contrib;
-        if (pmask) break;
-        look_at -= 32;
-      }
-      if (lane == 0) st_relaxed(&look[tile], (2ull << 32) | (excl + agg));
+    for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) {
+      const uint32_t x = s_warp[wi];
+      if (wi < warp) warp_off += x;
+      agg += x;
     }
-    if (lane == 0) {
-      s_excl = excl;
-      if (tile == ntiles - 1) c.counts[file] = excl + agg;
-    }
-  }
-  __syncthreads();
-  uint32_t idx = s_excl + warp_off + incl - cnt;
-  if (cnt) {
-    bool overflow = false;
+    if (tid == 0 && t + SCAN_STAGES < t1) issue(t + SCAN_STAGES);   // stage s is free again
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      uint32_t w = f[k];
-      while (w) {
-        const int b = __ffs(w) - 1;
-        w &= w - 1;
-        if (idx < c.nl_cap) nl[idx] = base + 4u * k + (uint32_t)(b >> 3);
+    for (int j = 0; j < SCAN_ROWS; ++j) {
+      uint32_t mm = m[j];
+      if (mm == 0) continue;
+      const uint32_t cj = (cp[j / 2] >> (16 * (j & 1))) & 0xffffu, ij = (ip[j / 2] >> (16 * (j & 1))) & 0xffffu;
+      uint32_t idx = run + warp_off + rowbase[j] + ij - cj;
+      const uint32_t off = wbase + 512u * j;
+      while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (idx < c.scan_cap) out[idx] = off + (uint32_t)b;
         else overflow = true;
         ++idx;
       }
     }
-    if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
+    run += agg;
+    __syncthreads();   // s_warp may be rewritten
   }
+  if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
+  if (tid == 0) c.range_counts[(size_t)file * gridDim.x + blockIdx.x] = run;
+}
+
+// Packs the per-range runs into the final newline table and leaves the total in counts[file].
+__global__ void __launch_bounds__(256) k_gather_newlines(ChunkDev c, int n_files) {
+  __shared__ uint32_t s_prefix;
+  const int file = blockIdx.y;
+  if (file >= n_files) return;
+  const uint32_t* rc = c.range_counts + (size_t)file * gridDim.x;
+  if (threadIdx.x < 32) {
+    uint32_t sum = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += 32u) sum += rc[i];
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (threadIdx.x == 0) s_prefix = sum;
+  }
+  __syncthreads();
+  const uint32_t prefix = s_prefix, n = min(rc[blockIdx.x], c.scan_cap);
+  const uint32_t* __restrict__ src = (file == 0 ? c.stg2 : c.stg1) + (size_t)blockIdx.x * c.scan_cap;
+  uint32_t* __restrict__ nl = file == 0 ? c.nl2 : c.nl1;
+  bool overflow = false;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    if (prefix + i < c.nl_cap) nl[prefix + i] = src[i];
+    else overflow = true;
+  }
+  if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) c.counts[file] = prefix + rc[blockIdx.x];   // every newline, stored or not
 }
 
 // ------------------------------------------------------------------ K2
@@ -475,33 +533,6 @@ struct StageDesc {
   uint32_t off1;          // where the paired read starts inside the stage's byte area
   uint32_t pad[3];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "W_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra D_%=;\n"
-      "bra W_%=;\n"
-      "D_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA engine, no tensor map): 16-byte aligned both sides, size % 16 == 0
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restrict__ Pg, ChunkDev c, EmitLayout lay) {
   extern __shared__ __align__(128) unsigned char smem[];

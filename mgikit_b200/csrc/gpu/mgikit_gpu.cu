@@ -34,7 +34,8 @@ struct Slot {
   // device
   uint8_t *d_r2 = nullptr, *d_r1 = nullptr, *out2 = nullptr, *out1 = nullptr;
   uint32_t *nl2 = nullptr, *nl1 = nullptr, *ctrl = nullptr, *tile_bins = nullptr, *group_sums = nullptr, *unassigned = nullptr;
-  unsigned long long *look2 = nullptr, *look1 = nullptr, *seg = nullptr;
+  uint32_t *stg2 = nullptr, *stg1 = nullptr;
+  unsigned long long* seg = nullptr;
   RecMeta* meta = nullptr;
   Status* status = nullptr;
   // pinned host
@@ -60,7 +61,7 @@ struct mgk_ctx {
   Status* h_status_init = nullptr;
   int total = 0, mism_w = 0;
   uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
-  uint32_t scan_tiles_max = 0, tiles_max = 0, groups_max = 0;
+  uint32_t scan_grid = 0, scan_cap = 0, tiles_max = 0, groups_max = 0;
   size_t match_smem = 0;
   int grid_match = 0, grid_emit = 0, n_sm = 0;
   uint32_t bins_stride = 0;
@@ -100,7 +101,7 @@ cudaError_t dalloc(T** p, size_t n) {
 void free_slot(Slot& s) {
   cudaFree(s.d_r2); cudaFree(s.d_r1); cudaFree(s.out2); cudaFree(s.out1);
   cudaFree(s.nl2); cudaFree(s.nl1); cudaFree(s.ctrl); cudaFree(s.tile_bins); cudaFree(s.group_sums);
-  cudaFree(s.unassigned); cudaFree(s.look2); cudaFree(s.look1); cudaFree(s.seg); cudaFree(s.meta); cudaFree(s.status);
+  cudaFree(s.unassigned); cudaFree(s.stg2); cudaFree(s.stg1); cudaFree(s.seg); cudaFree(s.meta); cudaFree(s.status);
   cudaFreeHost(s.h_out2); cudaFreeHost(s.h_out1); cudaFreeHost(s.h_status); cudaFreeHost(s.h_seg); cudaFreeHost(s.h_unassigned);
   for (auto& e : s.ev) if (e) cudaEventDestroy(e);
   if (s.ev_status) cudaEventDestroy(s.ev_status);
@@ -264,7 +265,12 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   const uint64_t growth = (uint64_t)P.prefix_len + 2ull * P.BL + 32ull;
   ctx->out_cap = ctx->cap_bytes + ctx->cap_records * growth;
   if (ctx->out_cap >= (1ull << 32) - 4096) BAD("mgk_create: chunk capacity too large for 32-bit output offsets; lower max_chunk_bytes");
-  ctx->scan_tiles_max = (uint32_t)((ctx->cap_bytes + SCAN_TILE - 1) / SCAN_TILE) + 1;
+  // newline scan: one CTA per SM and stream, each with its own run of the staging array.  A run holds four times
+  // the mean share of a range plus a whole stage of newlines; lanes whose newline density is more skewed than
+  // that are refused (MGK_ERR_CAPACITY), real FASTQ is nowhere near.
+  ctx->scan_grid = (uint32_t)ctx->n_sm;
+  ctx->scan_cap = (uint32_t)((4 * (ctx->cap_records * 4 + 4)) / ctx->scan_grid + SCAN_TILE + 64) & ~3u;
+  CUC(cudaFuncSetAttribute(k_scan_newlines, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_STAGES * SCAN_TILE));
   ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
   ctx->groups_max = (ctx->tiles_max + GROUP_TILES - 1) / GROUP_TILES;
   ctx->match_smem = (size_t)P.n_codes * 8 + (size_t)2 * P.total * 4 + 16;
@@ -341,9 +347,9 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
       CUC(dalloc(&s.nl1, ctx->cap_records * 4 + 16));
       CUC(cudaMemcpy(s.nl1, nl_sentinel, sizeof nl_sentinel, cudaMemcpyHostToDevice));
     }
-    CUC(dalloc(&s.look2, (size_t)ctx->scan_tiles_max));
-    CUC(dalloc(&s.look1, (size_t)ctx->scan_tiles_max));
-    CUC(dalloc(&s.ctrl, 8));
+    CUC(dalloc(&s.stg2, (size_t)ctx->scan_grid * ctx->scan_cap));
+    if (P.paired) CUC(dalloc(&s.stg1, (size_t)ctx->scan_grid * ctx->scan_cap));
+    CUC(dalloc(&s.ctrl, 8 + 2 * (size_t)ctx->scan_grid));
     CUC(dalloc(&s.meta, ctx->cap_records + 1));
     CUC(dalloc(&s.tile_bins, (size_t)ctx->tiles_max * ctx->bins_stride));
     CUC(dalloc(&s.group_sums, (size_t)ctx->groups_max * B2));
@@ -361,8 +367,9 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     c.bins_stride = ctx->bins_stride;
     c.nl_cap = (uint32_t)(ctx->cap_records * 4 + 4);
     c.max_records = (uint32_t)ctx->cap_records;
-    c.look2 = s.look2; c.look1 = s.look1;
-    c.tickets = s.ctrl; c.counts = s.ctrl + 2;
+    c.stg2 = s.stg2; c.stg1 = s.stg1;
+    c.scan_grid = ctx->scan_grid; c.scan_cap = ctx->scan_cap;
+    c.counts = s.ctrl; c.range_counts = s.ctrl + 8;
     c.meta = s.meta; c.tile_bins = s.tile_bins; c.group_sums = s.group_sums; c.seg = s.seg;
     c.out2 = s.out2; c.out1 = s.out1;
     c.out_cap2 = ctx->out_cap; c.out_cap1 = ctx->out_cap;
@@ -420,16 +427,13 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
     c.r2 = s.d_r2;
     c.r1 = s.d_r1;
   }
-  CU(cudaMemsetAsync(s.ctrl, 0, 8 * sizeof(uint32_t), st));
   CU(cudaMemcpyAsync(s.status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice, st));
-  const uint32_t t2 = (uint32_t)((r2_len + SCAN_TILE - 1) / SCAN_TILE), t1 = (uint32_t)((r1_len + SCAN_TILE - 1) / SCAN_TILE);
-  if (t2) CU(cudaMemsetAsync(s.look2, 0, (size_t)t2 * 8, st));
-  if (t1) CU(cudaMemsetAsync(s.look1, 0, (size_t)t1 * 8, st));
   CU(cudaEventRecord(s.ev[1], st));  // [0..1): input copy
-  const uint32_t tmax = t2 > t1 ? t2 : t1;
-  if (tmax) {
-    k_scan_newlines<<<dim3(tmax, P.paired ? 2 : 1), SCAN_THREADS, 0, st>>>(c, P.paired ? 2 : 1);
-    ++ctx->launches;
+  {
+    const dim3 grid(ctx->scan_grid, P.paired ? 2 : 1);
+    k_scan_newlines<<<grid, SCAN_THREADS, SCAN_STAGES * SCAN_TILE, st>>>(c, P.paired ? 2 : 1);
+    k_gather_newlines<<<grid, 256, 0, st>>>(c, P.paired ? 2 : 1);
+    ctx->launches += 2;
   }
   CU(cudaEventRecord(s.ev[2], st));
   // the grids below are sized from the byte length (a record is >= 8 bytes); the kernels
@@ -664,13 +668,13 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
   if (!ctx || (!buf && len) || !count || len >= (1ull << 31)) return MGK_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
   uint8_t* d_buf = nullptr;
-  uint32_t *d_nl = nullptr, *d_ctrl = nullptr;
-  unsigned long long* d_look = nullptr;
+  uint32_t *d_nl = nullptr, *d_ctrl = nullptr, *d_stg = nullptr;
   Status* d_status = nullptr;
-  const uint32_t tiles = (uint32_t)((len + SCAN_TILE - 1) / SCAN_TILE);
+  const uint32_t grid = ctx->scan_grid;
+  const uint64_t tiles = (len + SCAN_TILE - 1) / SCAN_TILE, per = (tiles + grid - 1) / grid;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(per * SCAN_TILE + 4, 0xfffffff0u);   // a range cannot hold more newlines than bytes
   int rc = MGK_OK;
-  Status hs;
-  uint32_t h_ctrl[8] = {0};
+  std::vector<uint32_t> h_ctrl(8 + grid, 0);
   do {
 #define TRY(call)                                                                  \
   if ((call) != cudaSuccess) {                                                     \
@@ -679,35 +683,34 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
   }
     TRY(dalloc(&d_buf, len + 256));
     TRY(dalloc(&d_nl, capacity + 4));
-    TRY(dalloc(&d_ctrl, 8));
-    TRY(dalloc(&d_look, (size_t)tiles + 1));
+    TRY(dalloc(&d_stg, (size_t)grid * cap));
+    TRY(dalloc(&d_ctrl, 8 + (size_t)grid));
     TRY(dalloc(&d_status, 1));
     TRY(cudaMemcpy(d_buf, buf, len, cudaMemcpyHostToDevice));
-    TRY(cudaMemset(d_ctrl, 0, 32));
-    TRY(cudaMemset(d_look, 0, ((size_t)tiles + 1) * 8));
+    TRY(cudaMemset(d_ctrl, 0, (8 + (size_t)grid) * 4));
     TRY(cudaMemcpy(d_status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice));
     ChunkDev c{};
     c.r2 = d_buf;
     c.len2 = (uint32_t)len;
     c.nl2 = d_nl;
     c.nl_cap = (uint32_t)std::min<uint64_t>(capacity, 0xffffffffu);
-    c.look2 = d_look;
-    c.tickets = d_ctrl;
-    c.counts = d_ctrl + 2;
+    c.stg2 = d_stg;
+    c.scan_grid = grid;
+    c.scan_cap = cap;
+    c.counts = d_ctrl;
+    c.range_counts = d_ctrl + 8;
     c.status = d_status;
-    if (tiles) {
-      k_scan_newlines<<<dim3(tiles, 1), SCAN_THREADS>>>(c, 1);
-      ++ctx->launches;
-    }
+    k_scan_newlines<<<dim3(grid, 1), SCAN_THREADS, SCAN_STAGES * SCAN_TILE>>>(c, 1);
+    k_gather_newlines<<<dim3(grid, 1), 256>>>(c, 1);
+    ctx->launches += 2;
     TRY(cudaDeviceSynchronize());
-    TRY(cudaMemcpy(h_ctrl, d_ctrl, 32, cudaMemcpyDeviceToHost));
-    TRY(cudaMemcpy(&hs, d_status, sizeof hs, cudaMemcpyDeviceToHost));
-    *count = h_ctrl[2];
+    TRY(cudaMemcpy(h_ctrl.data(), d_ctrl, 32, cudaMemcpyDeviceToHost));
+    *count = h_ctrl[0];
     const uint64_t ncopy = std::min<uint64_t>(*count, capacity);
     if (ncopy) TRY(cudaMemcpy(positions, d_nl, ncopy * 4, cudaMemcpyDeviceToHost));
     if (*count > capacity) rc = fail(ctx, MGK_ERR_CAPACITY, "mgk_scan_newlines: %llu newlines, capacity %llu", (unsigned long long)*count, (unsigned long long)capacity);
   } while (0);
-  cudaFree(d_buf); cudaFree(d_nl); cudaFree(d_ctrl); cudaFree(d_look); cudaFree(d_status);
+  cudaFree(d_buf); cudaFree(d_nl); cudaFree(d_ctrl); cudaFree(d_stg); cudaFree(d_status);
   return rc;
 }
 
