@@ -24,9 +24,9 @@
 namespace mgk {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ROWS = 4;                                      // 16-byte vectors per thread and tile
-constexpr int SCAN_TILE = SCAN_THREADS * 16 * SCAN_ROWS;         // 16 KiB of text per stage
-constexpr int SCAN_STAGES = 6;                                    // bulk copies in flight per CTA
+constexpr int SCAN_ROWS = 2;                                      // 32-byte pieces per thread and tile
+constexpr int SCAN_TILE = SCAN_THREADS * 32 * SCAN_ROWS;         // 16 KiB of text per stage
+constexpr int SCAN_STAGES = 4;                                    // bulk copies in flight per CTA (3 CTAs per SM)
 constexpr int TILE_RECORDS = 256;                                // read pairs per K2/K4 tile
 constexpr int GROUP_TILES = 64;                                  // tiles per scan group
 
@@ -148,7 +148,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int n_files) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_full[SCAN_STAGES];
-  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  __shared__ uint32_t s_warp[2][SCAN_THREADS / 32];
   const int file = blockIdx.y;
   if (file >= n_files) return;
   const uint8_t* __restrict__ buf = file == 0 ? c.r2 : c.r1;
@@ -181,50 +181,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int 
     const int s = (int)(it % SCAN_STAGES);
     mbar_wait(&s_full[s], (it / SCAN_STAGES) & 1u);
     const unsigned char* st = smem + (size_t)s * SCAN_TILE;
-    const uint32_t wbase = t * SCAN_TILE + (uint32_t)warp * (512u * SCAN_ROWS) + 16u * (uint32_t)lane;
-    uint32_t m[SCAN_ROWS];   // one bit per byte of the lane's vector
-    uint32_t cp[SCAN_ROWS / 2];
+    // a warp's 2 KiB: SCAN_ROWS rows of 1 KiB, lane l = bytes 32l..32l+31 of the row
+    const uint32_t wbase = t * SCAN_TILE + (uint32_t)warp * (1024u * SCAN_ROWS) + 32u * (uint32_t)lane;
+    const bool last_tile = t * SCAN_TILE + SCAN_TILE > len;   // only the stream's last tile holds bytes beyond len
+    uint32_t m[SCAN_ROWS];   // bit p set <=> byte p of the lane's 32 bytes is a newline
+    uint32_t cp = 0;         // newline counts of the rows, 16 bits each (a row holds at most 1024)
 #pragma unroll
     for (int j = 0; j < SCAN_ROWS; ++j) {
-      const uint32_t off = wbase + 512u * j;
-      const uint4 v = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE));
-      uint32_t f0 = nl_flags(v.x), f1 = nl_flags(v.y), f2 = nl_flags(v.z), f3 = nl_flags(v.w);
-      // 0x80 flags of a word -> 4 bits
-      uint32_t mm = (((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | ((((f1 >> 7) * 0x00204081u) >> 21 & 0xfu) << 4) |
-                    ((((f2 >> 7) * 0x00204081u) >> 21 & 0xfu) << 8) | ((((f3 >> 7) * 0x00204081u) >> 21 & 0xfu) << 12);
-      if (off + 16u > len) mm = off >= len ? 0u : mm & ((1u << (len - off)) - 1u);   // bytes beyond the stream
+      const uint32_t off = wbase + 1024u * j;
+      const uint4 va = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE));
+      const uint4 vb = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE) + 16u);
+      // 0x80 flags of a word -> 4 bits at the top of the product (no two partial products meet, so no carries)
+      const uint32_t C = 0x00204081u;
+      uint32_t mm = ((nl_flags(va.x) * C) >> 28) | (((nl_flags(va.y) * C) >> 24) & 0xf0u) | (((nl_flags(va.z) * C) >> 20) & 0xf00u) |
+                    (((nl_flags(va.w) * C) >> 16) & 0xf000u) | (((nl_flags(vb.x) * C) >> 12) & 0xf0000u) |
+                    (((nl_flags(vb.y) * C) >> 8) & 0xf00000u) | (((nl_flags(vb.z) * C) >> 4) & 0xf000000u) |
+                    ((nl_flags(vb.w) * C) & 0xf0000000u);
+      if (last_tile && off + 32u > len) mm = off >= len ? 0u : mm & ((1u << (len - off)) - 1u);   // bytes beyond the stream
       m[j] = mm;
-      const uint32_t n = (uint32_t)__popc(mm);
-      if ((j & 1) == 0) cp[j / 2] = n;
-      else cp[j / 2] += n << 16;
+      cp += (uint32_t)__popc(mm) << (16 * j);
     }
-    uint32_t ip[SCAN_ROWS / 2];   // inclusive scan over the lanes, two rows per register (a row holds at most 512)
-#pragma unroll
-    for (int h = 0; h < SCAN_ROWS / 2; ++h) ip[h] = cp[h];
+    uint32_t ip = cp;   // inclusive scan over the lanes
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-      for (int h = 0; h < SCAN_ROWS / 2; ++h) {
-        const uint32_t x = __shfl_up_sync(0xffffffffu, ip[h], d);
-        if (lane >= d) ip[h] += x;
-      }
+      const uint32_t x = __shfl_up_sync(0xffffffffu, ip, d);
+      if (lane >= d) ip += x;
     }
-    uint32_t rowbase[SCAN_ROWS];  // newlines of this warp in the rows before row j
-    uint32_t wtotal = 0;
-#pragma unroll
-    for (int h = 0; h < SCAN_ROWS / 2; ++h) {
-      const uint32_t x = __shfl_sync(0xffffffffu, ip[h], 31);
-      rowbase[2 * h] = wtotal;
-      wtotal += x & 0xffffu;
-      rowbase[2 * h + 1] = wtotal;
-      wtotal += x >> 16;
-    }
-    if (lane == 0) s_warp[warp] = wtotal;
-    __syncthreads();   // every thread has read its part of stage s; s_warp is complete
+    const uint32_t tot = __shfl_sync(0xffffffffu, ip, 31);
+    const uint32_t row0 = tot & 0xffffu, wtotal = row0 + (tot >> 16);
+    if (lane == 0) s_warp[it & 1u][warp] = wtotal;
+    __syncthreads();   // every thread has read its part of stage s; s_warp[it & 1] is complete (and [~it & 1] free again)
     uint32_t warp_off = 0, agg = 0;
 #pragma unroll
     for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) {
-      const uint32_t x = s_warp[wi];
+      const uint32_t x = s_warp[it & 1u][wi];
       if (wi < warp) warp_off += x;
       agg += x;
     }
@@ -233,19 +223,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int 
     for (int j = 0; j < SCAN_ROWS; ++j) {
       uint32_t mm = m[j];
       if (mm == 0) continue;
-      const uint32_t cj = (cp[j / 2] >> (16 * (j & 1))) & 0xffffu, ij = (ip[j / 2] >> (16 * (j & 1))) & 0xffffu;
-      uint32_t idx = run + warp_off + rowbase[j] + ij - cj;
-      const uint32_t off = wbase + 512u * j;
-      while (mm) {
-        const int b = __ffs(mm) - 1;
+      const uint32_t cj = (cp >> (16 * j)) & 0xffffu, ij = (ip >> (16 * j)) & 0xffffu;
+      uint32_t idx = run + warp_off + (j ? row0 : 0u) + ij - cj;
+      const uint32_t off = wbase + 1024u * j;
+      if (idx + cj > c.scan_cap) {
+        overflow = true;
+        continue;
+      }
+      uint32_t* o = out + idx;
+      o[0] = off + (uint32_t)(__ffs(mm) - 1);          // a record's "\n+\n" makes two per lane common: straight-line
+      mm &= mm - 1;
+      if (mm) {
+        o[1] = off + (uint32_t)(__ffs(mm) - 1);
         mm &= mm - 1;
-        if (idx < c.scan_cap) out[idx] = off + (uint32_t)b;
-        else overflow = true;
-        ++idx;
+        for (uint32_t q = 2; mm; ++q) {
+          o[q] = off + (uint32_t)(__ffs(mm) - 1);
+          mm &= mm - 1;
+        }
       }
     }
     run += agg;
-    __syncthreads();   // s_warp may be rewritten
   }
   if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
   if (tid == 0) c.range_counts[(size_t)file * gridDim.x + blockIdx.x] = run;

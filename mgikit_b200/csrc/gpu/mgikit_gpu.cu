@@ -268,7 +268,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   // newline scan: one CTA per SM and stream, each with its own run of the staging array.  A run holds four times
   // the mean share of a range plus a whole stage of newlines; lanes whose newline density is more skewed than
   // that are refused (MGK_ERR_CAPACITY), real FASTQ is nowhere near.
-  ctx->scan_grid = (uint32_t)ctx->n_sm;
+  ctx->scan_grid = (uint32_t)ctx->n_sm * 3u / (P.paired ? 2u : 1u);   // 3 CTAs per SM over both streams, one wave
   ctx->scan_cap = (uint32_t)((4 * (ctx->cap_records * 4 + 4)) / ctx->scan_grid + SCAN_TILE + 64) & ~3u;
   CUC(cudaFuncSetAttribute(k_scan_newlines, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_STAGES * SCAN_TILE));
   ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
