@@ -58,6 +58,8 @@ struct TemplateDev {
   int32_t off_i7, off_i5;  // first packed index in Params::codes
   int32_t off_pair;        // first entry in Params::pairs
   int32_t wide;            // any index longer than 16 bases -> 64-bit compare
+  // exact-match hash tables over the raw index bytes (only when !wide): first slot in Params::hkeys / hids, slots - 1
+  int32_t h7_off, h7_mask, h5_off, h5_mask;
 };
 
 struct Params {
@@ -73,7 +75,18 @@ struct Params {
   const int32_t* xlat;      // translation tables
   const int32_t* writing;   // [total] writing_samples
   const uint8_t* consts;    // illumina prefix followed by the literals below
+  const uint64_t* hkeys;    // exact-match tables: two words per slot = the index's bytes, zero padded to 16
+  const int32_t* hids;      // index id of the slot, -1 = empty
 };
+
+// slot of a 16-byte key in a table of (mask + 1) slots; linear probing from there
+MGK_HD uint32_t index_hash(uint64_t lo, uint64_t hi, uint32_t mask) {
+  uint64_t x = lo ^ (hi * 0x9E3779B97F4A7C15ull);
+  x ^= x >> 29;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 32;
+  return (uint32_t)x & mask;
+}
 // layout of Params::consts after the prefix
 constexpr int LIT_COLON = 0;   // ":"
 constexpr int LIT_SPACE = 1;   // " "
@@ -170,8 +183,43 @@ struct MatchOut {
   int panicked; // the reference would have panicked (stale dictionary lookup)
 };
 
-// `codes` may point to a shared-memory copy of P.codes.  `bar` = BL observed bytes.
-MGK_HD MatchOut match_barcode(const Params& P, const uint64_t* codes, const uint8_t* bar) {
+// Where the nearest-set of an observed index comes from.  The default computes it on the
+// spot (XOR + popcount against every index of the dictionary); k_match_plan substitutes
+// results it obtained with an exact-match hash probe or a warp-wide search.
+//   di    dictionary (= template whose index set is searched; lags behind t on the reference's
+//         `continue` path, src/lib.rs:375-376)
+//   t     template whose geometry cuts the observed bytes
+//   which 7 or 5
+struct BruteNearest {
+  const Params& P;
+  const uint64_t* codes;
+  MGK_HD Nearest get(int di, int t, int which, const uint8_t* bar) const {
+    const TemplateDev& T = P.tpl[t];
+    const TemplateDev& D = P.tpl[di];
+    Nearest n;
+    n.d = INF_MISMATCH;
+    n.cnt = 0;
+    n.first = -1;
+    // dictionary `di` holds keys of D's index length; a lookup of another length misses
+    if (which == 7) {
+      if (T.g[1] == D.g[1] && D.n_i7 > 0) {
+        const Packed x = pack_observed(bar + P.BL - T.g[2], T.g[1]);
+        n = D.wide ? nearest_index<true>(codes + D.off_i7, D.n_i7, x) : nearest_index<false>(codes + D.off_i7, D.n_i7, x);
+      }
+    } else {
+      if (T.g[4] == D.g[4] && D.n_i5 > 0) {
+        const Packed x = pack_observed(bar + P.BL - T.g[5], T.g[4]);
+        n = D.wide ? nearest_index<true>(codes + D.off_i5, D.n_i5, x) : nearest_index<false>(codes + D.off_i5, D.n_i5, x);
+      }
+    }
+    return n;
+  }
+};
+
+// find_matching_sample (src/lib.rs:223-443).  `codes` may point to a shared-memory copy of
+// P.codes.  `bar` = BL observed bytes.
+template <class NF>
+MGK_HD MatchOut match_barcode_nf(const Params& P, const uint64_t* codes, const uint8_t* bar, const NF& nf) {
   const int total = P.total, und = total - 2, amb = total - 1;
   MatchOut r;
   r.sample = und;
@@ -183,29 +231,10 @@ MGK_HD MatchOut match_barcode(const Params& P, const uint64_t* codes, const uint
     const TemplateDev& T = P.tpl[t];
     const TemplateDev& D = P.tpl[di];
     bool skip_tail = false;
-    // dictionary `di` holds keys of D's index length; a lookup of another length misses
-    Nearest n7;
-    n7.d = INF_MISMATCH;
-    n7.cnt = 0;
-    n7.first = -1;
-    Packed x7;
-    x7.valid = 0;
-    if (T.g[1] == D.g[1] && D.n_i7 > 0) {
-      x7 = pack_observed(bar + P.BL - T.g[2], T.g[1]);
-      n7 = D.wide ? nearest_index<true>(codes + D.off_i7, D.n_i7, x7) : nearest_index<false>(codes + D.off_i7, D.n_i7, x7);
-    }
+    const Nearest n7 = nf.get(di, t, 7, bar);
     if (n7.d <= P.m) {  // Some(i7_matches) && .1 <= allowed  (:262-268)
       if (T.has_i5) {
-        Nearest n5;
-        n5.d = INF_MISMATCH;
-        n5.cnt = 0;
-        n5.first = -1;
-        Packed x5;
-        x5.valid = 0;
-        if (T.g[4] == D.g[4] && D.n_i5 > 0) {
-          x5 = pack_observed(bar + P.BL - T.g[5], T.g[4]);
-          n5 = D.wide ? nearest_index<true>(codes + D.off_i5, D.n_i5, x5) : nearest_index<false>(codes + D.off_i5, D.n_i5, x5);
-        }
+        const Nearest n5 = nf.get(di, t, 5, bar);
         if (n5.d <= P.m) {  // Some(i5_matches)  (:274); dictionary entries never exceed m
           const int tot = n7.d + n5.d;
           if (!(latest < tot)) {  // :278-282
@@ -230,7 +259,9 @@ MGK_HD MatchOut match_barcode(const Params& P, const uint64_t* codes, const uint
                   npairs = 1;
                   first_sample = s;
                 }
-              } else {
+              } else {   // several indexes at the minimum distance: rare, enumerate them
+                const Packed x7 = pack_observed(bar + P.BL - T.g[2], T.g[1]);
+                const Packed x5 = pack_observed(bar + P.BL - T.g[5], T.g[4]);
                 for (int a = 0; a < D.n_i7 && npairs < 2; ++a) {
                   if (dist_to(codes[D.off_i7 + a], x7) != n7.d) continue;
                   int ia = a;
@@ -294,6 +325,11 @@ MGK_HD MatchOut match_barcode(const Params& P, const uint64_t* codes, const uint
   if (r.sample >= total) r.sample = und;   // src/lib.rs:1020-1022
   r.mism = curr;
   return r;
+}
+
+MGK_HD MatchOut match_barcode(const Params& P, const uint64_t* codes, const uint8_t* bar) {
+  const BruteNearest nf{P, codes};
+  return match_barcode_nf(P, codes, bar, nf);
 }
 
 // ---------------------------------------------------------------- record plan

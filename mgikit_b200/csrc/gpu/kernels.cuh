@@ -294,10 +294,130 @@ __device__ __forceinline__ RecGeom load_geom(const ChunkDev& c, const Params& P,
   return G;
 }
 
+// Matching of one barcode per thread, CTA-wide.  With a single template of indexes up to 16
+// bases (every BASELINE configuration) the nearest-set of an observed index is found in two
+// steps that keep the warps converged:
+//   1. every thread probes the exact-match hash table with the raw bytes (an index found
+//      there is at distance 0 and alone at that distance);
+//   2. the misses (sequencing errors, N, random barcodes: ~1 read in 8) are queued in shared
+//      memory and each is searched by a WHOLE warp: lane k packs base k, then the lanes split
+//      the index table, XOR + popcount, min / count / first by warp reductions.
+// The decision logic on top (match_barcode_nf) is the one the CPU emulation runs.
+struct MatchShared {
+  const uint8_t* bar[TILE_RECORDS];
+  uint2 res[2][TILE_RECORDS];        // x = distance, y = count << 16 | first
+  uint32_t queue[2 * TILE_RECORDS];  // thread | which << 16
+  uint32_t nq;
+};
+
+struct StoredNearest {
+  Nearest n7, n5;
+  __device__ __forceinline__ Nearest get(int, int, int which, const uint8_t*) const { return which == 7 ? n7 : n5; }
+};
+
+__device__ __forceinline__ bool probe_exact(const Params& P, const uint8_t* p, int len, int off, int mask, Nearest& n) {
+  const uint32_t sh = (uint32_t)((uintptr_t)p & 15u);
+  const uint4* q = reinterpret_cast<const uint4*>(p - sh);
+  const uint4 v = shift16(__ldg(q), __ldg(q + 1), sh);
+  uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+  if (len < 8) {
+    lo &= (1ull << (8 * len)) - 1ull;
+    hi = 0;
+  } else if (len < 16) {
+    hi &= len == 8 ? 0ull : (1ull << (8 * (len - 8))) - 1ull;
+  }
+  uint32_t s = index_hash(lo, hi, (uint32_t)mask);
+  for (;;) {
+    const int id = __ldg(P.hids + off + s);
+    if (id < 0) return false;
+    if (__ldg(P.hkeys + 2 * (off + s)) == lo && __ldg(P.hkeys + 2 * (off + s) + 1) == hi) {
+      n.d = 0;
+      n.cnt = 1;
+      n.first = id;
+      return true;
+    }
+    s = (s + 1u) & (uint32_t)mask;
+  }
+}
+
+// all threads of the CTA call this; bar == nullptr: nothing to match for this thread
+__device__ __forceinline__ MatchOut cta_match(const Params& P, const uint64_t* s_codes, const uint8_t* bar, MatchShared& ms) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MatchOut mo;
+  mo.sample = P.total - 2;
+  mo.mism = 0;
+  mo.bar_t = mo.umi_t = -1;
+  mo.panicked = 0;
+  if (P.n_tpl != 1 || P.tpl[0].wide) {   // general path: every thread on its own
+    if (bar) mo = match_barcode(P, s_codes, bar);
+    return mo;
+  }
+  const TemplateDev& T = P.tpl[0];
+  StoredNearest nf;
+  nf.n7.d = nf.n5.d = INF_MISMATCH;
+  nf.n7.cnt = nf.n5.cnt = 0;
+  nf.n7.first = nf.n5.first = -1;
+  if (tid == 0) ms.nq = 0;
+  ms.bar[tid] = bar;
+  __syncthreads();
+  bool slow7 = false, slow5 = false;
+  if (bar) {
+    slow7 = T.n_i7 > 0 && !probe_exact(P, bar + P.BL - T.g[2], T.g[1], T.h7_off, T.h7_mask, nf.n7);
+    slow5 = T.has_i5 && T.n_i5 > 0 && !probe_exact(P, bar + P.BL - T.g[5], T.g[4], T.h5_off, T.h5_mask, nf.n5);
+    if (slow7) ms.queue[atomicAdd(&ms.nq, 1u)] = (uint32_t)tid;
+    if (slow5) ms.queue[atomicAdd(&ms.nq, 1u)] = (uint32_t)tid | 0x10000u;
+  }
+  __syncthreads();
+  const uint32_t nq = ms.nq;
+  for (uint32_t q = (uint32_t)warp; q < nq; q += blockDim.x / 32) {
+    const uint32_t item = ms.queue[q], who = item & 0xffffu, which = item >> 16;
+    const int len = which ? T.g[4] : T.g[1], n = which ? T.n_i5 : T.n_i7;
+    const uint8_t* p = ms.bar[who] + P.BL - (which ? T.g[5] : T.g[2]);
+    const uint64_t* codes = s_codes + (which ? T.off_i5 : T.off_i7);
+    const uint32_t b = lane < len ? __ldg(p + lane) : (uint32_t)'A';
+    const bool acgt = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T'), isn = b == 'N';
+    const bool invalid = __any_sync(0xffffffffu, !(acgt | isn));
+    const uint32_t code = __reduce_or_sync(0xffffffffu, (acgt && lane < len) ? ((b >> 1) & 3u) << (2 * (lane & 15)) : 0u);
+    const uint32_t nm = __reduce_or_sync(0xffffffffu, isn ? 1u << (2 * (lane & 15)) : 0u);
+    int best = INF_MISMATCH, cnt = 0, first = 0x7fffffff;
+    for (int k = lane; k < n; k += 32) {
+      const uint32_t v = code ^ (uint32_t)codes[k];
+      const int d = __popc(((v | (v >> 1)) & 0x55555555u) | nm);
+      if (d < best) {
+        best = d;
+        cnt = 1;
+        first = k;
+      } else if (d == best) {
+        ++cnt;
+      }
+    }
+    const int dmin = __reduce_min_sync(0xffffffffu, best);
+    const int ctot = __reduce_add_sync(0xffffffffu, best == dmin ? cnt : 0);
+    const int fmin = __reduce_min_sync(0xffffffffu, best == dmin ? first : 0x7fffffff);
+    if (lane == 0) ms.res[which][who] = invalid ? make_uint2((uint32_t)INF_MISMATCH, 0u) : make_uint2((uint32_t)dmin, ((uint32_t)ctot << 16) | (uint32_t)fmin);
+  }
+  __syncthreads();
+  if (!bar) return mo;
+  if (slow7) {
+    const uint2 r = ms.res[0][tid];
+    nf.n7.d = (int)r.x;
+    nf.n7.cnt = (int)(r.y >> 16);
+    nf.n7.first = r.x == (uint32_t)INF_MISMATCH ? -1 : (int)(r.y & 0xffffu);
+  }
+  if (slow5) {
+    const uint2 r = ms.res[1][tid];
+    nf.n5.d = (int)r.x;
+    nf.n5.cnt = (int)(r.y >> 16);
+    nf.n5.first = r.x == (uint32_t)INF_MISMATCH ? -1 : (int)(r.y & 0xffffu);
+  }
+  return match_barcode_nf(P, s_codes, bar, nf);
+}
+
 // dynamic shared memory: uint64 codes[n_codes] | uint32 bin_acc[2*total]
 __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __restrict__ Pg, ChunkDev c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Params P;
+  __shared__ MatchShared ms;
   copy_params_to_smem(&P, Pg);
   __syncthreads();
   uint64_t* s_codes = reinterpret_cast<uint64_t*>(smem_raw);
@@ -330,19 +450,18 @@ __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __res
     mt.mism = mt.flags = 0;
     bool unassigned = false, is_amb = false;
     uint32_t bar_off = 0;
+    RecGeom G;
+    G.h2 = G.s2 = G.p2 = G.q2 = G.e2 = G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
+    const uint8_t* bar = nullptr;
     if (active) {
-      const RecGeom G = load_geom(c, P, rec);
-      const uint32_t BL = (uint32_t)P.BL;
-      const bool layout_ok = (G.p2 - G.s2 >= BL + 1u);
-      MatchOut mo;
-      mo.sample = total - 2;
-      mo.mism = 0;
-      mo.bar_t = mo.umi_t = -1;
-      mo.panicked = 0;
-      if (layout_ok) {
-        bar_off = G.p2 - 1u - BL;
-        mo = match_barcode(P, s_codes, c.r2 + bar_off);
+      G = load_geom(c, P, rec);
+      if (G.p2 - G.s2 >= (uint32_t)P.BL + 1u) {   // the sequence line holds a whole barcode
+        bar_off = G.p2 - 1u - (uint32_t)P.BL;
+        bar = c.r2 + bar_off;
       }
+    }
+    const MatchOut mo = cta_match(P, s_codes, bar, ms);   // CTA-wide: every thread calls it
+    if (active) {
       if (mo.panicked) atomicOr(&c.status->error, ERR_PANIC);
       const RecPlan pl = record_plan(P, c.r2, G, mo.sample, mo.bar_t, mo.umi_t);
       if (pl.fmt_error) {
@@ -723,20 +842,26 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
 }
 
 // ------------------------------------------------------------------ stage kernels (parity tests)
-__global__ void k_match_only(const Params* __restrict__ Pg, const uint8_t* __restrict__ bars, uint32_t n, int32_t* sample,
-                             int32_t* mism, uint32_t* error) {
+__global__ void __launch_bounds__(TILE_RECORDS) k_match_only(const Params* __restrict__ Pg, const uint8_t* __restrict__ bars, uint32_t n,
+                                                             int32_t* sample, int32_t* mism, uint32_t* error) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Params P;
+  __shared__ MatchShared ms;
   copy_params_to_smem(&P, Pg);
   __syncthreads();
   uint64_t* s_codes = reinterpret_cast<uint64_t*>(smem_raw);
   for (int i = threadIdx.x; i < P.n_codes; i += blockDim.x) s_codes[i] = P.codes[i];
   __syncthreads();
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const MatchOut mo = match_barcode(P, s_codes, bars + (size_t)i * P.BL);
-    if (mo.panicked) atomicOr(error, ERR_PANIC);
-    sample[i] = mo.sample;
-    mism[i] = mo.mism;
+  const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (uint32_t r = 0; r < rounds; ++r) {   // uniform trip count: cta_match is CTA-wide
+    const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const MatchOut mo = cta_match(P, s_codes, i < n ? bars + (size_t)i * P.BL : nullptr, ms);
+    if (i < n) {
+      if (mo.panicked) atomicOr(error, ERR_PANIC);
+      sample[i] = mo.sample;
+      mism[i] = mo.mism;
+    }
+    __syncthreads();
   }
 }
 

@@ -55,7 +55,8 @@ struct mgk_ctx {
   Params hp{};              // host copy (pointers are device pointers)
   Params* d_params = nullptr;
   uint64_t* d_codes = nullptr;
-  int32_t *d_pairs = nullptr, *d_xlat = nullptr, *d_writing = nullptr;
+  int32_t *d_pairs = nullptr, *d_xlat = nullptr, *d_writing = nullptr, *d_hids = nullptr;
+  uint64_t* d_hkeys = nullptr;
   uint8_t* d_consts = nullptr;
   unsigned long long *d_stats = nullptr, *d_mism = nullptr, *d_prof = nullptr;
   Status* h_status_init = nullptr;
@@ -173,6 +174,7 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
   }
   for (auto& s : ctx->slots) free_slot(s);
   cudaFree(ctx->d_params); cudaFree(ctx->d_codes); cudaFree(ctx->d_pairs); cudaFree(ctx->d_xlat);
+  cudaFree(ctx->d_hkeys); cudaFree(ctx->d_hids);
   cudaFree(ctx->d_writing); cudaFree(ctx->d_consts); cudaFree(ctx->d_stats); cudaFree(ctx->d_mism);
   cudaFreeHost(ctx->h_status_init);
   if (ctx->span_begin) cudaEventDestroy(ctx->span_begin);
@@ -241,6 +243,12 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   CUC(dalloc(&ctx->d_pairs, pairs.size() + 1));
   CUC(dalloc(&ctx->d_xlat, xlat.size() + 1));
   CUC(dalloc(&ctx->d_writing, (size_t)P.total));
+  CUC(dalloc(&ctx->d_hkeys, tb.hkeys.size() + 2));
+  CUC(dalloc(&ctx->d_hids, tb.hids.size() + 1));
+  if (!tb.hids.empty()) {
+    CUC(cudaMemcpy(ctx->d_hkeys, tb.hkeys.data(), tb.hkeys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->d_hids, tb.hids.data(), tb.hids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   CUC(dalloc(&ctx->d_consts, consts.size()));
   CUC(dalloc(&ctx->d_stats, (size_t)P.total * MGK_N_STATS));
   CUC(dalloc(&ctx->d_mism, (size_t)P.total * P.mism_w));
@@ -257,6 +265,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   P.xlat = ctx->d_xlat;
   P.writing = ctx->d_writing;
   P.consts = ctx->d_consts;
+  P.hkeys = ctx->d_hkeys;
+  P.hids = ctx->d_hids;
   CUC(cudaMemcpy(ctx->d_params, &P, sizeof P, cudaMemcpyHostToDevice));
 
   // capacities

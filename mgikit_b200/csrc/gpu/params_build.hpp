@@ -16,7 +16,29 @@ struct HostTables {
   std::vector<int32_t> xlat;     // index-id translation between templates
   std::vector<int32_t> writing;
   std::string consts;            // illumina prefix + literal bytes
+  std::vector<uint64_t> hkeys;   // exact-match hash tables (two words per slot)
+  std::vector<int32_t> hids;
 };
+
+// open-addressing table over n index strings of `len` (<= 16) bytes; returns the first slot, sets mask
+inline int build_index_hash(HostTables& tb, const char* seqs, int n, int len, int32_t& mask) {
+  uint32_t slots = 16;
+  while (slots < 2u * (uint32_t)n) slots <<= 1;
+  mask = (int32_t)(slots - 1);
+  const int off = (int)tb.hids.size();
+  tb.hids.resize((size_t)off + slots, -1);
+  tb.hkeys.resize(2 * ((size_t)off + slots), 0);
+  for (int i = 0; i < n; ++i) {
+    uint64_t k[2] = {0, 0};
+    memcpy(k, seqs + (size_t)i * len, (size_t)len);
+    uint32_t s = index_hash(k[0], k[1], (uint32_t)mask);
+    while (tb.hids[(size_t)off + s] >= 0) s = (s + 1) & (uint32_t)mask;
+    tb.hids[(size_t)off + s] = i;
+    tb.hkeys[2 * ((size_t)off + s)] = k[0];
+    tb.hkeys[2 * ((size_t)off + s) + 1] = k[1];
+  }
+  return off;
+}
 
 // Fills P (pointer members left null) and tb.  Returns false with a reason.
 inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, std::string& why) {
@@ -62,6 +84,11 @@ inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, 
     for (int i = 0; i < T.n_i7; ++i) tb.codes.push_back(pack_index_host(s.i7 + (size_t)i * T.g[1], T.g[1]));
     T.off_i5 = (int)tb.codes.size();
     for (int i = 0; i < T.n_i5; ++i) tb.codes.push_back(pack_index_host(s.i5 + (size_t)i * T.g[4], T.g[4]));
+    T.h7_off = T.h5_off = T.h7_mask = T.h5_mask = 0;
+    if (!T.wide) {
+      T.h7_off = build_index_hash(tb, s.i7, T.n_i7, T.g[1], T.h7_mask);
+      if (T.has_i5) T.h5_off = build_index_hash(tb, s.i5, T.n_i5, T.g[4], T.h5_mask);
+    }
     T.off_pair = (int)tb.pairs.size();
     const size_t np = T.has_i5 ? (size_t)T.n_i7 * T.n_i5 : (size_t)T.n_i7;
     tb.pairs.insert(tb.pairs.end(), s.pair_sample, s.pair_sample + np);

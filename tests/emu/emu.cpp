@@ -43,6 +43,8 @@ int emu_create(const mgk_config* cfg, emu_ctx** out) {
   c->P.xlat = c->tb.xlat.data();
   c->P.writing = c->tb.writing.data();
   c->P.consts = (const uint8_t*)c->tb.consts.data();
+  c->P.hkeys = c->tb.hkeys.data();
+  c->P.hids = c->tb.hids.data();
   c->stats.assign((size_t)c->P.total * MGK_N_STATS, 0);
   c->mism.assign((size_t)c->P.total * c->P.mism_w, 0);
   *out = c;
