@@ -414,7 +414,7 @@ __device__ __forceinline__ MatchOut cta_match(const Params& P, const uint64_t* s
 }
 
 // dynamic shared memory: uint64 codes[n_codes] | uint32 bin_acc[2*total]
-__global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __restrict__ Pg, ChunkDev c) {
+__global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __restrict__ Pg, ChunkDev c, int mism_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Params P;
   __shared__ MatchShared ms;
@@ -424,6 +424,10 @@ __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __res
   uint32_t* bin_acc = reinterpret_cast<uint32_t*>(s_codes + P.n_codes);
   for (int i = threadIdx.x; i < P.n_codes; i += blockDim.x) s_codes[i] = P.codes[i];
   const int total = P.total, B2 = 2 * total;
+  // per-CTA mismatch counters in shared memory when the table is small enough (mism_smem of the launch)
+  uint32_t* mism_acc = mism_smem ? bin_acc + B2 : nullptr;
+  if (mism_acc)
+    for (int i = threadIdx.x; i < total * P.mism_w; i += blockDim.x) mism_acc[i] = 0;
   const uint32_t raw2 = c.counts[0] >> 2, raw1 = P.paired ? c.counts[1] >> 2 : raw2;
   const uint32_t n_rec = device_n_records(c, P);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -478,7 +482,8 @@ __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __res
       mt.mism = (uint8_t)mo.mism;
       if (!pl.fmt_error) {
         // update_mismatches(sample_id, curr_mismatch + 1, 1), src/lib.rs:1212
-        atomicAdd(&c.mism[(size_t)mo.sample * P.mism_w + mo.mism + 1], 1ull);
+        if (mism_acc) atomicAdd(&mism_acc[mo.sample * P.mism_w + mo.mism + 1], 1u);   // flushed once per CTA
+        else atomicAdd(&c.mism[(size_t)mo.sample * P.mism_w + mo.mism + 1], 1ull);
         unassigned = !pl.matched && P.report_level > 1;  // src/lib.rs:1082-1088
         is_amb = mo.sample == total - 1;
       }
@@ -531,6 +536,13 @@ __global__ void __launch_bounds__(TILE_RECORDS) k_match_plan(const Params* __res
     if (active) c.meta[rec] = mt;
     uint32_t* row = c.tile_bins + (size_t)tile * c.bins_stride;
     for (int i = threadIdx.x; i < B2; i += blockDim.x) row[i] = bin_acc[i];
+  }
+  if (mism_acc) {   // a CTA sees fewer than 2^32 records
+    __syncthreads();
+    for (int i = threadIdx.x; i < total * P.mism_w; i += blockDim.x) {
+      const uint32_t v = mism_acc[i];
+      if (v) atomicAdd(&c.mism[i], (unsigned long long)v);
+    }
   }
 }
 

@@ -64,6 +64,7 @@ struct mgk_ctx {
   uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
   uint32_t scan_grid = 0, scan_cap = 0, tiles_max = 0, groups_max = 0;
   size_t match_smem = 0;
+  int mism_smem = 0;
   int grid_match = 0, grid_emit = 0, n_sm = 0;
   uint32_t bins_stride = 0;
   EmitLayout lay{};
@@ -284,6 +285,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
   ctx->groups_max = (ctx->tiles_max + GROUP_TILES - 1) / GROUP_TILES;
   ctx->match_smem = (size_t)P.n_codes * 8 + (size_t)2 * P.total * 4 + 16;
+  ctx->mism_smem = (size_t)P.total * P.mism_w <= 8192 ? 1 : 0;   // per-CTA mismatch counters in shared memory
+  if (ctx->mism_smem) ctx->match_smem += (size_t)P.total * P.mism_w * 4;
   if (ctx->match_smem > 200 * 1024) BAD("mgk_create: index tables (%zu B) do not fit the shared-memory staging area", ctx->match_smem);
   CUC(cudaFuncSetAttribute(k_match_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
   CUC(cudaFuncSetAttribute(k_match_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->match_smem));
@@ -452,7 +455,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   const uint32_t tiles_bound = (uint32_t)((rec_bound + TILE_RECORDS - 1) / TILE_RECORDS);
   const uint32_t groups_bound = (tiles_bound + GROUP_TILES - 1) / GROUP_TILES;
   const uint32_t B2 = 2u * (uint32_t)P.total;
-  k_match_plan<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_match), TILE_RECORDS, ctx->match_smem, st>>>(ctx->d_params, c);
+  k_match_plan<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_match), TILE_RECORDS, ctx->match_smem, st>>>(ctx->d_params, c, ctx->mism_smem);
   CU(cudaEventRecord(s.ev[3], st));
   const uint32_t scan_threads = groups_bound * B2;
   k_scan_groups<<<(scan_threads + 255) / 256, 256, 0, st>>>(ctx->d_params, c);
