@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1 << 21, help="read pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=1 << 20, help="read pairs per step per GPU (746 MB of text: > 5x L2)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -53,7 +53,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -235,7 +235,6 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = hp.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     stats, mism = hp.counters()
     total_expected = n * a.steps * (world if world > 1 else 1)
     assert int(mism[:, 1:].sum()) == total_expected, "counter tables do not add up to the reads processed"
@@ -279,9 +278,22 @@ def main():
                "d2h_bytes_per_step": int(d2h), "timing": "host clock between barrier+synchronize, max over ranks; pinned buffers, "
                                                           "2 chunks in flight"}
 
-    if rank != 0:
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (resident and end to end)
+    def teardown():
+        """Every rank leaves the same way: NCCL communicators (the library's and torch's) are destroyed collectively;
+        a watchdog ends the process if a peer is already gone."""
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        if world > 1:
+            dist.barrier()
+        hp.close()
         if world > 1:
             dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
+
+    if rank != 0:
+        teardown()
         return
 
     # ---- roofline of the dominant kernel (scatter + QC)
@@ -297,8 +309,15 @@ def main():
     algo_bytes = in_bytes + out_bytes                # every input byte read once, every output byte written once
     scatter_ms = float(k_ms[:, 3].mean())
     achieved = algo_bytes / (scatter_ms * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of k_emit from the committed ncu capture, scaled per pair
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_emit_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = int(tr["dram_bytes_per_launch"] * (n / tr["pairs_per_launch"]))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_emit", "timing": "CUDA events on the launching stream, one chunk in flight", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
                 "kernel_ms": {"scan_newlines": float(k_ms[:, 0].mean()), "match_plan": float(k_ms[:, 1].mean()),
                               "bin_scan": float(k_ms[:, 2].mean()), "emit_qc": scatter_ms, "chunk": float(k_ms[:, 4].mean())},
                 "whole_path_frac": (algo_bytes * a.steps / (span_max * 1e-3) / 1e9) / peak}
@@ -313,10 +332,8 @@ def main():
             "ms_per_step": span_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "wall_s_resident": wall}
-    print(json.dumps(line))
-    hp.close()
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    teardown()
 
 
 if __name__ == "__main__":

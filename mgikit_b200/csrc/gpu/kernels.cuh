@@ -249,28 +249,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int 
 }
 
 // Packs the per-range runs into the final newline table and leaves the total in counts[file].
+// grid = (scan_grid * GATHER_SPLIT, files): GATHER_SPLIT CTAs share one range.
+constexpr int GATHER_SPLIT = 4;
 __global__ void __launch_bounds__(256) k_gather_newlines(ChunkDev c, int n_files) {
   __shared__ uint32_t s_prefix;
   const int file = blockIdx.y;
   if (file >= n_files) return;
-  const uint32_t* rc = c.range_counts + (size_t)file * gridDim.x;
+  const uint32_t range = blockIdx.x / GATHER_SPLIT, part = blockIdx.x % GATHER_SPLIT;
+  const uint32_t* rc = c.range_counts + (size_t)file * c.scan_grid;
   if (threadIdx.x < 32) {
     uint32_t sum = 0;
-    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += 32u) sum += rc[i];
+    for (uint32_t i = threadIdx.x; i < range; i += 32u) sum += rc[i];
     sum = __reduce_add_sync(0xffffffffu, sum);
     if (threadIdx.x == 0) s_prefix = sum;
   }
   __syncthreads();
-  const uint32_t prefix = s_prefix, n = min(rc[blockIdx.x], c.scan_cap);
-  const uint32_t* __restrict__ src = (file == 0 ? c.stg2 : c.stg1) + (size_t)blockIdx.x * c.scan_cap;
+  const uint32_t prefix = s_prefix, n = min(rc[range], c.scan_cap);
+  const uint32_t* __restrict__ src = (file == 0 ? c.stg2 : c.stg1) + (size_t)range * c.scan_cap;
   uint32_t* __restrict__ nl = file == 0 ? c.nl2 : c.nl1;
   bool overflow = false;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (uint32_t i = part * blockDim.x + threadIdx.x; i < n; i += GATHER_SPLIT * blockDim.x) {
     if (prefix + i < c.nl_cap) nl[prefix + i] = src[i];
     else overflow = true;
   }
   if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) c.counts[file] = prefix + rc[blockIdx.x];   // every newline, stored or not
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) c.counts[file] = prefix + rc[range];   // every newline, stored or not
 }
 
 // ------------------------------------------------------------------ K2
@@ -572,10 +575,15 @@ __global__ void __launch_bounds__(1024) k_scan_bins(const Params* __restrict__ P
   unsigned long long* seg = c.seg;  // [off2 | len2 | off1 | len1] x total
   for (int b = threadIdx.x; b < B2; b += blockDim.x) {
     uint32_t run = 0;
-    for (uint32_t g = 0; g < n_groups; ++g) {
-      const uint32_t v = c.group_sums[(size_t)g * B2 + b];
-      c.group_sums[(size_t)g * B2 + b] = run;
-      run += v;
+    for (uint32_t g0 = 0; g0 < n_groups; g0 += 8) {   // loads of a batch first: reads and writes alias for the compiler
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = g0 + k < n_groups ? c.group_sums[(size_t)(g0 + k) * B2 + b] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (g0 + k < n_groups) c.group_sums[(size_t)(g0 + k) * B2 + b] = run;
+        run += v[k];
+      }
     }
     seg[(b < total ? 1 : 3) * total + (b % total)] = run;
   }
@@ -612,10 +620,15 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
   if (g >= n_groups) return;
   const uint32_t t0 = g * GROUP_TILES, t1 = min(n_tiles, t0 + GROUP_TILES);
   uint32_t run = c.group_sums[(size_t)g * B2 + b] + (uint32_t)c.seg[(b < (uint32_t)total ? 0 : 2) * total + (b % total)];
-  for (uint32_t t = t0; t < t1; ++t) {
-    const uint32_t v = c.tile_bins[(size_t)t * c.bins_stride + b];
-    c.tile_bins[(size_t)t * c.bins_stride + b] = run;
-    run += v;
+  for (uint32_t tb = t0; tb < t1; tb += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = tb + k < t1 ? c.tile_bins[(size_t)(tb + k) * c.bins_stride + b] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (tb + k < t1) c.tile_bins[(size_t)(tb + k) * c.bins_stride + b] = run;
+      run += v[k];
+    }
   }
 }
 
@@ -686,12 +699,11 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
   const uint32_t n_rec = device_n_records(c, P);
   if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY)) return;  // nothing safe to write
-  // this CTA's run of plan tiles
+  // this CTA's plan tiles: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
+  // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk
+  // size (measured equal to a contiguous run per CTA on chunks of 0.5-4 M pairs; kept for the bounded page set).
   const uint32_t n_pt = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
-  const uint32_t pt0 = (uint32_t)(((unsigned long long)n_pt * blockIdx.x) / gridDim.x);
-  const uint32_t pt1 = (uint32_t)(((unsigned long long)n_pt * (blockIdx.x + 1)) / gridDim.x);
-  const uint32_t R0 = pt0 * TILE_RECORDS, R1 = min(pt1 * TILE_RECORDS, n_rec);
-  if (R0 >= R1) return;
+  if (blockIdx.x >= n_pt) return;
   const uint32_t bins_stride = (2u * (uint32_t)total + 3u) & ~3u;
 
   // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are halved below)
@@ -703,19 +715,21 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
 
   // producer state (lane 0 of the producer warp)
-  uint32_t next_rec = R0, start2 = 0, start1 = 0;
-  if (warp == PRODUCER_WARP && lane == 0) {
-    start2 = c.nl2[(long long)4 * R0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
-    start1 = paired ? c.nl1[(long long)4 * R0 - 1] + 1u : 0u;
-  }
+  uint32_t next_rec = blockIdx.x * TILE_RECORDS, start2 = 0, start1 = 0;
+  bool fresh = true;   // next_rec opens a plan tile: its byte offsets come from the newline table
   auto produce = [&](int s) {   // lane 0 of the producer warp
     StageDesc& d = s_desc[s];
-    if (next_rec >= R1) {
+    if (next_rec >= n_rec) {
       d.n = 0;
       return;
     }
     const uint32_t r0 = next_rec;
-    uint32_t lim = min(min(r0 + n_tile, R1), (r0 / TILE_RECORDS + 1u) * TILE_RECORDS);
+    if (fresh) {
+      start2 = c.nl2[(long long)4 * r0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
+      start1 = paired ? c.nl1[(long long)4 * r0 - 1] + 1u : 0u;
+    }
+    const uint32_t pt_end = min((r0 / TILE_RECORDS + 1u) * TILE_RECORDS, n_rec);
+    uint32_t lim = min(r0 + n_tile, pt_end);
     const uint32_t base2 = start2 & ~15u, base1 = start1 & ~15u;
     uint32_t e2, e1, len2, len1, off1;
     for (;;) {
@@ -730,7 +744,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     if (off1 + len1 + 64u > lay.cap) {   // one read pair larger than a stage
       atomicOr(&c.status->error, ERR_REC_TOO_LONG);
       d.n = 0;
-      next_rec = R1;
+      next_rec = n_rec;
       return;
     }
     const uint32_t n = lim - r0;
@@ -748,7 +762,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     if (paired) bulk_g2s(st + lay.nl1, c.nl1 + ((long long)4 * r0 - 4), nl_bytes, &s_bar[s]);
     bulk_g2s(st + lay.meta, c.meta + r0, meta_bytes, &s_bar[s]);
     bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / TILE_RECORDS) * bins_stride, bins_bytes, &s_bar[s]);
-    next_rec = lim;
+    fresh = lim == pt_end;
+    next_rec = fresh ? (r0 / TILE_RECORDS + gridDim.x) * TILE_RECORDS : lim;
     start2 = e2;
     start1 = e1;
   };

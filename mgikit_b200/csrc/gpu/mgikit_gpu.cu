@@ -445,7 +445,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   {
     const dim3 grid(ctx->scan_grid, P.paired ? 2 : 1);
     k_scan_newlines<<<grid, SCAN_THREADS, SCAN_STAGES * SCAN_TILE, st>>>(c, P.paired ? 2 : 1);
-    k_gather_newlines<<<grid, 256, 0, st>>>(c, P.paired ? 2 : 1);
+    k_gather_newlines<<<dim3(grid.x * GATHER_SPLIT, grid.y), 256, 0, st>>>(c, P.paired ? 2 : 1);
     ctx->launches += 2;
   }
   CU(cudaEventRecord(s.ev[2], st));
@@ -714,7 +714,7 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
     c.range_counts = d_ctrl + 8;
     c.status = d_status;
     k_scan_newlines<<<dim3(grid, 1), SCAN_THREADS, SCAN_STAGES * SCAN_TILE>>>(c, 1);
-    k_gather_newlines<<<dim3(grid, 1), 256>>>(c, 1);
+    k_gather_newlines<<<dim3(grid * GATHER_SPLIT, 1), 256>>>(c, 1);
     ctx->launches += 2;
     TRY(cudaDeviceSynchronize());
     TRY(cudaMemcpy(h_ctrl.data(), d_ctrl, 32, cudaMemcpyDeviceToHost));
