@@ -3,14 +3,16 @@
 // fast byte array `S` (shared memory on the B200, a host array in the CPU
 // emulation that the `-m "not gpu"` tests check against the oracle).
 //
-// ONE THREAD PER (record, role): the control-heavy part of a record (where the
-// header digits start, which bytes survive the trim) is scalar work, so every
-// lane of a warp carries a different record and runs the same straight-line
-// code; nothing here needs a warp collective, which is also why the CPU
-// emulation can call these functions as they are.
-//   role A  emit_read2()   barcode read: new header, trimmed sequence and qualities
-//   role B  emit_read1()   paired read: copy of the header, rest of the record verbatim
-//   role C  qc_pair() / validate_pair()
+// Two kinds of work, two kinds of workers (k_emit):
+//   * control-heavy, tiny: where a header's digits start, which template cut the barcode,
+//     the quality sums.  ONE THREAD PER (record, role): build_header() front / tail,
+//     qc_pair(), validate_pair() — every lane of a warp carries a different record.
+//   * bulk bytes: an output record is at most three byte ranges (header | "\n" sequence |
+//     "\n+\n" qualities), see plan_read().  A HALF-WARP moves one range with copy_piece():
+//     16-byte stores aligned on the destination, fully coalesced, fed by unaligned reads of
+//     S (aligned words + funnel shift), the < 16 bytes at either end one byte per lane.
+// The functions take the lane as an argument and use no warp intrinsic, so the CPU
+// emulation runs the very same code with the lanes looped.
 //
 // What it restates (reference = /root/reference):
 //   write_illumina_header        src/sample_data.rs:569-654, call site src/lib.rs:1240-1293
@@ -24,9 +26,10 @@
 
 namespace mgk {
 
-// ---------------------------------------------------------------- 16-byte gather
+// ---------------------------------------------------------------- reading S at any alignment
 MGK_HD uint32_t s_u8(const uint8_t* S, uint32_t off) { return S[off]; }
-MGK_HD uint4 s_v4(const uint8_t* S, uint32_t off) { return *reinterpret_cast<const uint4*>(S + off); }
+MGK_HD uint32_t s_u32(const uint8_t* S, uint32_t off) { return *reinterpret_cast<const uint32_t*>(S + off); }   // off % 4 == 0
+MGK_HD uint4 s_v4(const uint8_t* S, uint32_t off) { return *reinterpret_cast<const uint4*>(S + off); }          // off % 16 == 0
 
 MGK_HD int ctz32(uint32_t x) {  // x != 0
 #if defined(__CUDA_ARCH__)
@@ -35,7 +38,6 @@ MGK_HD int ctz32(uint32_t x) {  // x != 0
   return __builtin_ctz(x);
 #endif
 }
-
 MGK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // sh in {0,8,16,24}
 #if defined(__CUDA_ARCH__)
   return __funnelshift_r(lo, hi, sh);
@@ -43,38 +45,15 @@ MGK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // sh in {0,8
   return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
-
-// 16 bytes starting at ANY offset: two aligned vectors, a word shift in two
-// select stages, then a byte funnel shift.  Reads S[addr & ~15 .. +32).
-MGK_HD uint4 gather16(const uint8_t* S, uint32_t addr) {
-  const uint32_t al = addr & ~15u, sh = addr & 15u;
-  const uint4 a = s_v4(S, al), b = s_v4(S, al + 16u);
-  const bool s2 = (sh & 8u) != 0u, s1 = (sh & 4u) != 0u;
-  const uint32_t t0 = s2 ? a.z : a.x, t1 = s2 ? a.w : a.y, t2 = s2 ? b.x : a.z, t3 = s2 ? b.y : a.w, t4 = s2 ? b.z : b.x,
-                 t5 = s2 ? b.w : b.y;
-  const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
-  const uint32_t bs = (sh & 3u) * 8u;
+// 16 bytes of S at any offset as four words: five independent aligned word loads (reads S[a & ~3 .. +20))
+MGK_HD uint4 ld16u(const uint8_t* S, uint32_t a) {
+  const uint32_t al = a & ~3u, sh = (a & 3u) * 8u;
+  const uint32_t w0 = s_u32(S, al), w1 = s_u32(S, al + 4u), w2 = s_u32(S, al + 8u), w3 = s_u32(S, al + 12u), w4 = s_u32(S, al + 16u);
   uint4 o;
-  o.x = funnel_r(u0, u1, bs);
-  o.y = funnel_r(u1, u2, bs);
-  o.z = funnel_r(u2, u3, bs);
-  o.w = funnel_r(u3, u4, bs);
-  return o;
-}
-
-// bytes [0,k) of a, bytes [k,16) of b     (0 < k < 16)
-MGK_HD uint32_t merge_word(uint32_t a, uint32_t b, int k) {  // k = bytes of this word taken from a, any int
-  if (k >= 4) return a;
-  if (k <= 0) return b;
-  const uint32_t m = (1u << (8 * k)) - 1u;
-  return (a & m) | (b & ~m);
-}
-MGK_HD uint4 merge16(const uint4& a, const uint4& b, int k) {
-  uint4 o;
-  o.x = merge_word(a.x, b.x, k);
-  o.y = merge_word(a.y, b.y, k - 4);
-  o.z = merge_word(a.z, b.z, k - 8);
-  o.w = merge_word(a.w, b.w, k - 12);
+  o.x = funnel_r(w0, w1, sh);
+  o.y = funnel_r(w1, w2, sh);
+  o.z = funnel_r(w2, w3, sh);
+  o.w = funnel_r(w3, w4, sh);
   return o;
 }
 MGK_HD uint32_t put_byte(uint32_t w, int i, uint32_t v) {  // byte i of the word := v when 0 <= i < 4
@@ -82,208 +61,30 @@ MGK_HD uint32_t put_byte(uint32_t w, int i, uint32_t v) {  // byte i of the word
   const uint32_t sh = 8u * (uint32_t)i;
   return (w & ~(0xffu << sh)) | (v << sh);
 }
-MGK_HD void put_byte16(uint4& o, int i, uint32_t v) {
-  o.x = put_byte(o.x, i, v);
-  o.y = put_byte(o.y, i - 4, v);
-  o.z = put_byte(o.z, i - 8, v);
-  o.w = put_byte(o.w, i - 12, v);
-}
 
-// ---------------------------------------------------------------- three-segment copy
-// An output record is the concatenation of up to three byte ranges of S
-// (rewritten header | sequence part | quality part).
-struct Seg3 {
-  uint32_t s0, n0, s1, n1, s2, n2;  // S offsets and lengths
-};
-
-MGK_HD void st_v4(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
-
-// lo, hi = two consecutive aligned vectors; the 16 bytes starting `sh` bytes into lo
-MGK_HD uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
-  const bool s2 = (sh & 8u) != 0u, s1 = (sh & 4u) != 0u;
-  const uint32_t t0 = s2 ? a.z : a.x, t1 = s2 ? a.w : a.y, t2 = s2 ? b.x : a.z, t3 = s2 ? b.y : a.w, t4 = s2 ? b.z : b.x,
-                 t5 = s2 ? b.w : b.y;
-  const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
-  const uint32_t bs = (sh & 3u) * 8u;
-  uint4 o;
-  o.x = funnel_r(u0, u1, bs);
-  o.y = funnel_r(u1, u2, bs);
-  o.z = funnel_r(u2, u3, bs);
-  o.w = funnel_r(u3, u4, bs);
-  return o;
-}
-
-// 32 bytes to a 32-byte aligned global address: one full DRAM sector per lane per store
-MGK_HD void st_v8(uint8_t* p, const uint4& a, const uint4& b) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
-               "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-#else
-  *reinterpret_cast<uint4*>(p) = a;
-  *reinterpret_cast<uint4*>(p + 16) = b;
-#endif
-}
-
-// the LAST n (< 32) bytes of the 32-byte value (a, b) go to [end - n, end), `end` 32-byte aligned: 16 + 8 + 4 + 2 + 1 ladder
-MGK_HD void store_before(uint8_t* end, const uint4& a, const uint4& b, uint32_t n) {
-  uint4 v = b;
-  uint8_t* p = end;
-  if (n & 16u) {
-    p -= 16;
-    st_v4(p, b);
-    v = a;
-  }
-  uint32_t cur = v.w, prev = v.z;
-  if (n & 8u) {
-    p -= 8;
-    uint2 t;
-    t.x = v.z;
-    t.y = v.w;
-    *reinterpret_cast<uint2*>(p) = t;
-    cur = v.y;
-    prev = v.x;
-  }
-  if (n & 4u) {
-    p -= 4;
-    *reinterpret_cast<uint32_t*>(p) = cur;
-    cur = prev;
-  }
-  if (n & 2u) {
-    p -= 2;
-    *reinterpret_cast<uint16_t*>(p) = (uint16_t)(cur >> 16);
-    cur <<= 16;
-  }
-  if (n & 1u) {
-    p -= 1;
-    *p = (uint8_t)(cur >> 24);
-  }
-}
-// the FIRST n (< 32) bytes of (a, b) go to [p, p + n), p 32-byte aligned
-MGK_HD void store_after(uint8_t* p, const uint4& a, const uint4& b, uint32_t n) {
-  uint4 v = a;
-  if (n & 16u) {
-    st_v4(p, a);
-    p += 16;
-    v = b;
-  }
-  uint32_t c0 = v.x, c1 = v.y;
-  if (n & 8u) {
-    uint2 t;
-    t.x = v.x;
-    t.y = v.y;
-    *reinterpret_cast<uint2*>(p) = t;
-    p += 8;
-    c0 = v.z;
-    c1 = v.w;
-  }
-  if (n & 4u) {
-    *reinterpret_cast<uint32_t*>(p) = c0;
-    p += 4;
-    c0 = c1;
-  }
-  if (n & 2u) {
-    *reinterpret_cast<uint16_t*>(p) = (uint16_t)(c0 & 0xffffu);
-    p += 2;
-    c0 >>= 16;
-  }
-  if (n & 1u) *p = (uint8_t)(c0 & 0xffu);
-}
-
-// A record's output may be shared by two threads: PART_HEAD takes the bytes in front of the
-// first aligned unit and the first `split` units, PART_TAIL the rest.  Both compute the same
-// split from the same inputs; `own0` leading output bytes (the staged header, which only the
-// head thread can see) are guaranteed to stay in the head part.
-enum { PART_HEAD = 0, PART_TAIL = 1, PART_ALL = 2 };
-
-// This thread writes its part of dst[0 .. n0+n1+n2).  The bulk moves as 32-byte stores ALIGNED
-// ON THE DESTINATION (one whole DRAM sector per store); inside a segment the source is read
-// as a sliding window of aligned 16-byte vectors (two shared-memory loads per store).  The at
-// most four "special" pieces — the < 32 bytes in front of the first aligned unit, the two
-// units that straddle a segment boundary, the < 32 bytes after the last unit — are assembled
-// from both sides of the boundary by ONE copy of the gather-and-merge code (instruction-cache
-// footprint matters: every lane of every emit warp runs this function).
-MGK_HD void copy3(uint8_t* dst, const uint8_t* S, const Seg3& g, int part, uint32_t own0) {
-  const uint32_t len = g.n0 + g.n1 + g.n2;
-  if (len == 0) return;
-  const uint32_t o1 = g.n0, o2 = g.n0 + g.n1;
-  const uint32_t b0 = g.s0, b1 = g.s1 - o1, b2 = g.s2 - o2;  // source offset of output byte y in segment j: bj + y
-  uint32_t hb = (32u - (uint32_t)((uintptr_t)dst & 31u)) & 31u;
-  if (hb > len) hb = len;
-  const uint32_t nfull = (len - hb) >> 5;
-  const uint32_t tail0 = hb + (nfull << 5), nt = len - tail0;
-  uint32_t split = (nfull * 3u) >> 3;
-  if (own0 > hb && ((own0 - hb + 31u) >> 5) > split) split = (own0 - hb + 31u) >> 5;
-  if (split > nfull) split = nfull;
-  const uint32_t x_lo = part == PART_TAIL ? hb + (split << 5) : hb;   // whole units of this part: [x_lo, x_hi)
-  const uint32_t x_hi = part == PART_HEAD ? hb + (split << 5) : tail0;
-  if (nfull == 0 && nt == 0) {   // the whole record sits in front of the first aligned boundary
-    if (part != PART_TAIL)
-      for (uint32_t y = 0; y < len; ++y) dst[y] = (uint8_t)s_u8(S, (y >= o2 ? b2 : (y >= o1 ? b1 : b0)) + y);
-    return;
-  }
-  // ---- whole units that lie inside one segment
-  MGK_LOOP_ROLLED
-  for (int j = 0; j < 3; ++j) {
-    const uint32_t bj = j == 0 ? b0 : (j == 1 ? b1 : b2);
-    const uint32_t beg = j == 0 ? 0u : (j == 1 ? o1 : o2);
-    uint32_t end = j == 0 ? o1 : (j == 1 ? o2 : len);
-    if (end > x_hi) end = x_hi;
-    uint32_t x = beg <= hb ? hb : hb + (((beg - hb) + 31u) & ~31u);   // first unit that starts inside the segment
-    if (x < x_lo) x = x_lo;
-    if (x + 32u <= end) {
-      const uint32_t addr = bj + x, sh = addr & 15u;
-      uint32_t al = addr - sh;
-      uint4 lo = s_v4(S, al);
-      do {
-        const uint4 mid = s_v4(S, al + 16u), hi = s_v4(S, al + 32u);
-        al += 32u;
-        st_v8(dst + x, shift16(lo, mid, sh), shift16(mid, hi, sh));
-        lo = hi;
-        x += 32u;
-      } while (x + 32u <= end);
+// ---------------------------------------------------------------- one byte range, one half-warp
+// Lane l16 (0..15) of a half-warp writes its share of dst[0 .. n) = S[src .. src+n), with output
+// byte `patch_at` (>= n: none) replaced by patch_val.  Lane u takes the 16-byte units u, u+16, ...
+// of the destination-aligned middle; lane l the l-th byte in front of it and the l-th after it.
+MGK_HD void copy_piece(uint8_t* dst, const uint8_t* S, uint32_t src, uint32_t n, int l16, uint32_t patch_at, uint32_t patch_val) {
+  uint32_t hb = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  if (hb > n) hb = n;
+  const uint32_t nfull = (n - hb) >> 4, tail0 = hb + (nfull << 4);
+  for (uint32_t u = (uint32_t)l16; u < nfull; u += 16u) {
+    const uint32_t x = hb + (u << 4);
+    uint4 w = ld16u(S, src + x);
+    if (patch_at - x < 16u) {
+      const int i = (int)(patch_at - x);
+      w.x = put_byte(w.x, i, patch_val);
+      w.y = put_byte(w.y, i - 4, patch_val);
+      w.z = put_byte(w.z, i - 8, patch_val);
+      w.w = put_byte(w.w, i - 12, patch_val);
     }
+    *reinterpret_cast<uint4*>(dst + x) = w;
   }
-  // ---- the special pieces: 0 head fragment, 1 / 2 unit across the boundary at o1 / o2, 3 tail fragment
-  const int tail_owner = own0 > tail0 ? PART_HEAD : PART_TAIL;   // a staged header reaching into the tail keeps it in the head part
-  uint32_t done_unit = 0xffffffffu;
-  MGK_LOOP_ROLLED
-  for (int k = 0; k < 4; ++k) {
-    uint32_t x;
-    bool on;
-    if (k == 0) {
-      x = hb - 32u;
-      on = hb != 0u && part != PART_TAIL;
-    } else if (k == 3) {
-      x = tail0;
-      on = nt != 0u && (part == PART_ALL || part == tail_owner);
-    } else {
-      const uint32_t o = k == 1 ? o1 : o2;
-      x = hb + ((o - hb) & ~31u);                       // unit holding output byte o, if o is past the head fragment
-      on = o > hb && o < tail0 && x != o && x >= x_lo && x + 32u <= x_hi && x != done_unit && (k == 1 ? g.n1 + g.n2 : g.n2) != 0u;
-      if (on) done_unit = x;
-    }
-    if (!on) continue;
-    // 2 x 16 output bytes starting at output offset x (may hang over either end of the record)
-    uint4 wa, wb;
-    wa.x = wa.y = wa.z = wa.w = 0;
-    wb = wa;
-    MGK_LOOP_ROLLED
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t xh = x + 16u * (uint32_t)h, xe = xh + 16u;
-      if ((int)xe <= 0 || (int)xh >= (int)len) continue;   // half entirely outside the record
-      int j = ((int)xh >= (int)o2 && g.n2) ? 2 : (((int)xh >= (int)o1 && g.n1) ? 1 : 0);   // never an empty segment:
-      if (j == 0 && g.n0 == 0) j = g.n1 ? 1 : 2;                                             // its base offset is meaningless
-      uint4 w = gather16(S, (j == 2 ? b2 : (j == 1 ? b1 : b0)) + xh);
-      if (j < 1 && (int)o1 < (int)xe && g.n1) w = merge16(w, gather16(S, b1 + xh), (int)(o1 - xh));
-      if (j < 2 && (int)o2 < (int)xe && g.n2) w = merge16(w, gather16(S, b2 + xh), (int)(o2 - xh));
-      if (h == 0) wa = w;
-      else wb = w;
-    }
-    if (k == 0) store_before(dst + hb, wa, wb, hb);
-    else if (k == 3) store_after(dst + tail0, wa, wb, nt);
-    else st_v8(dst + x, wa, wb);
-  }
+  if ((uint32_t)l16 < hb) dst[l16] = (uint8_t)((uint32_t)l16 == patch_at ? patch_val : s_u8(S, src + (uint32_t)l16));
+  const uint32_t y = tail0 + (uint32_t)l16;
+  if (y < n) dst[y] = (uint8_t)(y == patch_at ? patch_val : s_u8(S, src + y));
 }
 
 // ---------------------------------------------------------------- header rewrite
@@ -294,15 +95,29 @@ struct HdrInfo {
   uint32_t z, f1, f2;  // first kept byte of the read number (== sep if none), of the two 3-digit fields
   uint32_t sep;        // the '/' (header length - 3, src/lib.rs:1007)
 };
-
+MGK_HD uint32_t bytes_ne(uint32_t x, uint32_t pat) {   // 0x80 in every byte of x that differs from the pattern byte, exact
+  const uint32_t v = x ^ pat;
+  return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
+}
 MGK_HD HdrInfo hdr_info(const Params& P, const uint8_t* S, const RecGeom& G) {
   HdrInfo h;
   const uint32_t L = (uint32_t)P.L, H = G.h2;
   h.sep = G.s2 - 3u;
-  h.f1 = s_u8(S, H + L + 3u) != '0' ? H + L + 3u : (s_u8(S, H + L + 4u) != '0' ? H + L + 4u : H + L + 5u);
-  h.f2 = s_u8(S, H + L + 7u) != '0' ? H + L + 7u : (s_u8(S, H + L + 8u) != '0' ? H + L + 8u : H + L + 9u);
+  // bytes H+L+3 .. H+L+18: ccc R rrr and the first nine digits of the read number, in one go
+  const uint4 v = ld16u(S, H + L + 3u);
+  const uint32_t Z = 0x30303030u, C = 0x00204081u;   // 0x80 flags of a word -> 4 bits at the top of the product
+  const uint32_t nz = ((bytes_ne(v.x, Z) * C) >> 28) | (((bytes_ne(v.y, Z) * C) >> 24) & 0xf0u) | (((bytes_ne(v.z, Z) * C) >> 20) & 0xf00u) |
+                      (((bytes_ne(v.w, Z) * C) >> 16) & 0xf000u);   // bit k <=> byte k is not '0'
+  h.f1 = (nz & 1u) ? H + L + 3u : ((nz & 2u) ? H + L + 4u : H + L + 5u);
+  h.f2 = (nz & 0x10u) ? H + L + 7u : ((nz & 0x20u) ? H + L + 8u : H + L + 9u);
   uint32_t z = H + L + 10u;
-  while (z < h.sep && s_u8(S, z) == '0') ++z;
+  const uint32_t rest = nz >> 7;   // the read number's first nine digits
+  if (rest) {
+    z += (uint32_t)ctz32(rest);
+  } else {
+    z += 9u;
+    while (z < h.sep && s_u8(S, z) == '0') ++z;   // longer runs of zeros: rare
+  }
   h.z = z < h.sep ? z : h.sep;
   return h;
 }
@@ -315,10 +130,8 @@ struct TailSpec {
   uint32_t i7_off, i7_len, i5_off, i5_len, has_i5, has_bar;
 };
 MGK_HD uint32_t barcode_len(const TailSpec& t) { return t.has_bar ? t.i7_len + (t.has_i5 ? 1u + t.i5_len : 0u) : 0u; }
-MGK_HD uint32_t tail_len(const TailSpec& t, int full) {
-  const uint32_t u = t.umi_len ? 1u + t.umi_len : 0u;
-  (void)full;
-  return u + 7u + barcode_len(t);   // both flavours: one separator more than the umi, n, ":N:0:"
+MGK_HD uint32_t tail_len(const TailSpec& t) {   // both flavours: one separator more than the umi, n, ":N:0:"
+  return (t.umi_len ? 1u + t.umi_len : 0u) + 7u + barcode_len(t);
 }
 MGK_HD TailSpec make_tail(const Params& P, const RecGeom& G, int bar_t, int umi_t) {
   TailSpec t;
@@ -344,26 +157,123 @@ MGK_HD TailSpec make_tail(const Params& P, const RecGeom& G, int bar_t, int umi_
   return t;
 }
 
-// A header is written front to back through a cursor `o`: into the (record, read)'s staging
-// slot in S or, for headers too long for the slot, straight to the destination (byte stores;
-// correct for any length, just slower).  ONE out-of-line copy of the byte loop serves every
-// piece: the emit code runs in every warp of the kernel and has to stay small.
+// Short pieces (digits, index, UMI) go through a cursor: 16 source bytes per round, fetched with
+// independent word loads, then stored byte by byte (the cursor has any alignment): no load depends on
+// a store.  ONE out-of-line copy: the emit code has to stay small (instruction cache).
 MGK_HD_NOINLINE uint8_t* put_span(uint8_t* o, const uint8_t* S, uint32_t src, uint32_t n) {
-  uint32_t k = 0;
   MGK_LOOP_ROLLED
-  for (; k + 4u <= n; k += 4u) {   // loads first: the cursor may alias S as far as the compiler knows
-    const uint32_t a = s_u8(S, src + k), b = s_u8(S, src + k + 1u), c = s_u8(S, src + k + 2u), d = s_u8(S, src + k + 3u);
-    o[0] = (uint8_t)a;
-    o[1] = (uint8_t)b;
-    o[2] = (uint8_t)c;
-    o[3] = (uint8_t)d;
-    o += 4;
+  for (uint32_t k = 0; k < n; k += 16u) {
+    const uint4 v = ld16u(S, src + k);
+    const uint32_t m = n - k;   // bytes of this round that count
+    uint32_t w = v.x;
+    if (m > 0) o[k + 0] = (uint8_t)w;
+    if (m > 1) o[k + 1] = (uint8_t)(w >> 8);
+    if (m > 2) o[k + 2] = (uint8_t)(w >> 16);
+    if (m > 3) o[k + 3] = (uint8_t)(w >> 24);
+    w = v.y;
+    if (m > 4) o[k + 4] = (uint8_t)w;
+    if (m > 5) o[k + 5] = (uint8_t)(w >> 8);
+    if (m > 6) o[k + 6] = (uint8_t)(w >> 16);
+    if (m > 7) o[k + 7] = (uint8_t)(w >> 24);
+    w = v.z;
+    if (m > 8) o[k + 8] = (uint8_t)w;
+    if (m > 9) o[k + 9] = (uint8_t)(w >> 8);
+    if (m > 10) o[k + 10] = (uint8_t)(w >> 16);
+    if (m > 11) o[k + 11] = (uint8_t)(w >> 24);
+    w = v.w;
+    if (m > 12) o[k + 12] = (uint8_t)w;
+    if (m > 13) o[k + 13] = (uint8_t)(w >> 8);
+    if (m > 14) o[k + 14] = (uint8_t)(w >> 16);
+    if (m > 15) o[k + 15] = (uint8_t)(w >> 24);
   }
-  MGK_LOOP_ROLLED
-  for (; k < n; ++k) *o++ = (uint8_t)s_u8(S, src + k);
-  return o;
+  return o + n;
 }
-MGK_HD uint8_t* put_tail(uint8_t* o, const uint8_t* S, const TailSpec& t, uint32_t n_digit, int full) {
+
+// ---------------------------------------------------------------- what a read's output is made of
+// Every output record, matched or not, is header | "\n" sequence | "\n+\n" qualities (+ "\n").
+// which = 2: barcode read -> new header, barcode trimmed off sequence and qualities
+//            (src/lib.rs:1240-1327); unmatched reads verbatim (:1225-1235)
+// which = 1: paired read  -> in illumina mode the barcode read's new header with its own
+//            read-number digit (src/sample_data.rs:302-328, src/lib.rs:1288), the rest of the
+//            record verbatim (:1328-1331); with --mgi-full-header ITS OWN header line (:1306-1318)
+// `out_len` = the record's output length as planned by k_match_plan (RecMeta::len2 / len1): the
+// header length follows from it without looking at the header bytes.
+enum { HDR_VERBATIM = 0, HDR_SLOT0 = 1, HDR_SLOT1 = 2 };
+struct ReadPlan {
+  uint32_t len;          // 0: nothing is written for this read
+  uint32_t hl, n1, n2;   // bytes of the three parts (the closing '\n' of a trimmed read not counted)
+  uint32_t h_src, src1, src2;   // S offsets of the header line (verbatim case), of "\n" seq, of "\n+\n" qual
+  int hdr;               // HDR_VERBATIM: from the input; HDR_SLOT0/1: rewritten, from that staging slot of the record
+  int trim;              // the closing '\n' is stored on its own
+  uint32_t patch_at;     // illumina paired read: index of the read-number digit inside the header (else ~0)
+  uint32_t patch_src;    // ... and where its own digit is in S
+};
+MGK_HD ReadPlan plan_read(const Params& P, const RecGeom& G, int which, int sample, int bar_t, uint32_t out_len) {
+  ReadPlan r;
+  const bool br = which == 2;
+  const uint32_t h = br ? G.h2 : G.h1, s = br ? G.s2 : G.s1, p = br ? G.p2 : G.p1, e = br ? G.e2 : G.e1;
+  const bool matched = sample < P.S;
+  r.len = (br && matched && !P.read2_has_sequence) ? 0u : out_len;   // samples get no barcode-read file, src/sample_data.rs:35-44
+  r.trim = br && matched;
+  const uint32_t wbl = (r.trim && !P.keep_barcode) ? (uint32_t)P.BL : 0u;
+  r.n1 = p - wbl - s;                                   // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
+  r.n2 = r.trim ? e - wbl - (p - 1u) : e + 2u - p;      // "\n+\n" qual[..-wbl]; a trimmed read's closing '\n' apart (:1324-1327)
+  r.hl = out_len - r.n1 - r.n2 - (r.trim ? 1u : 0u);
+  r.h_src = h;
+  r.src1 = s - 1u;
+  r.src2 = p - 1u;
+  r.hdr = HDR_VERBATIM;
+  r.patch_at = 0xffffffffu;
+  r.patch_src = 0;
+  if (matched && P.out_mode != MGK_OUT_MGI) {
+    if (P.out_mode == MGK_OUT_MGI_FULL_HEADER) {
+      r.hdr = br ? HDR_SLOT0 : HDR_SLOT1;
+    } else {
+      r.hdr = HDR_SLOT0;
+      if (!br) {   // fix_paired_read_header: n is tail_offset = len(barcode) + 6 from the end, src/lib.rs:1019
+        r.patch_at = r.hl - 6u - barcode_text_len(P, bar_t);
+        r.patch_src = G.s1 - 2u;
+      }
+    }
+  }
+  return r;
+}
+
+// Rewritten header of one read into its staging slot `o` (16-byte aligned), in two independent halves:
+// part 0 = everything in front of the tail, part 1 = the tail ([umi] n ":N:0:" barcode).
+// which = 2: the barcode read's (illumina: also the paired read's, up to one digit); which = 1:
+// the paired read's own full header (--mgi-full-header only).  `hl` = the header's length.
+MGK_HD void build_header(const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G, int which, int bar_t, int umi_t,
+                         uint32_t hl, uint8_t* o, int part) {
+  const TailSpec t = make_tail(P, G, bar_t, umi_t);
+  const uint32_t tl = tail_len(t);
+  const bool full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
+  const uint32_t h = which == 2 ? G.h2 : G.h1, s = which == 2 ? G.s2 : G.s1;
+  if (part == 0) {
+    if (full) {
+      put_span(o, S, h, s - h - 1u);   // its own header line without the '\n'
+    } else {                             // prefix lane ":" readno ":" ccc ":" rrr
+      const HdrInfo hi = hdr_info(P, S, G);
+      const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len;
+      if (((uintptr_t)o & 15u) == 0) {   // a staging slot: whole vectors (the constants are aligned too)
+        MGK_LOOP_ROLLED
+        for (uint32_t k = 0; k < Pn; k += 16u) *reinterpret_cast<uint4*>(o + k) = s_v4(S, cs0 + k);
+        o += Pn;
+      } else {
+        o = put_span(o, S, cs0, Pn);
+      }
+      *o++ = (uint8_t)s_u8(S, H + L + 1u);
+      *o++ = ':';
+      o = put_span(o, S, hi.z, hi.sep - hi.z);
+      *o++ = ':';
+      o = put_span(o, S, hi.f1, H + L + 6u - hi.f1);
+      *o++ = ':';
+      put_span(o, S, hi.f2, H + L + 10u - hi.f2);
+    }
+    return;
+  }
+  o += hl - tl;
+  const uint32_t n_digit = s_u8(S, s - 2u);   // src/lib.rs:1275,1288,1302,1314
   if (full) {
     *o++ = ' ';
     if (t.umi_len) {
@@ -387,101 +297,34 @@ MGK_HD uint8_t* put_tail(uint8_t* o, const uint8_t* S, const TailSpec& t, uint32
     o = put_span(o, S, t.i7_off, t.i7_len);
     if (t.has_i5) {
       *o++ = '+';
-      o = put_span(o, S, t.i5_off, t.i5_len);
+      put_span(o, S, t.i5_off, t.i5_len);
     }
   }
-  return o;
-}
-MGK_HD uint32_t illumina_header_len(const Params& P, const RecGeom& G, const HdrInfo& hi, const TailSpec& t) {
-  const uint32_t L = (uint32_t)P.L, H = G.h2;
-  return (uint32_t)P.prefix_len + 2u + (hi.sep - hi.z) + 1u + (H + L + 6u - hi.f1) + 1u + (H + L + 10u - hi.f2) + tail_len(t, 0);
-}
-// prefix lane ":" readno ":" ccc ":" rrr tail.  `cs0` = S offset of the prefix; `vec`: the cursor is
-// a 16-byte aligned staging slot, so the constant prefix goes in as whole vectors.
-MGK_HD uint8_t* put_illumina_header(uint8_t* o, bool vec, const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G,
-                                    const HdrInfo& hi, const TailSpec& t, uint32_t n_digit) {
-  const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len;
-  if (vec) {
-    MGK_LOOP_ROLLED
-    for (uint32_t k = 0; k < Pn; k += 16u) *reinterpret_cast<uint4*>(o + k) = s_v4(S, cs0 + k);
-    o += Pn;
-  } else {
-    o = put_span(o, S, cs0, Pn);
-  }
-  *o++ = (uint8_t)s_u8(S, H + L + 1u);
-  *o++ = ':';
-  o = put_span(o, S, hi.z, hi.sep - hi.z);
-  *o++ = ':';
-  o = put_span(o, S, hi.f1, H + L + 6u - hi.f1);
-  *o++ = ':';
-  o = put_span(o, S, hi.f2, H + L + 10u - hi.f2);
-  return put_tail(o, S, t, n_digit, 0);
 }
 
-// ---------------------------------------------------------------- the emit roles
-constexpr uint32_t HDR_SLOT_BYTES = 96;     // per (record, read) staging slot; longer headers take the byte-store path
-// Every record, matched or not, is cut into the SAME three pieces (header line | sequence
-// line | "+" and quality lines) so that the lanes of a warp, each on its own record, run the
-// copy loops of copy3() in step whatever their records look like; and both reads go through
-// the SAME function so that the four emit roles of the kernel share one set of instructions.
-//
-// which = 2: barcode read -> new header, barcode trimmed off sequence and qualities
-//            (src/lib.rs:1240-1327); unmatched reads verbatim (:1225-1235)
-// which = 1: paired read  -> in illumina mode the barcode read's new header with its own
-//            read-number digit (src/sample_data.rs:302-328, src/lib.rs:1288), the rest of the
-//            record verbatim (:1328-1331); with --mgi-full-header ITS OWN header line (:1306-1318)
-// `hs` = this (record, read)'s staging slot (S offset, 16-byte aligned), written by the
-// PART_HEAD thread only.
-MGK_HD void emit_read(const Params& P, uint8_t* S, uint32_t hs, uint32_t cs0, const RecGeom& G, int which, int sample, int bar_t,
-                      int umi_t, uint8_t* d, int part) {
-  const bool br = which == 2;
-  const uint32_t h = br ? G.h2 : G.h1, s = br ? G.s2 : G.s1, p = br ? G.p2 : G.p1, e = br ? G.e2 : G.e1;
-  const bool matched = sample < P.S;
-  if (br && matched && !P.read2_has_sequence) return;   // samples get no barcode-read file, src/sample_data.rs:35-44
-  const bool trim = br && matched;
-  const uint32_t wbl = (trim && !P.keep_barcode) ? (uint32_t)P.BL : 0u;
-  Seg3 g;
-  g.s1 = s - 1u;
-  g.n1 = p - wbl - s;                                   // "\n" seq[..-wbl], src/lib.rs:1293,1321-1323
-  g.s2 = p - 1u;
-  g.n2 = trim ? e - wbl - (p - 1u) : e + 2u - p;        // "\n+\n" qual[..-wbl]; a trimmed read's closing '\n' is stored on its own
-  g.s0 = h;
-  g.n0 = s - 1u - h;                                    // the header line as it is
-  uint32_t own0 = 0, skip = 0;
-  if (matched && P.out_mode != MGK_OUT_MGI) {
-    const int full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
-    const TailSpec t = make_tail(P, G, bar_t, umi_t);
-    const uint32_t n_digit = s_u8(S, s - 2u);           // src/lib.rs:1275,1288,1302,1314
-    HdrInfo hi;
-    uint32_t hl;
-    if (full) {
-      hi.z = hi.f1 = hi.f2 = hi.sep = 0;
-      hl = s - h - 1u + tail_len(t, 1);
-    } else {
-      hi = hdr_info(P, S, G);
-      hl = illumina_header_len(P, G, hi, t);
-    }
-    const bool slot = hl <= HDR_SLOT_BYTES;
-    if (part != PART_TAIL) {   // too long for the slot: bytes straight to the destination
-      uint8_t* o = slot ? S + hs : d;
-      if (full) {
-        o = put_span(o, S, h, s - h - 1u);
-        put_tail(o, S, t, n_digit, 1);
-      } else {
-        put_illumina_header(o, slot, P, S, cs0, G, hi, t, n_digit);
-      }
-    }
-    if (slot) {
-      g.s0 = hs;
-      g.n0 = hl;
-      own0 = hl;
-    } else {
-      g.s0 = g.n0 = 0;
-      skip = hl;
-    }
+constexpr uint32_t HDR_SLOT_BYTES = 96;    // staging slot of a rewritten header; longer ones are built at their destination
+
+// The two byte ranges of a read's output that come straight from the input:
+//   k = 0: [header line verbatim |] "\n" sequence
+//   k = 1: "\n+\n" qualities [| "\n" unless the read is trimmed: then its closing '\n' is stored apart]
+struct Piece {
+  uint32_t dst_off, src, n;   // n == 0: no such piece
+};
+MGK_HD Piece read_piece(const ReadPlan& r, int k) {
+  Piece pc;
+  pc.dst_off = pc.src = pc.n = 0;
+  if (r.len == 0) return pc;
+  const bool staged = r.hdr != HDR_VERBATIM;
+  if (k == 0) {
+    pc.dst_off = staged ? r.hl : 0u;
+    pc.src = staged ? r.src1 : r.h_src;
+    pc.n = (staged ? 0u : r.hl) + r.n1;
+  } else {
+    pc.dst_off = r.hl + r.n1;
+    pc.src = r.src2;
+    pc.n = r.n2;
   }
-  copy3(d + skip, S, g, part, own0);
-  if (trim && part != PART_HEAD) d[skip + g.n0 + g.n1 + g.n2] = '\n';   // src/lib.rs:1327
+  return pc;
 }
 
 // ---------------------------------------------------------------- QC sums out of S

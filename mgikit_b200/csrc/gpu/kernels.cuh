@@ -39,11 +39,13 @@ enum : uint32_t {
 };
 
 struct __align__(16) RecMeta {
-  uint32_t off2, off1;   // byte offset of the record inside its (tile, bin) run
-  uint16_t sample, bin;
-  int8_t bar_t, umi_t;
-  uint8_t mism, flags;   // flags bit0: format error
+  uint32_t off2, off1;   // byte offset of the record inside its (tile, bin) run, barcode read / paired read
+  uint16_t sample;       // 0..S+1; the bin is writing[sample] for a matched read, the sample itself otherwise
+  uint16_t len2, len1;   // output bytes of the two records
+  uint8_t tpl;           // template that cut the barcode text (low nibble) and the UMI (high nibble); 15 = none
+  uint8_t flags;         // bit0: format error
 };
+static_assert(sizeof(RecMeta) == 16, "RecMeta is one 16-byte row");
 
 struct Status {
   uint32_t n_records, consumed2, consumed1, error;
@@ -319,9 +321,15 @@ struct StoredNearest {
 };
 
 __device__ __forceinline__ bool probe_exact(const Params& P, const uint8_t* p, int len, int off, int mask, Nearest& n) {
-  const uint32_t sh = (uint32_t)((uintptr_t)p & 15u);
-  const uint4* q = reinterpret_cast<const uint4*>(p - sh);
-  const uint4 v = shift16(__ldg(q), __ldg(q + 1), sh);
+  // 16 bytes at any alignment: five aligned words, funnel-shifted
+  const uint32_t sh = (uint32_t)((uintptr_t)p & 3u) * 8u;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p - ((uintptr_t)p & 3u));
+  const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4);
+  uint4 v;
+  v.x = __funnelshift_r(w0, w1, sh);
+  v.y = __funnelshift_r(w1, w2, sh);
+  v.z = __funnelshift_r(w2, w3, sh);
+  v.w = __funnelshift_r(w3, w4, sh);
   uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
   if (len < 8) {
     lo &= (1ull << (8 * len)) - 1ull;
@@ -452,9 +460,10 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
     uint32_t l2 = 0, l1 = 0;
     RecMeta mt;
     mt.off2 = mt.off1 = 0;
-    mt.sample = mt.bin = 0;
-    mt.bar_t = mt.umi_t = -1;
-    mt.mism = mt.flags = 0;
+    mt.sample = 0;
+    mt.len2 = mt.len1 = 0;
+    mt.tpl = 0xff;
+    mt.flags = 0;
     bool unassigned = false, is_amb = false;
     uint32_t bar_off = 0;
     RecGeom G;
@@ -479,10 +488,10 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
       l2 = pl.len2;
       l1 = pl.len1;
       mt.sample = (uint16_t)mo.sample;
-      mt.bin = (uint16_t)bin;
-      mt.bar_t = (int8_t)mo.bar_t;
-      mt.umi_t = (int8_t)mo.umi_t;
-      mt.mism = (uint8_t)mo.mism;
+      mt.len2 = (uint16_t)l2;
+      mt.len1 = (uint16_t)l1;
+      mt.tpl = (uint8_t)((mo.bar_t & 15) | ((mo.umi_t & 15) << 4));
+      if (l2 > 0xffffu || l1 > 0xffffu) atomicOr(&c.status->error, ERR_REC_TOO_LONG);
       if (!pl.fmt_error) {
         // update_mismatches(sample_id, curr_mismatch + 1, 1), src/lib.rs:1212
         if (mism_acc) atomicAdd(&mism_acc[mo.sample * P.mism_w + mo.mism + 1], 1u);   // flushed once per CTA
@@ -633,38 +642,56 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
 }
 
 // ------------------------------------------------------------------ K4
-// Persistent, one CTA per SM.  Each CTA owns a contiguous run of plan tiles and
-// streams its records through two shared-memory stages: while the warps emit
-// the records of stage s, the TMA engine (cp.async.bulk, completion on an
-// mbarrier) fills stage s^1 with the next tile's bytes of both reads, its
-// newline positions, its RecMeta rows and its row of bin offsets.  Every byte
-// of the input therefore crosses HBM->SM exactly once in this kernel, as
-// full-width bulk copies, and every output byte leaves as part of a 16-byte
-// store aligned on its destination (emit3, emit_logic.cuh).
+// TMA in, scalar threads for the control-heavy crumbs, half-warps for the bytes.  Persistent,
+// one CTA per SM.  A producer warp keeps two shared-memory stages full with bulk copies
+// (cp.async.bulk + mbarrier) of the next 128 records: text of both reads, newline rows, RecMeta
+// rows, bin-offset row.  On the staged tile, concurrently:
+//   * 16 warps, one thread per (record, role): role 0 / 1 build the front / the tail of the
+//     rewritten header in a staging slot, role 2 / 3 the QC sums of the paired / barcode read
+//     (and --validate): scalar work with data-dependent branches, a different record per lane;
+//   * 12 warps, one HALF-WARP per byte range: every output record is header | "\n" sequence |
+//     "\n+\n" qualities (plan_read), the last two straight out of the staged input.  copy_piece
+//     writes 16-byte units aligned on the destination, adjacent lanes adjacent units.
+// then, after one barrier, all 28 warps move the staged headers out the same way (the paired
+// read's copy with its own read-number digit patched in).  Every input byte crosses HBM->SM
+// once (bulk copies), every output byte SM->HBM once, in coalesced stores.
 constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
-// one thread per (record, role): 0/1 head and tail part of the barcode read, 2/3 of the paired read,
-// 4 QC of the paired read (+ validate), 5 QC of the barcode read
-constexpr int EMIT_ROLES = 6;
-constexpr int EMIT_WORKERS = EMIT_ROLES * EMIT_NMAX;
-constexpr int EMIT_THREADS = EMIT_WORKERS + 32;   // + the producer warp (bulk copies of the next tile)
+constexpr int EMIT_SROLES = 4;
+constexpr int EMIT_SWARPS = EMIT_SROLES * EMIT_NMAX / 32;
+constexpr int EMIT_WWARPS = 8;
+constexpr int EMIT_PRODUCER = EMIT_SWARPS + EMIT_WWARPS;
+constexpr int EMIT_THREADS = (EMIT_PRODUCER + 1) * 32;
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
-// staging slot of (role, record): inside a warp's 32 slots, rows of 8 are skewed by 16 bytes so that the lanes spread
-// over all banks
+// staging slot k (0 barcode read's header, 1 paired read's own full header) of record i; inside a warp's 32 records,
+// rows of 8 are skewed by 16 bytes so that the lanes spread over all banks
 constexpr uint32_t HDR_WARP_BYTES = 32u * HDR_SLOT_BYTES + 64u;
-constexpr uint32_t HDR_ROLE_BYTES = (EMIT_NMAX / 32) * HDR_WARP_BYTES;
-constexpr uint32_t HDR_AREA_BYTES = 2u * HDR_ROLE_BYTES;
-__host__ __device__ inline uint32_t hdr_slot(uint32_t role, uint32_t i) {
-  return role * HDR_ROLE_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 16u * ((i >> 3) & 3u);
+constexpr uint32_t HDR_KIND_BYTES = (EMIT_NMAX / 32) * HDR_WARP_BYTES;
+constexpr uint32_t HDR_AREA_BYTES = 2u * HDR_KIND_BYTES;
+__host__ __device__ inline uint32_t hdr_slot(uint32_t k, uint32_t i) {
+  return k * HDR_KIND_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 16u * ((i >> 3) & 3u);
 }
 
 struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 16-byte aligned
   uint32_t consts;        // prefix + literals (+ slack)
   uint32_t stats;         // [total][QC_SLOTS] u32
+  uint32_t writing;       // [total] writing_samples (bin of a matched sample)
   uint32_t hdr;           // header staging slots, hdr_slot()
+  uint32_t desc;          // [EMIT_NMAX][EMIT_PIECES] PieceDesc of the tile in flight
   uint32_t stage0, stage_stride;   // two stages, each: nl2 | nl1 | meta | bins | bytes
   uint32_t nl1, meta, bins, bytes;   // offsets inside a stage (nl2 at 0)
   uint32_t cap;           // bytes of text one stage holds (both reads)
   uint32_t total_bytes;
+};
+
+// One byte range to move: S[src .. src+n) -> out2/out1 + dst.  Six per record: piece 0 / 1 of the barcode read,
+// piece 0 / 1 of the paired read (all straight from the staged input), staged header of the barcode / paired read.
+constexpr int EMIT_PIECES = 6;
+struct __align__(16) PieceDesc {
+  uint32_t dst;   // offset in the output buffer of its read
+  uint32_t src;   // S offset
+  uint32_t n;     // bytes (0: nothing)
+  uint32_t aux;   // bit 31: paired-read buffer; bit 30: store '\n' at dst + n (a trimmed read's closing newline);
+                  // bits 0-15: 1 + index of a byte to replace (0: none), bits 16-23: its value
 };
 
 struct StageDesc {
@@ -681,7 +708,6 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ StageDesc s_desc[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int PRODUCER_WARP = EMIT_WORKERS / 32;
 
   copy_params_to_smem(&P, Pg);
   if (tid == 0) {
@@ -691,22 +717,24 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
   __syncthreads();
   const int total = P.total, paired = P.paired;
-  {  // constants and QC accumulators
+  {  // constants, QC accumulators, bin of every sample
     const uint32_t nconst = (uint32_t)P.prefix_len + LIT_BYTES;
     for (uint32_t i = tid; i < nconst; i += EMIT_THREADS) smem[lay.consts + i] = P.consts[i];
     uint32_t* st = reinterpret_cast<uint32_t*>(smem + lay.stats);
     for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) st[i] = 0;
+    int32_t* wr = reinterpret_cast<int32_t*>(smem + lay.writing);
+    for (int i = tid; i < total; i += EMIT_THREADS) wr[i] = P.writing[i];
   }
+  const int32_t* s_writing = reinterpret_cast<const int32_t*>(smem + lay.writing);
   const uint32_t n_rec = device_n_records(c, P);
-  if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY)) return;  // nothing safe to write
+  if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY | ERR_REC_TOO_LONG)) return;  // nothing safe to write
   // this CTA's plan tiles: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
-  // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk
-  // size (measured equal to a contiguous run per CTA on chunks of 0.5-4 M pairs; kept for the bounded page set).
+  // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk size.
   const uint32_t n_pt = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
   if (blockIdx.x >= n_pt) return;
   const uint32_t bins_stride = (2u * (uint32_t)total + 3u) & ~3u;
 
-  // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are halved below)
+  // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are shrunk below)
   uint32_t n_tile;
   {
     const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
@@ -767,7 +795,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     start2 = e2;
     start1 = e1;
   };
-  if (warp == PRODUCER_WARP && lane == 0) produce(0);
+  if (warp == EMIT_PRODUCER && lane == 0) produce(0);
   __syncthreads();
 
   uint32_t* s_stats = reinterpret_cast<uint32_t*>(smem + lay.stats);
@@ -781,76 +809,218 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       }
     }
   };
-  const int role = tid / EMIT_NMAX;            // warp-uniform; EMIT_ROLES = the producer warp
-  const uint32_t i = (uint32_t)(tid % EMIT_NMAX);
-  const uint32_t hs = lay.hdr + hdr_slot(role >= 2 ? 1u : 0u, i);
 
-  unsigned long long t_wait = 0, t_work = 0, t_bar = 0, t_prod = 0;
+  unsigned long long t_wait = 0, t_work = 0, t_bar = 0, t_prod = 0, t_s2 = 0, t_s4 = 0;
   for (uint32_t k = 0;; ++k) {
     const int s = (int)(k & 1u);
     const long long c0 = c.prof ? clock64() : 0;
-    if (warp == PRODUCER_WARP && lane == 0) produce(s ^ 1);
+    if (warp == EMIT_PRODUCER && lane == 0) produce(s ^ 1);
     const long long c1 = c.prof ? clock64() : 0;
     t_prod += (unsigned long long)(c1 - c0);
     const StageDesc d = s_desc[s];
     if (d.n == 0) break;
-    const int val_role = paired ? 4 : 5;   // --validate goes to the QC thread every record has
-    const bool idle = role >= EMIT_ROLES || i >= d.n || (!paired && role >= 2 && role <= 4) ||
-                      (role >= 4 && P.report_level == 0 && !(P.validate && role == val_role));
-    long long c2 = c1;
-    if (!idle) {
-      mbar_wait(&s_bar[s], (k >> 1) & 1u);
-      c2 = c.prof ? clock64() : 0;
-      t_wait += (unsigned long long)(c2 - c1);
-      unsigned char* st = smem + (lay.stage0 + (uint32_t)s * lay.stage_stride);
-      const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
-      const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
-      const RecMeta mt = reinterpret_cast<const RecMeta*>(st + lay.meta)[i];
-      const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
-      if (!(mt.flags & 1)) {   // layout errors are reported through status, nothing is emitted
-        // S offsets of chunk byte 0 of either read
-        const uint32_t o2 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes - d.base2;
-        const uint32_t o1 = (lay.stage0 + (uint32_t)s * lay.stage_stride) + lay.bytes + d.off1 - d.base1;
-        RecGeom G;
-        {
-          const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
-          G.h2 = nl2s[4u * i + 3u] + 1u + o2;
-          G.s2 = a.x + 1u + o2;
-          G.p2 = a.y + 1u + o2;
-          G.q2 = a.z + 1u + o2;
-          G.e2 = a.w + o2;
-          G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
-          if (paired) {
-            const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
-            G.h1 = nl1s[4u * i + 3u] + 1u + o1;
-            G.s1 = b.x + 1u + o1;
-            G.p1 = b.y + 1u + o1;
-            G.q1 = b.z + 1u + o1;
-            G.e1 = b.w + o1;
-          }
-        }
-        const int sample = mt.sample, bin = mt.bin;
-        if (role < 4) {
-          const bool br = role < 2;
-          uint8_t* dst = br ? c.out2 + bins[bin] + mt.off2 : c.out1 + bins[total + bin] + mt.off1;
-          emit_read(P, smem, hs, lay.consts, G, br ? 2 : 1, sample, mt.bar_t, mt.umi_t, dst, role & 1);
+    if (warp < EMIT_PRODUCER) mbar_wait(&s_bar[s], (k >> 1) & 1u);
+    const long long c2 = c.prof ? clock64() : 0;
+    t_wait += (unsigned long long)(c2 - c1);
+    const uint32_t stage = lay.stage0 + (uint32_t)s * lay.stage_stride;
+    const unsigned char* st = smem + stage;
+    const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
+    const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
+    const RecMeta* metas = reinterpret_cast<const RecMeta*>(st + lay.meta);
+    const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
+    // S offsets of chunk byte 0 of either read
+    const uint32_t o2 = stage + lay.bytes - d.base2;
+    const uint32_t o1 = stage + lay.bytes + d.off1 - d.base1;
+    auto geom = [&](uint32_t i) {
+      RecGeom G;
+      const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
+      G.h2 = nl2s[4u * i + 3u] + 1u + o2;
+      G.s2 = a.x + 1u + o2;
+      G.p2 = a.y + 1u + o2;
+      G.q2 = a.z + 1u + o2;
+      G.e2 = a.w + o2;
+      G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
+      if (paired) {
+        const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
+        G.h1 = nl1s[4u * i + 3u] + 1u + o1;
+        G.s1 = b.x + 1u + o1;
+        G.p1 = b.y + 1u + o1;
+        G.q1 = b.z + 1u + o1;
+        G.e1 = b.w + o1;
+      }
+      return G;
+    };
+    auto dest = [&](const RecMeta& mt, int which) -> uint8_t* {   // where the record's output starts
+      const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
+      return which == 2 ? c.out2 + bins[bin] + mt.off2 : c.out1 + bins[total + bin] + mt.off1;
+    };
+
+    PieceDesc* descs = reinterpret_cast<PieceDesc*>(smem + lay.desc);
+    // ---- step 1, one thread per record: the record's byte ranges (where from, where to), so that the half-warps
+    // below start moving bytes after a single 16-byte load
+    if (warp < 2 * (EMIT_NMAX / 32)) {   // thread per (record, read)
+      const uint32_t i = (uint32_t)tid % EMIT_NMAX;
+      const int which = tid < EMIT_NMAX ? 2 : 1;
+      if (i < d.n) {
+        const RecMeta mt = metas[i];
+        auto put = [&](int kind, uint32_t dst, uint32_t src, uint32_t n, uint32_t aux) {
+          PieceDesc x;
+          x.dst = dst;
+          x.src = src;
+          x.n = n;
+          x.aux = aux;
+          descs[kind * EMIT_NMAX + i] = x;
+        };
+        const int k0 = which == 2 ? 0 : 2, kh = which == 2 ? 4 : 5;   // this read's piece 0, piece 1 = k0 + 1, staged header
+        if ((mt.flags & 1) || (which == 1 && !paired)) {   // layout errors are reported through status, nothing is emitted
+          put(k0, 0u, 0u, 0u, 0u);
+          put(k0 + 1, 0u, 0u, 0u, 0u);
+          put(kh, 0u, 0u, 0u, 0u);
         } else {
-          if (P.report_level > 0) {   // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
-            const QcSix q = qc_pair(P, smem, G, role == 4 ? 1 : 2);
-#pragma unroll
-            for (int j = 0; j < QC_SLOTS; ++j)
-              if (q.v[j]) atomicAdd(&s_stats[sample * QC_SLOTS + j], q.v[j]);
+          const RecGeom G = geom(i);
+          const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15);
+          const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
+          const uint32_t buf = which == 2 ? 0u : 1u << 31;
+          const uint32_t dst = which == 2 ? bins[bin] + mt.off2 : bins[total + bin] + mt.off1;
+          const ReadPlan r = plan_read(P, G, which, mt.sample, bar_t, which == 2 ? mt.len2 : mt.len1);
+          const Piece a = read_piece(r, 0), b = read_piece(r, 1);
+          put(k0, dst + a.dst_off, a.src, a.n, buf);
+          put(k0 + 1, dst + b.dst_off, b.src, b.n, buf | ((r.trim && r.len) ? 1u << 30 : 0u));
+          const bool staged = r.len && r.hdr != HDR_VERBATIM && r.hl <= HDR_SLOT_BYTES;
+          const uint32_t patch = r.patch_at != 0xffffffffu ? (r.patch_at + 1u) | ((uint32_t)smem[r.patch_src] << 16) : 0u;
+          put(kh, dst, lay.hdr + hdr_slot(staged ? (uint32_t)r.hdr - 1u : 0u, i), staged ? r.hl : 0u, buf | patch);
+        }
+      }
+    }
+    __syncthreads();
+    // A QUARTER-warp (8 lanes) moves one byte range: lane l takes the 16-byte units l and l + 8 of the range's
+    // destination-aligned middle (adjacent lanes, adjacent units: the 8 lanes write 128 contiguous bytes per store)
+    // and the l-th / (l + 8)-th byte in front of and after it.  Four ranges per warp and round, two stores per lane
+    // in flight.  Every warp of the CTA takes its share once its scalar role is done.
+    auto move_piece = [&](const PieceDesc pd, int l8) {
+      // every address and predicate first, then every shared-memory load, then every store: one load round trip
+      uint8_t* g = ((pd.aux >> 31) ? c.out1 : c.out2) + pd.dst;
+      const uint32_t hb = min((16u - (pd.dst & 15u)) & 15u, pd.n);   // the output buffers are 16-byte aligned
+      const uint32_t nfull = (pd.n - hb) >> 4, tail0 = hb + (nfull << 4);
+      const uint32_t pa = (pd.aux & 0xffffu) - 1u, pv = (pd.aux >> 16) & 0xffu;   // pa == 0xffffffff: nothing to replace
+      const uint32_t u0 = (uint32_t)l8, u1 = (uint32_t)l8 + 8u;
+      const uint32_t x0 = hb + (u0 << 4), x1 = hb + (u1 << 4);
+      const bool on0 = u0 < nfull, on1 = u1 < nfull;
+      const uint32_t y0 = (uint32_t)l8, y1 = (uint32_t)l8 + 8u, z0 = tail0 + y0, z1 = tail0 + y1;
+      const bool h0 = y0 < hb, h1 = y1 < hb, t0 = z0 < pd.n, t1 = z1 < pd.n;
+      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+      uint32_t bh0 = 0, bh1 = 0, bt0 = 0, bt1 = 0;
+      if (on0) v0 = ld16u(smem, pd.src + x0);
+      if (on1) v1 = ld16u(smem, pd.src + x1);
+      if (h0) bh0 = smem[pd.src + y0];
+      if (h1) bh1 = smem[pd.src + y1];
+      if (t0) bt0 = smem[pd.src + z0];
+      if (t1) bt1 = smem[pd.src + z1];
+      if (pa != 0xffffffffu) {   // the paired read's copy of the header: its own read-number digit
+        const int i0 = (int)(pa - x0), i1 = (int)(pa - x1);
+        v0.x = put_byte(v0.x, i0, pv); v0.y = put_byte(v0.y, i0 - 4, pv); v0.z = put_byte(v0.z, i0 - 8, pv); v0.w = put_byte(v0.w, i0 - 12, pv);
+        v1.x = put_byte(v1.x, i1, pv); v1.y = put_byte(v1.y, i1 - 4, pv); v1.z = put_byte(v1.z, i1 - 8, pv); v1.w = put_byte(v1.w, i1 - 12, pv);
+        bh0 = y0 == pa ? pv : bh0;
+        bh1 = y1 == pa ? pv : bh1;
+        bt0 = z0 == pa ? pv : bt0;
+        bt1 = z1 == pa ? pv : bt1;
+      }
+      if (on0) *reinterpret_cast<uint4*>(g + x0) = v0;
+      if (on1) *reinterpret_cast<uint4*>(g + x1) = v1;
+      if (h0) g[y0] = (uint8_t)bh0;
+      if (h1) g[y1] = (uint8_t)bh1;
+      if (t0) g[z0] = (uint8_t)bt0;
+      if (t1) g[z1] = (uint8_t)bt1;
+      if ((pd.aux & (1u << 30)) && l8 == 0) g[pd.n] = '\n';   // a trimmed read's closing newline, src/lib.rs:1327
+      if (nfull > 16u) {   // ranges longer than 16 units: the rest, plainly
+        for (uint32_t u = (uint32_t)l8 + 16u; u < nfull; u += 8u) {
+          const uint32_t x = hb + (u << 4);
+          uint4 v = ld16u(smem, pd.src + x);
+          if (pa - x < 16u) {
+            const int i = (int)(pa - x);
+            v.x = put_byte(v.x, i, pv); v.y = put_byte(v.y, i - 4, pv); v.z = put_byte(v.z, i - 8, pv); v.w = put_byte(v.w, i - 12, pv);
           }
-          if (P.validate && role == val_role) {
-            const int v = validate_pair(P, smem, G);
-            if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)v);
+          *reinterpret_cast<uint4*>(g + x) = v;
+        }
+      }
+    };
+    // quarter-warp `qw` of `nqw` takes the ranges first + qw, + nqw, ... of [first, end)
+    auto move_all = [&](uint32_t first, uint32_t end, uint32_t qw, uint32_t nqw) {
+      const int l8 = lane & 7;
+      MGK_LOOP_ROLLED
+      for (uint32_t it = first + qw; it < end; it += nqw)
+        if (it % EMIT_NMAX < d.n) {
+          const PieceDesc pd = descs[it];
+          if (pd.n) move_piece(pd, l8);
+        }
+    };
+
+    if (warp < EMIT_SWARPS) {
+      // ---- step 2a, one thread per (record, role)
+      const int role = warp / (EMIT_NMAX / 32);
+      const uint32_t i = (uint32_t)tid % EMIT_NMAX;
+      if (i < d.n) {
+        const RecMeta mt = metas[i];
+        const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15), umi_t = (mt.tpl >> 4) == 15 ? -1 : (mt.tpl >> 4);
+        if (role < 2) {
+          if (!(mt.flags & 1) && mt.sample < P.S && P.out_mode != MGK_OUT_MGI) {   // rewritten headers
+            const RecGeom G = geom(i);
+            const ReadPlan p2 = plan_read(P, G, 2, mt.sample, bar_t, mt.len2);
+            ReadPlan p1 = p2;
+            p1.len = 0;
+            if (paired) p1 = plan_read(P, G, 1, mt.sample, bar_t, mt.len1);
+#pragma unroll 1
+            for (int which = 2; which >= 1; --which) {
+              const ReadPlan& r = which == 2 ? p2 : p1;
+              const int slot = which == 2 ? HDR_SLOT0 : HDR_SLOT1;
+              const bool own = r.hdr == slot && r.len != 0, lent = which == 2 && p1.hdr == HDR_SLOT0 && p1.len != 0;
+              if (!own && !lent) continue;
+              const uint32_t hl = own ? r.hl : p1.hl;   // illumina: both reads carry the same header
+              if (hl <= HDR_SLOT_BYTES) {
+                build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, smem + lay.hdr + hdr_slot((uint32_t)slot - 1u, i), role);
+              } else {   // too long for a slot: byte by byte at its destination(s)
+#pragma unroll 1
+                for (int to = 2; to >= 1; --to) {
+                  const ReadPlan& t = to == 2 ? p2 : p1;
+                  if (t.hdr != slot || t.len == 0) continue;
+                  uint8_t* g = dest(mt, to);
+                  build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, g, role);
+                  if (role == 1 && t.patch_at != 0xffffffffu) g[t.patch_at] = smem[t.patch_src];
+                }
+              }
+            }
+          }
+        } else if (!(mt.flags & 1)) {
+          const int val_role = paired ? 2 : 3;   // --validate goes to the QC thread every record has
+          const bool qc = P.report_level > 0 && (role == 3 || paired);
+          if (qc || (P.validate && role == val_role)) {
+            const RecGeom G = geom(i);
+            if (qc) {   // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
+              const QcSix q = qc_pair(P, smem, G, role == 2 ? 1 : 2);
+#pragma unroll
+              for (int j = 0; j < QC_SLOTS; ++j)
+                if (q.v[j]) atomicAdd(&s_stats[mt.sample * QC_SLOTS + j], q.v[j]);
+            }
+            if (P.validate && role == val_role) {
+              const int v = validate_pair(P, smem, G);
+              if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)v);
+            }
           }
         }
       }
     }
+    // ---- step 2b: the byte ranges that come straight from the staged input (kinds 0-3)
+    if (warp < EMIT_PRODUCER) move_all(0u, 4u * EMIT_NMAX, (uint32_t)warp * 4u + (uint32_t)(lane >> 3), 4u * EMIT_PRODUCER);
+    const long long q2 = c.prof ? clock64() : 0;
+    t_s2 += (unsigned long long)(q2 - c2);
+    __syncthreads();   // the staged headers are complete
+    const long long q3 = c.prof ? clock64() + (long long)(descs[0].n & 0u) : 0;
+    // ---- step 3: staged headers out (kinds 4-5)
+    if (warp < EMIT_PRODUCER) move_all(4u * EMIT_NMAX, 6u * EMIT_NMAX, (uint32_t)warp * 4u + (uint32_t)(lane >> 3), 4u * EMIT_PRODUCER);
     const long long c3 = c.prof ? clock64() : 0;
     t_work += (unsigned long long)(c3 - c2);
-    __syncthreads();   // stage s is free again; desc[s^1] is published
+    t_s4 += (unsigned long long)(c3 - q3);
+    __syncthreads();   // stage s and the header slots are free again; desc[s^1] is published
     if (c.prof) t_bar += (unsigned long long)(clock64() - c3);
     if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {
       flush_stats();
@@ -863,8 +1033,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     unsigned long long* o = c.prof + ((size_t)blockIdx.x * (EMIT_THREADS / 32) + warp) * 4;
     o[0] = t_wait;
     o[1] = t_work;
-    o[2] = t_bar;
-    o[3] = t_prod;
+    o[2] = t_s2;
+    o[3] = t_s4;
   }
 }
 

@@ -169,7 +169,7 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
       double a[4] = {0, 0, 0, 0};
       for (int b = 0; b < ctx->n_sm; ++b)
         for (int k = 0; k < 4; ++k) a[k] += (double)h[((size_t)b * nw + w) * 4 + k] / ctx->n_sm;
-      fprintf(stderr, "[mgk profile] k_emit warp %2d: wait %.0f work %.0f barrier %.0f produce %.0f cycles\n", w, a[0], a[1], a[2], a[3]);
+      fprintf(stderr, "[mgk profile] k_emit warp %2d: wait %.0f work %.0f step2-own %.0f step4 %.0f cycles\n", w, a[0], a[1], a[2], a[3]);
     }
     cudaFree(ctx->d_prof);
   }
@@ -306,9 +306,13 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     at += up((uint32_t)P.prefix_len + LIT_BYTES + 48u, 16u);
     L.stats = at;
     at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
+    L.writing = at;
+    at += up((uint32_t)P.total * 4u, 16u);
     at += 32u;                                   // slack in front of the header staging areas (gather16 reads around them)
     L.hdr = at;
-    at += HDR_AREA_BYTES + 32u;
+    at += (P.out_mode == MGK_OUT_MGI_FULL_HEADER && P.paired ? 2u : 1u) * HDR_KIND_BYTES + 32u;   // the paired read has its own header only with --mgi-full-header
+    L.desc = at;
+    at += EMIT_NMAX * EMIT_PIECES * (uint32_t)sizeof(PieceDesc);
     at = up(at, 128u);
     const uint32_t nl_bytes = 16u * (EMIT_NMAX + 1u);
     L.nl1 = up(nl_bytes, 16u);

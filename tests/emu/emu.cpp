@@ -129,10 +129,10 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   uint8_t* o1 = c->out1.data();
   memset(&c->res, 0, sizeof c->res);
   // the staged tile: the whole chunk as ONE tile, laid out like the kernel's shared memory
-  //   [slack | prefix + literals | header staging | barcode read bytes | paired read bytes | slack]
+  //   [slack | prefix + literals | two header staging slots | barcode read bytes | paired read bytes | slack]
   const uint32_t cs0 = 64;
-  const uint32_t hs = (cs0 + (uint32_t)c->tb.consts.size() + 31u) / 16u * 16u + 16u;   // two slots: barcode read, paired read
-  const uint32_t b2 = hs + 2u * HDR_SLOT_BYTES + 16u;
+  const uint32_t hs = (cs0 + (uint32_t)c->tb.consts.size() + 63u) / 16u * 16u + 16u;
+  const uint32_t b2 = hs + 2u * HDR_SLOT_BYTES + 32u;
   const uint32_t b1 = (b2 + (uint32_t)r2_len + 15u) / 16u * 16u + 16u + (uint32_t)(seq % 3) * 16u;
   const size_t s_bytes = (size_t)b1 + r1_len + 128;
   uint8_t* S = (uint8_t*)aligned_alloc(64, (s_bytes + 63) / 64 * 64);
@@ -146,19 +146,43 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     RecGeom G = R.G;   // into S offsets
     G.h2 += b2; G.s2 += b2; G.p2 += b2; G.q2 += b2; G.e2 += b2;
     G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
-    uint8_t* d2 = o2 + c->off2[(size_t)R.bin] + R.d2;
-    uint8_t* d1 = o1 + c->off1[(size_t)R.bin] + R.d1;
-    // the per-record roles of k_emit, one after the other: every third record in one piece, the others
-    // head part and tail part like the two threads that share a record on the GPU
-    if (i % 3 == 2) {
-      emit_read(P, S, hs, cs0, G, 2, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, PART_ALL);
-      if (P.paired) emit_read(P, S, hs + HDR_SLOT_BYTES, cs0, G, 1, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1, PART_ALL);
-    } else {
-      const int first = i % 3 == 0 ? PART_HEAD : PART_TAIL;   // the two parts are independent: either order
-      for (int part : {first, 1 - first}) {
-        emit_read(P, S, hs, cs0, G, 2, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d2, part);
-        if (P.paired) emit_read(P, S, hs + HDR_SLOT_BYTES, cs0, G, 1, R.mo.sample, R.mo.bar_t, R.mo.umi_t, d1, part);
+    uint8_t* dst[3] = {nullptr, o1 + c->off1[(size_t)R.bin] + R.d1, o2 + c->off2[(size_t)R.bin] + R.d2};
+    // what k_emit does for one pair: header halves by scalar roles, byte ranges by half-warps (lanes looped)
+    ReadPlan plan[3];
+    plan[2] = plan_read(P, G, 2, R.mo.sample, R.mo.bar_t, R.pl.len2);
+    plan[1] = plan_read(P, G, 1, R.mo.sample, R.mo.bar_t, P.paired ? R.pl.len1 : 0u);
+    for (int which = 2; which >= 1; --which) {   // scalar roles: the rewritten headers
+      const ReadPlan& r = plan[which];
+      const int slot = which == 2 ? HDR_SLOT0 : HDR_SLOT1;
+      const bool own = r.hdr == slot && r.len != 0, lent = which == 2 && plan[1].hdr == HDR_SLOT0 && plan[1].len != 0;
+      if (!own && !lent) continue;
+      const uint32_t hl = own ? r.hl : plan[1].hl;   // illumina: both reads carry the same header
+      if (hl <= HDR_SLOT_BYTES) {
+        uint8_t* o = S + hs + (uint32_t)(slot - 1) * HDR_SLOT_BYTES;
+        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 1 : 0);   // the two halves, either order
+        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 0 : 1);
+      } else {   // too long for a slot: at its destination(s)
+        for (int to = 2; to >= 1; --to) {
+          if (plan[to].hdr != slot || plan[to].len == 0) continue;
+          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 0);
+          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 1);
+          if (plan[to].patch_at != 0xffffffffu) dst[to][plan[to].patch_at] = S[plan[to].patch_src];
+        }
       }
+    }
+    for (int which = 2; which >= 1; --which) {   // half-warps: byte ranges
+      const ReadPlan& r = plan[which];
+      if (r.len == 0) continue;
+      for (int k = 0; k < 2; ++k) {
+        const Piece pc = read_piece(r, k);
+        for (int l = 0; l < 16; ++l)
+          if (pc.n) copy_piece(dst[which] + pc.dst_off, S, pc.src, pc.n, l, 0xffffffffu, 0u);
+      }
+      if (r.trim) dst[which][r.len - 1] = '\n';
+      if (r.hdr != HDR_VERBATIM && r.hl <= HDR_SLOT_BYTES)
+        for (int l = 0; l < 16; ++l)
+          copy_piece(dst[which], S, hs + (uint32_t)(r.hdr - 1) * HDR_SLOT_BYTES, r.hl, l, r.patch_at,
+                     r.patch_at != 0xffffffffu ? S[r.patch_src] : 0u);
     }
     if (P.report_level > 0) {
       QcSix q = qc_pair(P, S, G, 1);
