@@ -302,7 +302,7 @@ MGK_HD void build_header(const Params& P, const uint8_t* S, uint32_t cs0, const 
   }
 }
 
-constexpr uint32_t HDR_SLOT_BYTES = 96;    // staging slot of a rewritten header; longer ones are built at their destination
+constexpr uint32_t HDR_SLOT_BYTES = 80;    // staging slot of a rewritten header; longer ones are built at their destination
 
 // The two byte ranges of a read's output that come straight from the input:
 //   k = 0: [header line verbatim |] "\n" sequence
@@ -392,18 +392,12 @@ MGK_HD QcSix qc_pair(const Params& P, const uint8_t* S, const RecGeom& G, int wh
   r.v[1] = q1.sum;
   r.v[2] = r.v[3] = r.v[4] = r.v[5] = 0;
   if (!(which & 2)) return r;
-  const Qc q2 = qc_line(S, G.q2, G.e2 - G.q2);
-  uint32_t sb = 0, hb = 0;
-  MGK_LOOP_ROLLED
-  for (uint32_t k = 0; k < BL; ++k) {   // the barcode's own qualities
-    const uint32_t q = s_u8(S, G.e2 - BL + k);
-    sb += q;
-    hb += q >= 63u ? 1u : 0u;
-  }
-  r.v[2] = hb;
-  r.v[3] = sb;
-  r.v[4] = q2.high - hb;
-  r.v[5] = q2.sum - sb;
+  // the barcode's own qualities are the last BL of the line (record_plan has refused shorter lines)
+  const Qc qb = qc_line(S, G.e2 - BL, BL), qr = qc_line(S, G.q2, G.e2 - BL - G.q2);
+  r.v[2] = qb.high;
+  r.v[3] = qb.sum;
+  r.v[4] = qr.high;
+  r.v[5] = qr.sum;
   return r;
 }
 

@@ -78,7 +78,7 @@ struct ChunkDev {
   Status* status;
   unsigned long long* stats;   // [total][10]   running totals of the context
   unsigned long long* mism;    // [total][2m+2]
-  unsigned long long* prof;    // optional [grid][warps][4] cycle counters of k_emit (MGK_PROFILE=1), else null
+  unsigned long long* prof;    // optional [grid][warps][6] cycle counters of k_emit (MGK_PROFILE=1), else null
 };
 
 // ------------------------------------------------------------------ helpers
@@ -110,12 +110,211 @@ __device__ __forceinline__ void copy_params_to_smem(T* dst, const T* src) {
 }
 
 // ------------------------------------------------------------------ TMA / mbarrier helpers
+// shared-memory loads by 32-bit shared-window address (the movers of k_emit: no generic-address arithmetic, predicates
+// evaluated once for a group of loads; registers of a predicated-off load keep their value)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// One lane's share (of a quarter-warp's) of a destination range g[0, N) fed by two source runs: byte j comes from
+// shared-window address sa + j if j < n0, else sb + j.  hb bytes lie in front of the first 16-byte boundary of g,
+// nfull whole units follow; the lane takes units l8, l8 + 8, l8 + 16 (unit u < ubf lies wholly in the first run, the
+// others in the second, unit ubs -- if any -- straddles the two and goes byte by byte), the bytes l8 and l8 + 8 of
+// the head, of the straddling unit and of the tail (z = first tail byte + l8), and lane 0 a closing '\n' if nl.
+// Stores carry their predicates; loads do not (a predicated load would make its register live across the whole
+// loop): they may read up to 512 bytes past the range, which the shared-memory layout leaves room for.
+__device__ __forceinline__ void move_pair_lane(uint8_t* g, uint32_t l8, uint32_t hb, uint32_t nfull, uint32_t N, uint32_t n0, uint32_t sa,
+                                               uint32_t sb, uint32_t ubf, uint32_t ubs, uint32_t z, uint32_t nl) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p0, p1, p2, c, v0, v1, v2, v3, v4, v5, pn;\n"
+      ".reg .u32 u1, u2, x0, a0, a1, a2, b0, b1, b2, s0, s1, s2, t, j0, j1, j2, j3, j4, j5, e0, e1, e2, e3, e4, e5, k;\n"
+      ".reg .u32 w<15>;\n"
+      ".reg .u64 gu, gh, gt, gb, gn, o;\n"
+      "add.u32 u1, %1, 8;\n"
+      "add.u32 u2, %1, 16;\n"
+      "setp.lt.u32 p0, %1, %3;\n"
+      "setp.ne.and.u32 p0, %1, %9, p0;\n"
+      "setp.lt.u32 p1, u1, %3;\n"
+      "setp.ne.and.u32 p1, u1, %9, p1;\n"
+      "setp.lt.u32 p2, u2, %3;\n"
+      "setp.ne.and.u32 p2, u2, %9, p2;\n"
+      "shl.b32 x0, %1, 4;\n"
+      "add.u32 x0, x0, %2;\n"
+      "setp.lt.u32 c, %1, %8;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 a0, t, x0;\n"
+      "setp.lt.u32 c, u1, %8;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 a1, t, x0;\n"
+      "setp.lt.u32 c, u2, %8;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 a2, t, x0;\n"
+      "shl.b32 s0, a0, 3;\n"
+      "shl.b32 s1, a1, 3;\n"
+      "shl.b32 s2, a2, 3;\n"
+      "and.b32 b0, a0, 0xfffffffc;\n"
+      "and.b32 b1, a1, 0xfffffffc;\n"
+      "and.b32 b2, a2, 0xfffffffc;\n"
+      "ld.shared.u32 w0, [b0];\n"
+      "ld.shared.u32 w1, [b0+4];\n"
+      "ld.shared.u32 w2, [b0+8];\n"
+      "ld.shared.u32 w3, [b0+12];\n"
+      "ld.shared.u32 w4, [b0+16];\n"
+      "ld.shared.u32 w5, [b1+128];\n"
+      "ld.shared.u32 w6, [b1+132];\n"
+      "ld.shared.u32 w7, [b1+136];\n"
+      "ld.shared.u32 w8, [b1+140];\n"
+      "ld.shared.u32 w9, [b1+144];\n"
+      "ld.shared.u32 w10, [b2+256];\n"
+      "ld.shared.u32 w11, [b2+260];\n"
+      "ld.shared.u32 w12, [b2+264];\n"
+      "ld.shared.u32 w13, [b2+268];\n"
+      "ld.shared.u32 w14, [b2+272];\n"
+      // the bytes: head (j0, j1), straddling unit (j2, j3), tail (j4, j5)
+      "mov.u32 j0, %1;\n"
+      "add.u32 j1, %1, 8;\n"
+      "shl.b32 k, %9, 4;\n"
+      "add.u32 k, k, %2;\n"
+      "add.u32 j2, k, %1;\n"
+      "add.u32 j3, j2, 8;\n"
+      "mov.u32 j4, %10;\n"
+      "add.u32 j5, %10, 8;\n"
+      "setp.lt.u32 v0, j0, %2;\n"
+      "setp.lt.u32 v1, j1, %2;\n"
+      "setp.ne.u32 v2, %9, 0xffffffff;\n"
+      "setp.ne.u32 v3, %9, 0xffffffff;\n"
+      "setp.lt.u32 v4, j4, %4;\n"
+      "setp.lt.u32 v5, j5, %4;\n"
+      "setp.lt.u32 c, j0, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j0;\n"
+      "ld.shared.u8 e0, [t];\n"
+      "setp.lt.u32 c, j1, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j1;\n"
+      "ld.shared.u8 e1, [t];\n"
+      "setp.lt.u32 c, j2, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j2;\n"
+      "ld.shared.u8 e2, [t];\n"
+      "setp.lt.u32 c, j3, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j3;\n"
+      "ld.shared.u8 e3, [t];\n"
+      "setp.lt.u32 c, j4, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j4;\n"
+      "ld.shared.u8 e4, [t];\n"
+      "setp.lt.u32 c, j5, %5;\n"
+      "selp.u32 t, %6, %7, c;\n"
+      "add.u32 t, t, j5;\n"
+      "ld.shared.u8 e5, [t];\n"
+      // realign (shf takes the shift amount modulo 32: 8 * (address & 3))
+      "shf.r.wrap.b32 w0, w0, w1, s0;\n"
+      "shf.r.wrap.b32 w1, w1, w2, s0;\n"
+      "shf.r.wrap.b32 w2, w2, w3, s0;\n"
+      "shf.r.wrap.b32 w3, w3, w4, s0;\n"
+      "shf.r.wrap.b32 w5, w5, w6, s1;\n"
+      "shf.r.wrap.b32 w6, w6, w7, s1;\n"
+      "shf.r.wrap.b32 w7, w7, w8, s1;\n"
+      "shf.r.wrap.b32 w8, w8, w9, s1;\n"
+      "shf.r.wrap.b32 w10, w10, w11, s2;\n"
+      "shf.r.wrap.b32 w11, w11, w12, s2;\n"
+      "shf.r.wrap.b32 w12, w12, w13, s2;\n"
+      "shf.r.wrap.b32 w13, w13, w14, s2;\n"
+      "cvt.u64.u32 o, x0;\n"
+      "add.u64 gu, %0, o;\n"
+      "@p0 st.global.v4.u32 [gu], {w0, w1, w2, w3};\n"
+      "@p1 st.global.v4.u32 [gu+128], {w5, w6, w7, w8};\n"
+      "@p2 st.global.v4.u32 [gu+256], {w10, w11, w12, w13};\n"
+      "cvt.u64.u32 o, j0;\n"
+      "add.u64 gh, %0, o;\n"
+      "@v0 st.global.u8 [gh], e0;\n"
+      "@v1 st.global.u8 [gh+8], e1;\n"
+      "cvt.u64.u32 o, j2;\n"
+      "add.u64 gb, %0, o;\n"
+      "@v2 st.global.u8 [gb], e2;\n"
+      "@v3 st.global.u8 [gb+8], e3;\n"
+      "cvt.u64.u32 o, j4;\n"
+      "add.u64 gt, %0, o;\n"
+      "@v4 st.global.u8 [gt], e4;\n"
+      "@v5 st.global.u8 [gt+8], e5;\n"
+      "setp.ne.u32 pn, %11, 0;\n"
+      "setp.eq.and.u32 pn, %1, 0, pn;\n"
+      "cvt.u64.u32 o, %4;\n"
+      "add.u64 gn, %0, o;\n"
+      "mov.u32 k, 10;\n"
+      "@pn st.global.u8 [gn], k;\n"
+      "}\n" ::"l"(g),
+      "r"(l8), "r"(hb), "r"(nfull), "r"(N), "r"(n0), "r"(sa), "r"(sb), "r"(ubf), "r"(ubs), "r"(z), "r"(nl)
+      : "memory");
+}
+// The same for a short range out of one source run (a staged header): unit l8, bytes l8 and l8 + 8 of head and tail.
+__device__ __forceinline__ void move_small_lane(uint8_t* g, uint32_t l8, uint32_t hb, uint32_t nfull, uint32_t n, uint32_t sa, uint32_t z) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p0, v0, v1, v4, v5;\n"
+      ".reg .u32 x0, a0, b0, s0, t, j1, j5, e0, e1, e4, e5;\n"
+      ".reg .u32 w<5>;\n"
+      ".reg .u64 gu, gh, gt, o;\n"
+      "setp.lt.u32 p0, %1, %3;\n"
+      "shl.b32 x0, %1, 4;\n"
+      "add.u32 x0, x0, %2;\n"
+      "add.u32 a0, %5, x0;\n"
+      "shl.b32 s0, a0, 3;\n"
+      "and.b32 b0, a0, 0xfffffffc;\n"
+      "ld.shared.u32 w0, [b0];\n"
+      "ld.shared.u32 w1, [b0+4];\n"
+      "ld.shared.u32 w2, [b0+8];\n"
+      "ld.shared.u32 w3, [b0+12];\n"
+      "ld.shared.u32 w4, [b0+16];\n"
+      "add.u32 j1, %1, 8;\n"
+      "add.u32 j5, %6, 8;\n"
+      "setp.lt.u32 v0, %1, %2;\n"
+      "setp.lt.u32 v1, j1, %2;\n"
+      "setp.lt.u32 v4, %6, %4;\n"
+      "setp.lt.u32 v5, j5, %4;\n"
+      "add.u32 t, %5, %1;\n"
+      "ld.shared.u8 e0, [t];\n"
+      "ld.shared.u8 e1, [t+8];\n"
+      "add.u32 t, %5, %6;\n"
+      "ld.shared.u8 e4, [t];\n"
+      "ld.shared.u8 e5, [t+8];\n"
+      "shf.r.wrap.b32 w0, w0, w1, s0;\n"
+      "shf.r.wrap.b32 w1, w1, w2, s0;\n"
+      "shf.r.wrap.b32 w2, w2, w3, s0;\n"
+      "shf.r.wrap.b32 w3, w3, w4, s0;\n"
+      "cvt.u64.u32 o, x0;\n"
+      "add.u64 gu, %0, o;\n"
+      "@p0 st.global.v4.u32 [gu], {w0, w1, w2, w3};\n"
+      "cvt.u64.u32 o, %1;\n"
+      "add.u64 gh, %0, o;\n"
+      "@v0 st.global.u8 [gh], e0;\n"
+      "@v1 st.global.u8 [gh+8], e1;\n"
+      "cvt.u64.u32 o, %6;\n"
+      "add.u64 gt, %0, o;\n"
+      "@v4 st.global.u8 [gt], e4;\n"
+      "@v5 st.global.u8 [gt+8], e5;\n"
+      "}\n" ::"l"(g),
+      "r"(l8), "r"(hb), "r"(nfull), "r"(n), "r"(sa), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ long long tick(bool on) {   // cycle counter, ordered with memory operations (profiling aid)
+  long long t = 0;
+  if (on) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -658,7 +857,7 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
 constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
 constexpr int EMIT_SROLES = 4;
 constexpr int EMIT_SWARPS = EMIT_SROLES * EMIT_NMAX / 32;
-constexpr int EMIT_WWARPS = 8;
+constexpr int EMIT_WWARPS = 11;
 constexpr int EMIT_PRODUCER = EMIT_SWARPS + EMIT_WWARPS;
 constexpr int EMIT_THREADS = (EMIT_PRODUCER + 1) * 32;
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
@@ -683,16 +882,19 @@ struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 
   uint32_t total_bytes;
 };
 
-// One byte range to move: S[src .. src+n) -> out2/out1 + dst.  Six per record: piece 0 / 1 of the barcode read,
-// piece 0 / 1 of the paired read (all straight from the staged input), staged header of the barcode / paired read.
-constexpr int EMIT_PIECES = 6;
+// What the movers work from, four 16-byte descriptors per record:
+//   kind 0 / 1: the body of the barcode / paired read, "\n" sequence | "\n+\n" qualities [| "\n"], two runs of the
+//               staged input that follow each other in the output ({dst, src0 | buffer << 31, src1 | newline << 31,
+//               n0 | n1 << 16}; newline: a trimmed read's closing '\n' is stored on its own);
+//   kind 2 / 3: the staged header of the barcode / paired read ({dst, src, n, aux}).
+constexpr int EMIT_PIECES = 4;
 struct __align__(16) PieceDesc {
   uint32_t dst;   // offset in the output buffer of its read
   uint32_t src;   // S offset
   uint32_t n;     // bytes (0: nothing)
-  uint32_t aux;   // bit 31: paired-read buffer; bit 30: store '\n' at dst + n (a trimmed read's closing newline);
-                  // bits 0-15: 1 + index of a byte to replace (0: none), bits 16-23: its value
+  uint32_t aux;   // bit 31: paired-read buffer; bits 0-15: 1 + index of a byte to replace (0: none), bits 16-23: its value
 };
+static_assert(HDR_SLOT_BYTES <= 8 * 16, "a staged header is at most one unit per lane of a quarter-warp");
 
 struct StageDesc {
   uint32_t n;             // records in the stage (0: no more tiles)
@@ -707,10 +909,12 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __shared__ Params P;
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ StageDesc s_desc[2];
+  __shared__ uint32_t s_claim;   // cursor of the tile's list of bodies
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   copy_params_to_smem(&P, Pg);
   if (tid == 0) {
+    s_claim = 0;
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -747,8 +951,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   bool fresh = true;   // next_rec opens a plan tile: its byte offsets come from the newline table
   auto produce = [&](int s) {   // lane 0 of the producer warp
     StageDesc& d = s_desc[s];
-    if (next_rec >= n_rec) {
+    if (next_rec >= n_rec) {   // no more tiles: an empty stage (the waiters read d.n after the barrier)
       d.n = 0;
+      mbar_arrive(&s_bar[s]);
       return;
     }
     const uint32_t r0 = next_rec;
@@ -773,6 +978,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       atomicOr(&c.status->error, ERR_REC_TOO_LONG);
       d.n = 0;
       next_rec = n_rec;
+      mbar_arrive(&s_bar[s]);
       return;
     }
     const uint32_t n = lim - r0;
@@ -799,6 +1005,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __syncthreads();
 
   uint32_t* s_stats = reinterpret_cast<uint32_t*>(smem + lay.stats);
+  const uint32_t smem_s = smem_u32(smem), desc_s = smem_s + lay.desc;   // shared-window addresses
   auto flush_stats = [&]() {   // all threads; s_stats quiescent
     for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) {
       const uint32_t v = s_stats[i];
@@ -810,161 +1017,170 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     }
   };
 
-  unsigned long long t_wait = 0, t_work = 0, t_bar = 0, t_prod = 0, t_s2 = 0, t_s4 = 0;
-  for (uint32_t k = 0;; ++k) {
-    const int s = (int)(k & 1u);
-    const long long c0 = c.prof ? clock64() : 0;
-    if (warp == EMIT_PRODUCER && lane == 0) produce(s ^ 1);
-    const long long c1 = c.prof ? clock64() : 0;
-    t_prod += (unsigned long long)(c1 - c0);
+  // One staged tile as the worker threads see it
+  struct TileView {
+    const uint32_t *nl2s, *nl1s, *bins;
+    const RecMeta* metas;
+    uint32_t o2, o1;   // S offsets of chunk byte 0 of either read
+    uint32_t n, r0;
+  };
+  auto tile_view = [&](int s) {
     const StageDesc d = s_desc[s];
-    if (d.n == 0) break;
-    if (warp < EMIT_PRODUCER) mbar_wait(&s_bar[s], (k >> 1) & 1u);
-    const long long c2 = c.prof ? clock64() : 0;
-    t_wait += (unsigned long long)(c2 - c1);
     const uint32_t stage = lay.stage0 + (uint32_t)s * lay.stage_stride;
     const unsigned char* st = smem + stage;
-    const uint32_t* nl2s = reinterpret_cast<const uint32_t*>(st);
-    const uint32_t* nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
-    const RecMeta* metas = reinterpret_cast<const RecMeta*>(st + lay.meta);
-    const uint32_t* bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
-    // S offsets of chunk byte 0 of either read
-    const uint32_t o2 = stage + lay.bytes - d.base2;
-    const uint32_t o1 = stage + lay.bytes + d.off1 - d.base1;
-    auto geom = [&](uint32_t i) {
-      RecGeom G;
-      const uint4 a = *reinterpret_cast<const uint4*>(nl2s + 4u * i + 4u);
-      G.h2 = nl2s[4u * i + 3u] + 1u + o2;
-      G.s2 = a.x + 1u + o2;
-      G.p2 = a.y + 1u + o2;
-      G.q2 = a.z + 1u + o2;
-      G.e2 = a.w + o2;
-      G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
-      if (paired) {
-        const uint4 b = *reinterpret_cast<const uint4*>(nl1s + 4u * i + 4u);
-        G.h1 = nl1s[4u * i + 3u] + 1u + o1;
-        G.s1 = b.x + 1u + o1;
-        G.p1 = b.y + 1u + o1;
-        G.q1 = b.z + 1u + o1;
-        G.e1 = b.w + o1;
-      }
-      return G;
-    };
-    auto dest = [&](const RecMeta& mt, int which) -> uint8_t* {   // where the record's output starts
-      const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
-      return which == 2 ? c.out2 + bins[bin] + mt.off2 : c.out1 + bins[total + bin] + mt.off1;
-    };
+    TileView T;
+    T.nl2s = reinterpret_cast<const uint32_t*>(st);
+    T.nl1s = reinterpret_cast<const uint32_t*>(st + lay.nl1);
+    T.metas = reinterpret_cast<const RecMeta*>(st + lay.meta);
+    T.bins = reinterpret_cast<const uint32_t*>(st + lay.bins);
+    T.o2 = stage + lay.bytes - d.base2;
+    T.o1 = stage + lay.bytes + d.off1 - d.base1;
+    T.n = d.n;
+    T.r0 = d.r0;
+    return T;
+  };
+  auto geom = [&](const TileView& T, uint32_t i) {
+    RecGeom G;
+    const uint4 a = *reinterpret_cast<const uint4*>(T.nl2s + 4u * i + 4u);
+    G.h2 = T.nl2s[4u * i + 3u] + 1u + T.o2;
+    G.s2 = a.x + 1u + T.o2;
+    G.p2 = a.y + 1u + T.o2;
+    G.q2 = a.z + 1u + T.o2;
+    G.e2 = a.w + T.o2;
+    G.h1 = G.s1 = G.p1 = G.q1 = G.e1 = 0;
+    if (paired) {
+      const uint4 b = *reinterpret_cast<const uint4*>(T.nl1s + 4u * i + 4u);
+      G.h1 = T.nl1s[4u * i + 3u] + 1u + T.o1;
+      G.s1 = b.x + 1u + T.o1;
+      G.p1 = b.y + 1u + T.o1;
+      G.q1 = b.z + 1u + T.o1;
+      G.e1 = b.w + T.o1;
+    }
+    return G;
+  };
+  auto dest = [&](const TileView& T, const RecMeta& mt, int which) -> uint8_t* {   // where the record's output starts
+    const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
+    return which == 2 ? c.out2 + T.bins[bin] + mt.off2 : c.out1 + T.bins[total + bin] + mt.off1;
+  };
 
-    PieceDesc* descs = reinterpret_cast<PieceDesc*>(smem + lay.desc);
-    // ---- step 1, one thread per record: the record's byte ranges (where from, where to), so that the half-warps
-    // below start moving bytes after a single 16-byte load
-    if (warp < 2 * (EMIT_NMAX / 32)) {   // thread per (record, read)
-      const uint32_t i = (uint32_t)tid % EMIT_NMAX;
-      const int which = tid < EMIT_NMAX ? 2 : 1;
-      if (i < d.n) {
-        const RecMeta mt = metas[i];
-        auto put = [&](int kind, uint32_t dst, uint32_t src, uint32_t n, uint32_t aux) {
-          PieceDesc x;
-          x.dst = dst;
-          x.src = src;
-          x.n = n;
-          x.aux = aux;
-          descs[kind * EMIT_NMAX + i] = x;
-        };
-        const int k0 = which == 2 ? 0 : 2, kh = which == 2 ? 4 : 5;   // this read's piece 0, piece 1 = k0 + 1, staged header
-        if ((mt.flags & 1) || (which == 1 && !paired)) {   // layout errors are reported through status, nothing is emitted
-          put(k0, 0u, 0u, 0u, 0u);
-          put(k0 + 1, 0u, 0u, 0u, 0u);
-          put(kh, 0u, 0u, 0u, 0u);
-        } else {
-          const RecGeom G = geom(i);
-          const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15);
-          const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
-          const uint32_t buf = which == 2 ? 0u : 1u << 31;
-          const uint32_t dst = which == 2 ? bins[bin] + mt.off2 : bins[total + bin] + mt.off1;
-          const ReadPlan r = plan_read(P, G, which, mt.sample, bar_t, which == 2 ? mt.len2 : mt.len1);
-          const Piece a = read_piece(r, 0), b = read_piece(r, 1);
-          put(k0, dst + a.dst_off, a.src, a.n, buf);
-          put(k0 + 1, dst + b.dst_off, b.src, b.n, buf | ((r.trim && r.len) ? 1u << 30 : 0u));
-          const bool staged = r.len && r.hdr != HDR_VERBATIM && r.hl <= HDR_SLOT_BYTES;
-          const uint32_t patch = r.patch_at != 0xffffffffu ? (r.patch_at + 1u) | ((uint32_t)smem[r.patch_src] << 16) : 0u;
-          put(kh, dst, lay.hdr + hdr_slot(staged ? (uint32_t)r.hdr - 1u : 0u, i), staged ? r.hl : 0u, buf | patch);
-        }
+  // ---- descriptors of a staged tile, thread t of 2 * EMIT_NMAX per (record, read): the record's byte ranges (where
+  // from, where to), so that the movers start after a single 16-byte load.  Two tables (tile parity): the table of
+  // tile k + 1 is made while tile k is being moved.
+  constexpr uint32_t DESC_TABLE = EMIT_PIECES * EMIT_NMAX * (uint32_t)sizeof(PieceDesc);
+  auto make_descs = [&](const TileView& T, uint32_t par, uint32_t t) {
+    PieceDesc* descs = reinterpret_cast<PieceDesc*>(smem + lay.desc + par * DESC_TABLE);
+    const uint32_t i = t % EMIT_NMAX;
+    const int which = t < EMIT_NMAX ? 2 : 1;
+    if (i >= T.n) return;
+    const RecMeta mt = T.metas[i];
+    auto put = [&](int kind, uint32_t dst, uint32_t src, uint32_t n, uint32_t aux) {
+      PieceDesc x;
+      x.dst = dst;
+      x.src = src;
+      x.n = n;
+      x.aux = aux;
+      descs[kind * EMIT_NMAX + i] = x;
+    };
+    const int kb = which == 2 ? 0 : 1, kh = kb + 2;   // this read's body and staged header
+    if ((mt.flags & 1) || (which == 1 && !paired)) {   // layout errors are reported through status, nothing is emitted
+      put(kb, 0u, 0u, 0u, 0u);
+      put(kh, 0u, 0u, 0u, 0u);
+      return;
+    }
+    const RecGeom G = geom(T, i);
+    const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15);
+    const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
+    const uint32_t buf = which == 2 ? 0u : 1u << 31;
+    const uint32_t dst = which == 2 ? T.bins[bin] + mt.off2 : T.bins[total + bin] + mt.off1;
+    const ReadPlan r = plan_read(P, G, which, mt.sample, bar_t, which == 2 ? mt.len2 : mt.len1);
+    const Piece a = read_piece(r, 0), b = read_piece(r, 1);   // b follows a in the output
+    put(kb, dst + a.dst_off, a.src | buf, b.src | ((r.trim && r.len) ? 1u << 31 : 0u), a.n | (b.n << 16));
+    const bool staged = r.len && r.hdr != HDR_VERBATIM && r.hl <= HDR_SLOT_BYTES;
+    const uint32_t patch = r.patch_at != 0xffffffffu ? (r.patch_at + 1u) | ((uint32_t)smem[r.patch_src] << 16) : 0u;
+    put(kh, dst, lay.hdr + hdr_slot(staged ? (uint32_t)r.hdr - 1u : 0u, i), staged ? r.hl : 0u, buf | patch);
+  };
+
+  // A QUARTER-warp (8 lanes) moves one descriptor's bytes in 16-byte units aligned on the destination, adjacent
+  // lanes adjacent units (the 8 lanes write 128 contiguous bytes per store), the bytes around the units one by one.
+  auto move_body = [&](const uint4 pd, uint32_t l8) {
+    const uint32_t n0 = pd.w & 0xffffu, N = n0 + (pd.w >> 16);
+    const uint32_t sa = smem_s + (pd.y & 0x7fffffffu), sb = smem_s + (pd.z & 0x7fffffffu) - n0;
+    uint8_t* g = ((int32_t)pd.y < 0 ? c.out1 : c.out2) + pd.x;
+    const uint32_t hb = min((0u - pd.x) & 15u, N);   // the output buffers are 16-byte aligned
+    const uint32_t mid = N - hb, nfull = mid >> 4, z = N - (mid & 15u) + l8;
+    const uint32_t d0 = n0 - hb;
+    const bool in0 = n0 > hb;
+    const uint32_t ubf = in0 ? d0 >> 4 : 0u;
+    const uint32_t ubs = (in0 && (d0 & 15u) && ubf < nfull) ? ubf : 0xffffffffu;
+    move_pair_lane(g, l8, hb, nfull, N, n0, sa, sb, ubf, ubs, z, pd.z >> 31);
+    if (nfull > 24u) {   // ranges longer than 24 units: the rest, plainly
+      for (uint32_t u = l8 + 24u; u < nfull; u += 8u) {
+        if (u == ubs) continue;
+        const uint32_t x = hb + (u << 4);
+        *reinterpret_cast<uint4*>(g + x) = ld16u(smem, (u < ubf ? sa : sb) + x - smem_s);
       }
     }
-    __syncthreads();
-    // A QUARTER-warp (8 lanes) moves one byte range: lane l takes the 16-byte units l and l + 8 of the range's
-    // destination-aligned middle (adjacent lanes, adjacent units: the 8 lanes write 128 contiguous bytes per store)
-    // and the l-th / (l + 8)-th byte in front of and after it.  Four ranges per warp and round, two stores per lane
-    // in flight.  Every warp of the CTA takes its share once its scalar role is done.
-    auto move_piece = [&](const PieceDesc pd, int l8) {
-      // every address and predicate first, then every shared-memory load, then every store: one load round trip
-      uint8_t* g = ((pd.aux >> 31) ? c.out1 : c.out2) + pd.dst;
-      const uint32_t hb = min((16u - (pd.dst & 15u)) & 15u, pd.n);   // the output buffers are 16-byte aligned
-      const uint32_t nfull = (pd.n - hb) >> 4, tail0 = hb + (nfull << 4);
-      const uint32_t pa = (pd.aux & 0xffffu) - 1u, pv = (pd.aux >> 16) & 0xffu;   // pa == 0xffffffff: nothing to replace
-      const uint32_t u0 = (uint32_t)l8, u1 = (uint32_t)l8 + 8u;
-      const uint32_t x0 = hb + (u0 << 4), x1 = hb + (u1 << 4);
-      const bool on0 = u0 < nfull, on1 = u1 < nfull;
-      const uint32_t y0 = (uint32_t)l8, y1 = (uint32_t)l8 + 8u, z0 = tail0 + y0, z1 = tail0 + y1;
-      const bool h0 = y0 < hb, h1 = y1 < hb, t0 = z0 < pd.n, t1 = z1 < pd.n;
-      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-      uint32_t bh0 = 0, bh1 = 0, bt0 = 0, bt1 = 0;
-      if (on0) v0 = ld16u(smem, pd.src + x0);
-      if (on1) v1 = ld16u(smem, pd.src + x1);
-      if (h0) bh0 = smem[pd.src + y0];
-      if (h1) bh1 = smem[pd.src + y1];
-      if (t0) bt0 = smem[pd.src + z0];
-      if (t1) bt1 = smem[pd.src + z1];
-      if (pa != 0xffffffffu) {   // the paired read's copy of the header: its own read-number digit
-        const int i0 = (int)(pa - x0), i1 = (int)(pa - x1);
-        v0.x = put_byte(v0.x, i0, pv); v0.y = put_byte(v0.y, i0 - 4, pv); v0.z = put_byte(v0.z, i0 - 8, pv); v0.w = put_byte(v0.w, i0 - 12, pv);
-        v1.x = put_byte(v1.x, i1, pv); v1.y = put_byte(v1.y, i1 - 4, pv); v1.z = put_byte(v1.z, i1 - 8, pv); v1.w = put_byte(v1.w, i1 - 12, pv);
-        bh0 = y0 == pa ? pv : bh0;
-        bh1 = y1 == pa ? pv : bh1;
-        bt0 = z0 == pa ? pv : bt0;
-        bt1 = z1 == pa ? pv : bt1;
-      }
-      if (on0) *reinterpret_cast<uint4*>(g + x0) = v0;
-      if (on1) *reinterpret_cast<uint4*>(g + x1) = v1;
-      if (h0) g[y0] = (uint8_t)bh0;
-      if (h1) g[y1] = (uint8_t)bh1;
-      if (t0) g[z0] = (uint8_t)bt0;
-      if (t1) g[z1] = (uint8_t)bt1;
-      if ((pd.aux & (1u << 30)) && l8 == 0) g[pd.n] = '\n';   // a trimmed read's closing newline, src/lib.rs:1327
-      if (nfull > 16u) {   // ranges longer than 16 units: the rest, plainly
-        for (uint32_t u = (uint32_t)l8 + 16u; u < nfull; u += 8u) {
-          const uint32_t x = hb + (u << 4);
-          uint4 v = ld16u(smem, pd.src + x);
-          if (pa - x < 16u) {
-            const int i = (int)(pa - x);
-            v.x = put_byte(v.x, i, pv); v.y = put_byte(v.y, i - 4, pv); v.z = put_byte(v.z, i - 8, pv); v.w = put_byte(v.w, i - 12, pv);
-          }
-          *reinterpret_cast<uint4*>(g + x) = v;
+  };
+  auto move_header = [&](const uint4 pd, uint32_t l8) {
+    const uint32_t n = pd.z, aux = pd.w;
+    uint8_t* g = ((int32_t)aux < 0 ? c.out1 : c.out2) + pd.x;
+    const uint32_t hb = min((0u - pd.x) & 15u, n);
+    const uint32_t mid = n - hb, nfull = mid >> 4, tail0 = n - (mid & 15u), z = tail0 + l8;
+    move_small_lane(g, l8, hb, nfull, n, smem_s + pd.y, z);
+    // the paired read's copy: its own read-number digit, stored by the lane that has just stored the bytes
+    // around it (same thread, program order)
+    const uint32_t pa = (aux & 0xffffu) - 1u, pv = (aux >> 16) & 0xffu;   // pa == 0xffffffff: nothing to replace
+    const uint32_t owner = pa < hb ? pa : pa >= tail0 ? pa - tail0 : (pa - hb) >> 4;
+    if (pa < n && (owner & 7u) == l8) g[pa] = (uint8_t)pv;
+  };
+  // quarter-warp `qw` of `nqw` takes the descriptors first + qw, + nqw, ... of [first, end) of a table
+  auto move_all = [&](uint32_t table_s, uint32_t n_tile_rec, uint32_t first, uint32_t end, uint32_t qw, uint32_t nqw, bool headers) {
+    const uint32_t l8 = (uint32_t)lane & 7u;
+    MGK_LOOP_ROLLED
+    for (uint32_t it = first + qw; it < end; it += nqw)
+      if (it % EMIT_NMAX < n_tile_rec) {
+        const uint4 pd = lds_v4(table_s + it * 16u);
+        if (headers) {
+          if (pd.z) move_header(pd, l8);
+        } else if (pd.w) {
+          move_body(pd, l8);
         }
       }
-    };
-    // quarter-warp `qw` of `nqw` takes the ranges first + qw, + nqw, ... of [first, end)
-    auto move_all = [&](uint32_t first, uint32_t end, uint32_t qw, uint32_t nqw) {
-      const int l8 = lane & 7;
-      MGK_LOOP_ROLLED
-      for (uint32_t it = first + qw; it < end; it += nqw)
-        if (it % EMIT_NMAX < d.n) {
-          const PieceDesc pd = descs[it];
-          if (pd.n) move_piece(pd, l8);
-        }
-    };
+  };
+  const uint32_t qw_all = (uint32_t)warp * 4u + (uint32_t)(lane >> 3);                  // quarter-warp among all workers
+  const uint32_t qw_w = (uint32_t)(warp - EMIT_SWARPS) * 4u + (uint32_t)(lane >> 3);    // ... among the warps without a role
+  const bool desc_warp = warp >= EMIT_SWARPS && warp < EMIT_SWARPS + 2 * (EMIT_NMAX / 32);
+  const uint32_t desc_t = (uint32_t)(tid - EMIT_SWARPS * 32);
 
+  // prologue: descriptors of this CTA's first tile
+  mbar_wait(&s_bar[0], 0u);
+  if (desc_warp && s_desc[0].n) make_descs(tile_view(0), 0u, desc_t);
+  __syncthreads();
+
+  unsigned long long t_wait = 0, t_s1 = 0, t_role = 0, t_mv = 0, t_b2 = 0, t_s3 = 0;   // MGK_PROFILE=1
+  for (uint32_t k = 0;; ++k) {
+    const int s = (int)(k & 1u);
+    if (warp == EMIT_PRODUCER && lane == 0) produce(s ^ 1);
+    const long long c1 = tick(c.prof);
+    mbar_wait(&s_bar[s], (k >> 1) & 1u);   // every thread: the stage's bytes and its s_desc entry are visible after it
+    if (s_desc[s].n == 0) break;
+    const long long c2 = tick(c.prof);
+    t_wait += (unsigned long long)(c2 - c1);
+    const TileView T = tile_view(s);
+    const uint32_t table_s = desc_s + (k & 1u) * DESC_TABLE;
+    const long long c4 = c2;
+
+    // ======== step 1: scalar roles; the bodies straight out of the staged input; the next tile's descriptors
     if (warp < EMIT_SWARPS) {
       // ---- step 2a, one thread per (record, role)
       const int role = warp / (EMIT_NMAX / 32);
       const uint32_t i = (uint32_t)tid % EMIT_NMAX;
-      if (i < d.n) {
-        const RecMeta mt = metas[i];
+      if (i < T.n) {
+        const RecMeta mt = T.metas[i];
         const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15), umi_t = (mt.tpl >> 4) == 15 ? -1 : (mt.tpl >> 4);
         if (role < 2) {
           if (!(mt.flags & 1) && mt.sample < P.S && P.out_mode != MGK_OUT_MGI) {   // rewritten headers
-            const RecGeom G = geom(i);
+            const RecGeom G = geom(T, i);
             const ReadPlan p2 = plan_read(P, G, 2, mt.sample, bar_t, mt.len2);
             ReadPlan p1 = p2;
             p1.len = 0;
@@ -983,7 +1199,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
                 for (int to = 2; to >= 1; --to) {
                   const ReadPlan& t = to == 2 ? p2 : p1;
                   if (t.hdr != slot || t.len == 0) continue;
-                  uint8_t* g = dest(mt, to);
+                  uint8_t* g = dest(T, mt, to);
                   build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, g, role);
                   if (role == 1 && t.patch_at != 0xffffffffu) g[t.patch_at] = smem[t.patch_src];
                 }
@@ -994,7 +1210,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
           const int val_role = paired ? 2 : 3;   // --validate goes to the QC thread every record has
           const bool qc = P.report_level > 0 && (role == 3 || paired);
           if (qc || (P.validate && role == val_role)) {
-            const RecGeom G = geom(i);
+            const RecGeom G = geom(T, i);
             if (qc) {   // sum_qc x3 + update_stats x6, src/lib.rs:1188-1210
               const QcSix q = qc_pair(P, smem, G, role == 2 ? 1 : 2);
 #pragma unroll
@@ -1003,25 +1219,56 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
             }
             if (P.validate && role == val_role) {
               const int v = validate_pair(P, smem, G);
-              if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(d.r0 + i) << 4) | (unsigned)v);
+              if (v) atomicMin(&c.status->validate_key, ((unsigned long long)(T.r0 + i) << 4) | (unsigned)v);
             }
           }
         }
       }
     }
-    // ---- step 2b: the byte ranges that come straight from the staged input (kinds 0-3)
-    if (warp < EMIT_PRODUCER) move_all(0u, 4u * EMIT_NMAX, (uint32_t)warp * 4u + (uint32_t)(lane >> 3), 4u * EMIT_PRODUCER);
-    const long long q2 = c.prof ? clock64() : 0;
-    t_s2 += (unsigned long long)(q2 - c2);
+    const long long c5 = tick(c.prof);
+    t_role += (unsigned long long)(c5 - c4);
+    // Every warp then draws rounds of four bodies from the tile's cursor until the list is exhausted (the next draw
+    // is in flight while a round is moved), so a warp joins whenever its other work is done; eight of the warps
+    // without a role make the next tile's descriptors after their first two rounds (its stage has landed by then).
+    if (warp < EMIT_PRODUCER) {
+      auto claim_bodies = [&](uint32_t max_rounds) {
+        const uint32_t l8 = (uint32_t)lane & 7u, q = (uint32_t)lane >> 3;
+        uint32_t raw = 0;
+        if (lane == 0) raw = atomicAdd(&s_claim, 4u);
+        uint32_t cur = __shfl_sync(0xffffffffu, raw, 0);
+        MGK_LOOP_ROLLED
+        for (uint32_t r = 1; cur < 2u * EMIT_NMAX; ++r) {
+          const bool more = r < max_rounds;
+          if (more && lane == 0) raw = atomicAdd(&s_claim, 4u);
+          const uint32_t it = cur + q;
+          if (it % EMIT_NMAX < T.n) {
+            const uint4 pd = lds_v4(table_s + it * 16u);
+            if (pd.w) move_body(pd, l8);
+          }
+          if (!more) break;
+          cur = __shfl_sync(0xffffffffu, raw, 0);
+        }
+      };
+      if (desc_warp) {
+        claim_bodies(2u);
+        const long long c8 = tick(c.prof);
+        mbar_wait(&s_bar[s ^ 1], ((k + 1u) >> 1) & 1u);
+        if (s_desc[s ^ 1].n) make_descs(tile_view(s ^ 1), (k + 1u) & 1u, desc_t);
+        __syncwarp();
+        t_s1 += (unsigned long long)(tick(c.prof) - c8);
+      }
+      claim_bodies(0xffffffffu);
+    }
+    const long long c6 = tick(c.prof);
+    t_mv += (unsigned long long)(c6 - c5);
     __syncthreads();   // the staged headers are complete
-    const long long q3 = c.prof ? clock64() + (long long)(descs[0].n & 0u) : 0;
-    // ---- step 3: staged headers out (kinds 4-5)
-    if (warp < EMIT_PRODUCER) move_all(4u * EMIT_NMAX, 6u * EMIT_NMAX, (uint32_t)warp * 4u + (uint32_t)(lane >> 3), 4u * EMIT_PRODUCER);
-    const long long c3 = c.prof ? clock64() : 0;
-    t_work += (unsigned long long)(c3 - c2);
-    t_s4 += (unsigned long long)(c3 - q3);
-    __syncthreads();   // stage s and the header slots are free again; desc[s^1] is published
-    if (c.prof) t_bar += (unsigned long long)(clock64() - c3);
+    const long long c7 = tick(c.prof);
+    t_b2 += (unsigned long long)(c7 - c6);
+    // ======== step 2: staged headers out
+    if (tid == 0) s_claim = 0;
+    if (warp < EMIT_PRODUCER) move_all(table_s, T.n, 2u * EMIT_NMAX, 4u * EMIT_NMAX, qw_all, 4u * EMIT_PRODUCER, true);
+    t_s3 += (unsigned long long)(tick(c.prof) - c7);
+    __syncthreads();   // stage s and the header slots are free again; the next tile's descriptors are published
     if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {
       flush_stats();
       __syncthreads();
@@ -1030,11 +1277,13 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __syncthreads();
   if (P.report_level > 0) flush_stats();
   if (c.prof && lane == 0) {
-    unsigned long long* o = c.prof + ((size_t)blockIdx.x * (EMIT_THREADS / 32) + warp) * 4;
+    unsigned long long* o = c.prof + ((size_t)blockIdx.x * (EMIT_THREADS / 32) + warp) * 6;
     o[0] = t_wait;
-    o[1] = t_work;
-    o[2] = t_s2;
-    o[3] = t_s4;
+    o[1] = t_s1;
+    o[2] = t_role;
+    o[3] = t_mv;
+    o[4] = t_b2;
+    o[5] = t_s3;
   }
 }
 

@@ -163,13 +163,14 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->d_prof) {   // last k_emit launch: mean cycles per warp index over the CTAs
     const int nw = EMIT_THREADS / 32;
-    std::vector<unsigned long long> h((size_t)ctx->n_sm * nw * 4);
+    std::vector<unsigned long long> h((size_t)ctx->n_sm * nw * 6);
     cudaMemcpy(h.data(), ctx->d_prof, h.size() * 8, cudaMemcpyDeviceToHost);
     for (int w = 0; w < nw; ++w) {
-      double a[4] = {0, 0, 0, 0};
+      double a[6] = {0, 0, 0, 0, 0, 0};
       for (int b = 0; b < ctx->n_sm; ++b)
-        for (int k = 0; k < 4; ++k) a[k] += (double)h[((size_t)b * nw + w) * 4 + k] / ctx->n_sm;
-      fprintf(stderr, "[mgk profile] k_emit warp %2d: wait %.0f work %.0f step2-own %.0f step4 %.0f cycles\n", w, a[0], a[1], a[2], a[3]);
+        for (int k = 0; k < 6; ++k) a[k] += (double)h[((size_t)b * nw + w) * 6 + k] / ctx->n_sm;
+      fprintf(stderr, "[mgk profile] k_emit warp %2d: stage wait %.0f, descriptors+barrier %.0f, role %.0f, bodies %.0f, barrier %.0f, headers %.0f cycles\n", w, a[0], a[1], a[2],
+              a[3], a[4], a[5]);
     }
     cudaFree(ctx->d_prof);
   }
@@ -312,20 +313,20 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     L.hdr = at;
     at += (P.out_mode == MGK_OUT_MGI_FULL_HEADER && P.paired ? 2u : 1u) * HDR_KIND_BYTES + 32u;   // the paired read has its own header only with --mgi-full-header
     L.desc = at;
-    at += EMIT_NMAX * EMIT_PIECES * (uint32_t)sizeof(PieceDesc);
+    at += 2u * EMIT_NMAX * EMIT_PIECES * (uint32_t)sizeof(PieceDesc);   // two tables (tile parity)
     at = up(at, 128u);
     const uint32_t nl_bytes = 16u * (EMIT_NMAX + 1u);
     L.nl1 = up(nl_bytes, 16u);
     L.meta = L.nl1 + up(nl_bytes, 16u);
     L.bins = L.meta + 16u * EMIT_NMAX;
     L.bytes = up(L.bins + 4u * ctx->bins_stride + 16u, 128u);
-    const int64_t avail = (int64_t)max_optin - (int64_t)fa.sharedSizeBytes - (int64_t)at - 256;
+    const int64_t avail = (int64_t)max_optin - (int64_t)fa.sharedSizeBytes - (int64_t)at - 256 - 512;   // 512: the movers' unpredicated loads run past a range
     const int64_t cap = (avail / 2 - (int64_t)L.bytes) / 128 * 128;
     if (cap < 4096) BAD("mgk_create: %d samples leave no shared memory for the record stages", P.S);
     L.cap = (uint32_t)cap;
     L.stage0 = at;
     L.stage_stride = L.bytes + L.cap;
-    L.total_bytes = L.stage0 + 2u * L.stage_stride;
+    L.total_bytes = L.stage0 + 2u * L.stage_stride + 512u;
     CUC(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
     int occ_e = 0;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_emit, EMIT_THREADS, L.total_bytes));
@@ -334,8 +335,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   }
 
   if (getenv("MGK_PROFILE")) {   // developer aid: per-warp cycle counters of k_emit, dumped at destroy
-    CUC(dalloc(&ctx->d_prof, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 4));
-    CUC(cudaMemset(ctx->d_prof, 0, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 4 * 8));
+    CUC(dalloc(&ctx->d_prof, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 6));
+    CUC(cudaMemset(ctx->d_prof, 0, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 6 * 8));
   }
   CUC(cudaEventCreate(&ctx->span_begin));
   CUC(cudaEventCreate(&ctx->span_end));
