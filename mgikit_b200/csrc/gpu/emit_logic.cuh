@@ -255,9 +255,10 @@ MGK_HD void build_header(const Params& P, const uint8_t* S, uint32_t cs0, const 
     } else {                             // prefix lane ":" readno ":" ccc ":" rrr
       const HdrInfo hi = hdr_info(P, S, G);
       const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len;
-      if (((uintptr_t)o & 15u) == 0) {   // a staging slot: whole vectors (the constants are aligned too)
+      if (((uintptr_t)o & 3u) == 0) {   // a staging slot: whole words (the constants are aligned too); the up to three
+                                        // bytes past the prefix are overwritten by this thread right below
         MGK_LOOP_ROLLED
-        for (uint32_t k = 0; k < Pn; k += 16u) *reinterpret_cast<uint4*>(o + k) = s_v4(S, cs0 + k);
+        for (uint32_t k = 0; k < Pn; k += 4u) *reinterpret_cast<uint32_t*>(o + k) = s_u32(S, cs0 + k);
         o += Pn;
       } else {
         o = put_span(o, S, cs0, Pn);
@@ -336,9 +337,22 @@ MGK_HD uint32_t keep_range(uint32_t wd, int lo, int hi) {  // keep bytes [lo,hi)
   if (lo) mask &= ~((1u << (8 * lo)) - 1u);
   return wd & mask;
 }
+// One word into the running sums.  q.high counts in units of -128: the bytes >= 63 are marked 0x80 and added as signed
+// bytes by the same dot-product instruction that adds the qualities (qc_line converts at the end).
+MGK_HD void qc_word(Qc& q, uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  q.sum = __dp4a(x, 0x01010101u, q.sum);
+  q.high = (uint32_t)__dp4a((int)bytes_ge63(x), 0x01010101, (int)q.high);
+#else
+  q.sum += byte_sum(x);
+  q.high -= 128u * (uint32_t)popc32(bytes_ge63(x));
+#endif
+}
 MGK_HD void qc_add(Qc& q, const uint4& a) {
-  q.sum += byte_sum(a.x) + byte_sum(a.y) + byte_sum(a.z) + byte_sum(a.w);
-  q.high += (uint32_t)(popc32(bytes_ge63(a.x)) + popc32(bytes_ge63(a.y)) + popc32(bytes_ge63(a.z)) + popc32(bytes_ge63(a.w)));
+  qc_word(q, a.x);
+  qc_word(q, a.y);
+  qc_word(q, a.z);
+  qc_word(q, a.w);
 }
 MGK_HD uint4 keep16(uint4 a, int lo, int hi) {
   a.x = keep_range(a.x, lo, hi);
@@ -359,6 +373,7 @@ MGK_HD Qc qc_line(const uint8_t* S, uint32_t start, uint32_t n) {
   MGK_LOOP_ROLLED
   for (uint32_t v = 1; v + 1u < nvec; ++v) qc_add(q, s_v4(S, al + (v << 4)));
   if (nvec > 1u) qc_add(q, keep16(s_v4(S, al + ((nvec - 1u) << 4)), 0, end - (int)((nvec - 1u) << 4)));
+  q.high = (0u - q.high) >> 7;
   return q;
 }
 

@@ -862,12 +862,13 @@ constexpr int EMIT_PRODUCER = EMIT_SWARPS + EMIT_WWARPS;
 constexpr int EMIT_THREADS = (EMIT_PRODUCER + 1) * 32;
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
 // staging slot k (0 barcode read's header, 1 paired read's own full header) of record i; inside a warp's 32 records,
-// rows of 8 are skewed by 16 bytes so that the lanes spread over all banks
+// rows of 8 are skewed by one word so that the 32 lanes of a warp, writing the same byte of their headers, hit 32 banks
+// (the slot stride is a multiple of 4 words)
 constexpr uint32_t HDR_WARP_BYTES = 32u * HDR_SLOT_BYTES + 64u;
 constexpr uint32_t HDR_KIND_BYTES = (EMIT_NMAX / 32) * HDR_WARP_BYTES;
 constexpr uint32_t HDR_AREA_BYTES = 2u * HDR_KIND_BYTES;
 __host__ __device__ inline uint32_t hdr_slot(uint32_t k, uint32_t i) {
-  return k * HDR_KIND_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 16u * ((i >> 3) & 3u);
+  return k * HDR_KIND_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 4u * ((i >> 3) & 3u);
 }
 
 struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 16-byte aligned
@@ -1058,6 +1059,17 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     }
     return G;
   };
+  auto geom_one = [&](const TileView& T, uint32_t i, int which) {   // only the rows of one read (the other's fields 0)
+    RecGeom G;
+    const uint32_t* nls = which == 2 ? T.nl2s : T.nl1s;
+    const uint32_t o = which == 2 ? T.o2 : T.o1;
+    const uint4 a = *reinterpret_cast<const uint4*>(nls + 4u * i + 4u);
+    const uint32_t h = nls[4u * i + 3u] + 1u + o, s1 = a.x + 1u + o, p1 = a.y + 1u + o, q1 = a.z + 1u + o, e1 = a.w + o;
+    const bool br = which == 2;
+    G.h2 = br ? h : 0u; G.s2 = br ? s1 : 0u; G.p2 = br ? p1 : 0u; G.q2 = br ? q1 : 0u; G.e2 = br ? e1 : 0u;
+    G.h1 = br ? 0u : h; G.s1 = br ? 0u : s1; G.p1 = br ? 0u : p1; G.q1 = br ? 0u : q1; G.e1 = br ? 0u : e1;
+    return G;
+  };
   auto dest = [&](const TileView& T, const RecMeta& mt, int which) -> uint8_t* {   // where the record's output starts
     const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
     return which == 2 ? c.out2 + T.bins[bin] + mt.off2 : c.out1 + T.bins[total + bin] + mt.off1;
@@ -1087,7 +1099,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       put(kh, 0u, 0u, 0u, 0u);
       return;
     }
-    const RecGeom G = geom(T, i);
+    const RecGeom G = geom_one(T, i, which);
     const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15);
     const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
     const uint32_t buf = which == 2 ? 0u : 1u << 31;
