@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1 << 20, help="read pairs per step per GPU (746 MB of text: > 5x L2)")
+    ap.add_argument("--pairs", type=int, default=1 << 21, help="read pairs per step per GPU (1.5 GB of text: > 10x L2)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
