@@ -841,18 +841,20 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
 }
 
 // ------------------------------------------------------------------ K4
-// TMA in, scalar threads for the control-heavy crumbs, half-warps for the bytes.  Persistent,
-// one CTA per SM.  A producer warp keeps two shared-memory stages full with bulk copies
+// TMA in, scalar threads for the control-heavy crumbs, quarter-warps for the bytes.  Persistent,
+// one CTA per SM.  A producer lane keeps two shared-memory stages full with bulk copies
 // (cp.async.bulk + mbarrier) of the next 128 records: text of both reads, newline rows, RecMeta
-// rows, bin-offset row.  On the staged tile, concurrently:
+// rows, bin-offset row.  On staged tile k, between two CTA-wide barriers:
 //   * 16 warps, one thread per (record, role): role 0 / 1 build the front / the tail of the
 //     rewritten header in a staging slot, role 2 / 3 the QC sums of the paired / barcode read
 //     (and --validate): scalar work with data-dependent branches, a different record per lane;
-//   * 12 warps, one HALF-WARP per byte range: every output record is header | "\n" sequence |
-//     "\n+\n" qualities (plan_read), the last two straight out of the staged input.  copy_piece
-//     writes 16-byte units aligned on the destination, adjacent lanes adjacent units.
-// then, after one barrier, all 28 warps move the staged headers out the same way (the paired
-// read's copy with its own read-number digit patched in).  Every input byte crosses HBM->SM
+//   * 8 of the other warps, one thread per (record, read): the descriptors of tile k + 1 (where every
+//     byte range of the record comes from and goes to), into the table of the other parity;
+//   * every warp, when that is done, draws rounds of four bodies from a shared cursor: a
+//     quarter-warp moves "\n" sequence | "\n+\n" qualities of one read as one destination range in
+//     16-byte units aligned on the destination, adjacent lanes adjacent units (move_pair_lane);
+// then, after a barrier, all warps move the staged headers out the same way (move_small_lane; the
+// paired read's copy with its own read-number digit patched in).  Every input byte crosses HBM->SM
 // once (bulk copies), every output byte SM->HBM once, in coalesced stores.
 constexpr int EMIT_NMAX = 128;               // records per staged tile (<= TILE_RECORDS, divides it)
 constexpr int EMIT_SROLES = 4;
