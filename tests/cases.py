@@ -105,6 +105,23 @@ def edge_cases():
         rag.append(pair(i + 1, bars[i % len(bars)], insert=ins, r1seq=r1s, q="?"))
     cases.append(("ragged-lengths", RunSpec(samples=samples, **kw), [chunk(rag)]))
     cases.append(("ragged-lengths-mgi", RunSpec(samples=samples, out_mode=1, **kw), [chunk(rag)]))
+    # long reads: bodies of many 16-byte units (the movers' loop past the units a lane takes in registers), the seam
+    # between sequence and qualities anywhere in them
+    lng = []
+    for i in range(300):
+        ins = "".join("ACGT"[v] for v in rng.integers(0, 4, size=int(rng.integers(180, 900))))
+        r1s = "".join("ACGT"[v] for v in rng.integers(0, 4, size=int(rng.integers(180, 1100))))
+        lng.append(pair(i + 1, bars[i % len(bars)], insert=ins, r1seq=r1s, q="F"))
+    cases.append(("long-reads", RunSpec(samples=samples, **kw), [chunk(lng)]))
+    cases.append(("long-reads-keep-barcode-mgi", RunSpec(samples=samples, out_mode=1, keep_barcode=True, **kw), [chunk(lng)]))
+    # very short reads: bodies shorter than one unit, seams inside the head or tail bytes
+    tiny = []
+    for i in range(300):
+        ins = "".join("ACGT"[v] for v in rng.integers(0, 4, size=int(rng.integers(0, 6))))
+        r1s = "".join("ACGT"[v] for v in rng.integers(0, 4, size=int(rng.integers(1, 9))))
+        tiny.append(pair(i + 1, bars[i % len(bars)], insert=ins, r1seq=r1s, q="#", hdr=f"@F{i % 10}L1C{i % 1000:03d}R{(i * 3) % 1000:03d}{i}"))
+    cases.append(("tiny-reads", RunSpec(samples=samples, **kw), [chunk(tiny)]))
+    cases.append(("tiny-reads-mgi", RunSpec(samples=samples, out_mode=1, **kw), [chunk(tiny)]))
     # empty chunk, one record, trailing partial record in either stream
     one = chunk(pairs[:1])
     cases.append(("single-record", RunSpec(samples=samples, **kw), [one]))
