@@ -935,9 +935,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   const int32_t* s_writing = reinterpret_cast<const int32_t*>(smem + lay.writing);
   const uint32_t n_rec = device_n_records(c, P);
   if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY | ERR_REC_TOO_LONG)) return;  // nothing safe to write
-  // this CTA's plan tiles: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
+  // this CTA's units of EMIT_NMAX records: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
   // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk size.
-  const uint32_t n_pt = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t n_pt = (n_rec + EMIT_NMAX - 1) / EMIT_NMAX;
   if (blockIdx.x >= n_pt) return;
   const uint32_t bins_stride = (2u * (uint32_t)total + 3u) & ~3u;
 
@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
 
   // producer state (lane 0 of the producer warp)
-  uint32_t next_rec = blockIdx.x * TILE_RECORDS, start2 = 0, start1 = 0;
+  uint32_t next_rec = blockIdx.x * EMIT_NMAX, start2 = 0, start1 = 0;
   bool fresh = true;   // next_rec opens a plan tile: its byte offsets come from the newline table
   auto produce = [&](int s) {   // lane 0 of the producer warp
     StageDesc& d = s_desc[s];
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       start2 = c.nl2[(long long)4 * r0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
       start1 = paired ? c.nl1[(long long)4 * r0 - 1] + 1u : 0u;
     }
-    const uint32_t pt_end = min((r0 / TILE_RECORDS + 1u) * TILE_RECORDS, n_rec);
+    const uint32_t pt_end = min((r0 / EMIT_NMAX + 1u) * EMIT_NMAX, n_rec);
     uint32_t lim = min(r0 + n_tile, pt_end);
     const uint32_t base2 = start2 & ~15u, base1 = start1 & ~15u;
     uint32_t e2, e1, len2, len1, off1;
@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     bulk_g2s(st + lay.meta, c.meta + r0, meta_bytes, &s_bar[s]);
     bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / TILE_RECORDS) * bins_stride, bins_bytes, &s_bar[s]);
     fresh = lim == pt_end;
-    next_rec = fresh ? (r0 / TILE_RECORDS + gridDim.x) * TILE_RECORDS : lim;
+    next_rec = fresh ? (r0 / EMIT_NMAX + gridDim.x) * EMIT_NMAX : lim;
     start2 = e2;
     start1 = e1;
   };
