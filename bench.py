@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 21, help="read pairs per step per GPU (1.5 GB of text: > 10x L2)")
+    ap.add_argument("--e2e-chunk-pairs", type=int, default=1 << 20, help="end to end, a step's batch goes through the C ABI in chunks of at most this many pairs")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -252,17 +253,29 @@ def main():
         h1 = torch.from_numpy(r1).pin_memory()
         host_args = ((h2.data_ptr(), h2.numel()), (h1.data_ptr(), h1.numel()))
 
+        # a step's batch goes through the ABI in chunks of at most --e2e-chunk-pairs (records have a fixed size in the
+        # synthetic lane, so the cuts are at record boundaries): (pointer, bytes) of both reads per chunk
+        assert r2.size == n * r2_rec and r1.size == n * r1_rec
+        n_sub = max(1, -(-n // a.e2e_chunk_pairs))
+        cuts = [n * j // n_sub for j in range(n_sub + 1)]
+        sub_args = [((h2.data_ptr() + cuts[j] * r2_rec, (cuts[j + 1] - cuts[j]) * r2_rec),
+                     (h1.data_ptr() + cuts[j] * r1_rec, (cuts[j + 1] - cuts[j]) * r1_rec)) for j in range(n_sub)]
+
         def run_e2e(steps):
             d2h = 0
-            for k in range(steps):
-                hp.submit(k, host_args[0], host_args[1], 0)
+            per_step = 0
+            for k in range(steps * n_sub):
+                hp.submit(k, sub_args[k % n_sub][0], sub_args[k % n_sub][1], 0)
                 if k >= 1:
                     res = hp.collect(device_out=True)      # results are in pinned host memory; no python copy
-                    d2h = res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
+                    per_step += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
                     hp.release(k - 1)
+                    if k % n_sub == 0:
+                        d2h, per_step = per_step, 0
             res = hp.collect(device_out=True)
-            d2h = res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
-            hp.release(steps - 1)
+            per_step += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
+            d2h = per_step
+            hp.release(steps * n_sub - 1)
             if world > 1:
                 hp.nccl_allreduce_counters()
             return d2h
@@ -276,7 +289,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": n * a.steps * world / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(in_bytes),
                "d2h_bytes_per_step": int(d2h), "timing": "host clock between barrier+synchronize, max over ranks; pinned buffers, "
-                                                          "2 chunks in flight"}
+                                                          f"{n_sub} chunk(s) per step, 2 chunks in flight"}
 
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (resident and end to end)
     def teardown():
