@@ -25,8 +25,9 @@ namespace mgk {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ROWS = 2;                                      // 32-byte pieces per thread and tile
-constexpr int SCAN_TILE = SCAN_THREADS * 32 * SCAN_ROWS;         // 16 KiB of text per stage
-constexpr int SCAN_STAGES = 4;                                    // bulk copies in flight per CTA (3 CTAs per SM)
+constexpr int SCAN_TILE = SCAN_THREADS * 32 * SCAN_ROWS * 2;     // 32 KiB of text per CTA and stage (SCAN_HALVES pieces per warp)
+constexpr int SCAN_STAGES = 2;                                    // bulk copies in flight per warp (3 CTAs of 8 warps per SM)
+constexpr int SCAN_HALVES = 2;                                    // 2 KiB pieces per stage: one bulk copy, one wait per 4 KiB
 constexpr int TILE_RECORDS = 256;                                // read pairs per K2/K4 tile
 constexpr int GROUP_TILES = 64;                                  // tiles per scan group
 
@@ -63,7 +64,7 @@ struct ChunkDev {
   uint32_t nl_cap, max_records;
   uint32_t* stg2;              // newline positions as found, one run per scan CTA (scan_cap entries each)
   uint32_t* stg1;
-  uint32_t* range_counts;      // [2][scan_grid] newlines found by each scan CTA
+  uint32_t* range_counts;      // [2][scan_grid * SCAN_WARPS] newlines found by each scan warp in its range
   uint32_t scan_grid, scan_cap;
   uint32_t* counts;            // [2] newline totals
   RecMeta* meta;
@@ -338,143 +339,176 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 
 // ------------------------------------------------------------------ K1
-// Newline scan without any inter-CTA dependency.  grid = (scan_grid, files), every CTA
-// owns ONE contiguous range of its stream and walks it through a ring of shared-memory
-// stages that the TMA engine keeps full (cp.async.bulk + mbarrier), so the bytes in
-// flight per SM are set by the ring depth, not by registers or by how long a CTA waits.
-// The index of a newline inside its range needs only the CTA's own running count; the
-// positions go to a per-range run of a staging array and k_gather_newlines then packs
-// the runs into the final table (32 B per read pair, L2-resident) once the per-range
-// totals are known.  Order inside a warp's 2 KiB: (row, lane), lane l = bytes 16l..16l+15.
+// Newline scan without any dependency between warps.  grid = (scan_grid, files); every WARP owns
+// ONE contiguous range of its stream (scan_grid * SCAN_WARPS ranges per stream) and walks it
+// through its own ring of shared-memory stages that the TMA engine keeps full (cp.async.bulk +
+// mbarrier, issued by the warp's lane 0), so the bytes in flight per SM are set by the ring depth,
+// not by registers, and no CTA-wide barrier is ever taken.  The index of a newline inside its
+// range needs only the warp's own running count; the positions go to a per-range run of a staging
+// array and k_gather_newlines then packs the runs into the final table (32 B per read pair,
+// L2-resident) once the per-range totals are known.  Order inside a warp's 2 KiB: (row, lane),
+// lane l = bytes 32l..32l+31 of the row.
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_PIECE = 32 * 32 * SCAN_ROWS;          // bytes a warp scans at a time
+constexpr int SCAN_WTILE = SCAN_PIECE * SCAN_HALVES;     // bytes per warp and stage
+static_assert(SCAN_TILE == SCAN_WARPS * SCAN_WTILE, "stage size");
+// '\n' flags of the words a (earlier bytes) and b as 8 bits in byte order at the top of the product: the flags sit at
+// bits 3,11,19,27 (a) and 7,15,23,31 (b), the four partial products of 0x00204081 put them at 24..27 and 28..31, and no
+// two of the 32 partial-product bits coincide (so no carries).  k0a / k7f: 0x0a0a0a0a / 0x7f7f7f7f held in registers
+// (lop3 takes one immediate at most).  Exact for every byte value.
+__device__ __forceinline__ uint32_t nl_raw(uint32_t w, uint32_t k0a, uint32_t k7f) {   // bit 7 of a byte CLEAR <=> it is '\n'
+  uint32_t x7, r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(x7) : "r"(w), "r"(k0a), "r"(k7f));            // (w ^ k0a) & k7f
+  const uint32_t t = x7 + 0x7f7f7f7fu;
+  asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(t), "r"(w), "r"(k0a));               // t | (w ^ k0a)
+  return r;
+}
+__device__ __forceinline__ uint32_t nl_pair(uint32_t a, uint32_t b, uint32_t k0a, uint32_t k7f) {
+  const uint32_t za = nl_raw(a, k0a, k7f) >> 4, zb = nl_raw(b, k0a, k7f);
+  uint32_t x;
+  asm("lop3.b32 %0, %1, %2, 0x08080808, 0xe4;" : "=r"(x) : "r"(za), "r"(zb));                // bits 3,11,.. of za, the others of zb
+  return (~x & 0x88888888u) * 0x00204081u;
+}
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_newlines(ChunkDev c, int n_files) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_full[SCAN_STAGES];
-  __shared__ uint32_t s_warp[2][SCAN_THREADS / 32];
+  __shared__ __align__(8) uint64_t s_full[SCAN_WARPS][SCAN_STAGES];
   const int file = blockIdx.y;
   if (file >= n_files) return;
   const uint8_t* __restrict__ buf = file == 0 ? c.r2 : c.r1;
   const uint32_t len = file == 0 ? c.len2 : c.len1;
-  uint32_t* __restrict__ out = (file == 0 ? c.stg2 : c.stg1) + (size_t)blockIdx.x * c.scan_cap;
-  const uint32_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
-  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t t0 = min(blockIdx.x * per, ntiles), t1 = min(t0 + per, ntiles);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
+  const uint32_t n_ranges = gridDim.x * SCAN_WARPS, range = blockIdx.x * SCAN_WARPS + (uint32_t)warp;
+  uint32_t* __restrict__ out = (file == 0 ? c.stg2 : c.stg1) + (size_t)range * c.scan_cap;
+  const uint32_t ntiles = (len + SCAN_WTILE - 1) / SCAN_WTILE;
+  const uint32_t per = (ntiles + n_ranges - 1) / n_ranges;
+  const uint32_t t0 = min(range * per, ntiles), t1 = min(t0 + per, ntiles);
+  unsigned char* ring = smem + (size_t)warp * (SCAN_STAGES * SCAN_WTILE);
+  uint64_t* full = s_full[warp];
+  if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  auto issue = [&](uint32_t t) {   // thread 0: tile t -> stage (t - t0) % SCAN_STAGES
+  __syncwarp();
+  auto issue = [&](uint32_t t) {   // lane 0: tile t -> stage (t - t0) % SCAN_STAGES of the warp's ring
     const int s = (int)((t - t0) % SCAN_STAGES);
-    const uint32_t off = t * SCAN_TILE;
-    const uint32_t bytes = (min(len - off, (uint32_t)SCAN_TILE) + 15u) & ~15u;   // chunk buffers are padded
-    mbar_expect_tx(&s_full[s], bytes);
-    bulk_g2s(smem + (size_t)s * SCAN_TILE, buf + off, bytes, &s_full[s]);
+    const uint32_t off = t * SCAN_WTILE;
+    const uint32_t bytes = (min(len - off, (uint32_t)SCAN_WTILE) + 15u) & ~15u;   // chunk buffers are padded
+    mbar_expect_tx(&full[s], bytes);
+    bulk_g2s(ring + (size_t)s * SCAN_WTILE, buf + off, bytes, &full[s]);
   };
-  if (tid == 0)
+  if (lane == 0)
     for (uint32_t t = t0; t < t1 && t < t0 + SCAN_STAGES; ++t) issue(t);
+  uint32_t k0a, k7f;
+  asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(k0a));   // opaque: kept in registers
+  asm volatile("mov.u32 %0, 0x7f7f7f7f;" : "=r"(k7f));
 
   uint32_t run = 0;   // newlines of this range so far
   bool overflow = false;
   for (uint32_t t = t0; t < t1; ++t) {
     const uint32_t it = t - t0;
     const int s = (int)(it % SCAN_STAGES);
-    mbar_wait(&s_full[s], (it / SCAN_STAGES) & 1u);
-    const unsigned char* st = smem + (size_t)s * SCAN_TILE;
-    // a warp's 2 KiB: SCAN_ROWS rows of 1 KiB, lane l = bytes 32l..32l+31 of the row
-    const uint32_t wbase = t * SCAN_TILE + (uint32_t)warp * (1024u * SCAN_ROWS) + 32u * (uint32_t)lane;
-    const bool last_tile = t * SCAN_TILE + SCAN_TILE > len;   // only the stream's last tile holds bytes beyond len
-    uint32_t m[SCAN_ROWS];   // bit p set <=> byte p of the lane's 32 bytes is a newline
-    uint32_t cp = 0;         // newline counts of the rows, 16 bits each (a row holds at most 1024)
+    mbar_wait(&full[s], (it / SCAN_STAGES) & 1u);
+#pragma unroll 1
+    for (int h = 0; h < SCAN_HALVES; ++h) {
+      const unsigned char* st = ring + (size_t)s * SCAN_WTILE + (size_t)h * SCAN_PIECE + 32u * (uint32_t)lane;
+      const uint32_t wbase = t * SCAN_WTILE + (uint32_t)h * SCAN_PIECE + 32u * (uint32_t)lane;
+      if (t * SCAN_WTILE + (uint32_t)h * SCAN_PIECE >= len) break;                          // warp-uniform
+      const bool last_piece = t * SCAN_WTILE + (uint32_t)(h + 1) * SCAN_PIECE > len;      // only the stream's last piece holds bytes beyond len
+      uint32_t m[SCAN_ROWS];   // bit p set <=> byte p of the lane's 32 bytes is a newline
+      uint32_t cp = 0;         // newline counts of the rows, 16 bits each (a row holds at most 1024)
 #pragma unroll
-    for (int j = 0; j < SCAN_ROWS; ++j) {
-      const uint32_t off = wbase + 1024u * j;
-      const uint4 va = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE));
-      const uint4 vb = *reinterpret_cast<const uint4*>(st + (off - t * SCAN_TILE) + 16u);
-      // 0x80 flags of a word -> 4 bits at the top of the product (no two partial products meet, so no carries)
-      const uint32_t C = 0x00204081u;
-      uint32_t mm = ((nl_flags(va.x) * C) >> 28) | (((nl_flags(va.y) * C) >> 24) & 0xf0u) | (((nl_flags(va.z) * C) >> 20) & 0xf00u) |
-                    (((nl_flags(va.w) * C) >> 16) & 0xf000u) | (((nl_flags(vb.x) * C) >> 12) & 0xf0000u) |
-                    (((nl_flags(vb.y) * C) >> 8) & 0xf00000u) | (((nl_flags(vb.z) * C) >> 4) & 0xf000000u) |
-                    ((nl_flags(vb.w) * C) & 0xf0000000u);
-      if (last_tile && off + 32u > len) mm = off >= len ? 0u : mm & ((1u << (len - off)) - 1u);   // bytes beyond the stream
-      m[j] = mm;
-      cp += (uint32_t)__popc(mm) << (16 * j);
-    }
-    uint32_t ip = cp;   // inclusive scan over the lanes
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t x = __shfl_up_sync(0xffffffffu, ip, d);
-      if (lane >= d) ip += x;
-    }
-    const uint32_t tot = __shfl_sync(0xffffffffu, ip, 31);
-    const uint32_t row0 = tot & 0xffffu, wtotal = row0 + (tot >> 16);
-    if (lane == 0) s_warp[it & 1u][warp] = wtotal;
-    __syncthreads();   // every thread has read its part of stage s; s_warp[it & 1] is complete (and [~it & 1] free again)
-    uint32_t warp_off = 0, agg = 0;
-#pragma unroll
-    for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) {
-      const uint32_t x = s_warp[it & 1u][wi];
-      if (wi < warp) warp_off += x;
-      agg += x;
-    }
-    if (tid == 0 && t + SCAN_STAGES < t1) issue(t + SCAN_STAGES);   // stage s is free again
-#pragma unroll
-    for (int j = 0; j < SCAN_ROWS; ++j) {
-      uint32_t mm = m[j];
-      if (mm == 0) continue;
-      const uint32_t cj = (cp >> (16 * j)) & 0xffffu, ij = (ip >> (16 * j)) & 0xffffu;
-      uint32_t idx = run + warp_off + (j ? row0 : 0u) + ij - cj;
-      const uint32_t off = wbase + 1024u * j;
-      if (idx + cj > c.scan_cap) {
-        overflow = true;
-        continue;
+      for (int j = 0; j < SCAN_ROWS; ++j) {
+        const uint32_t off = wbase + 1024u * j;
+        const uint4 va = *reinterpret_cast<const uint4*>(st + 1024u * j);
+        const uint4 vb = *reinterpret_cast<const uint4*>(st + 1024u * j + 16u);
+        const uint32_t lo = __byte_perm(nl_pair(va.x, va.y, k0a, k7f), nl_pair(va.z, va.w, k0a, k7f), 0x0073u);
+        const uint32_t hi = __byte_perm(nl_pair(vb.x, vb.y, k0a, k7f), nl_pair(vb.z, vb.w, k0a, k7f), 0x0073u);
+        uint32_t mm = __byte_perm(lo, hi, 0x5410u);
+        if (last_piece && off + 32u > len) mm = off >= len ? 0u : mm & ((1u << (len - off)) - 1u);   // bytes beyond the stream
+        m[j] = mm;
+        cp += (uint32_t)__popc(mm) << (16 * j);
       }
-      uint32_t* o = out + idx;
-      o[0] = off + (uint32_t)(__ffs(mm) - 1);          // a record's "\n+\n" makes two per lane common: straight-line
-      mm &= mm - 1;
-      if (mm) {
-        o[1] = off + (uint32_t)(__ffs(mm) - 1);
-        mm &= mm - 1;
-        for (uint32_t q = 2; mm; ++q) {
-          o[q] = off + (uint32_t)(__ffs(mm) - 1);
+      uint32_t ip = cp;   // inclusive scan over the lanes
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, ip, d);
+        if (lane >= d) ip += x;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, ip, 31);
+      const uint32_t row0 = tot & 0xffffu, wtotal = row0 + (tot >> 16);
+      if (run + wtotal > c.scan_cap) {   // warp-uniform
+        overflow = true;
+      } else {
+        uint32_t* orun = out + run;
+#pragma unroll
+        for (int j = 0; j < SCAN_ROWS; ++j) {
+          uint32_t mm = m[j];
+          if (mm == 0) continue;
+          const uint32_t cj = (cp >> (16 * j)) & 0xffffu, ij = (ip >> (16 * j)) & 0xffffu;
+          uint32_t* o = orun + ((j ? row0 : 0u) + ij - cj);
+          const uint32_t off = wbase + 1024u * j;
+          o[0] = off + (uint32_t)(__ffs(mm) - 1);          // a record's "\n+\n" makes two per lane common: straight-line
           mm &= mm - 1;
+          if (mm) {
+            o[1] = off + (uint32_t)(__ffs(mm) - 1);
+            mm &= mm - 1;
+            for (uint32_t q = 2; mm; ++q) {
+              o[q] = off + (uint32_t)(__ffs(mm) - 1);
+              mm &= mm - 1;
+            }
+          }
         }
       }
+      run += wtotal;
     }
-    run += agg;
+    __syncwarp();   // every lane has read its part of stage s
+    if (lane == 0 && t + SCAN_STAGES < t1) issue(t + SCAN_STAGES);
   }
-  if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
-  if (tid == 0) c.range_counts[(size_t)file * gridDim.x + blockIdx.x] = run;
+  if (overflow && lane == 0) atomicOr(&c.status->error, ERR_NL_CAPACITY);
+  if (lane == 0) c.range_counts[(size_t)file * n_ranges + range] = run;
 }
 
 // Packs the per-range runs into the final newline table and leaves the total in counts[file].
-// grid = (scan_grid * GATHER_SPLIT, files): GATHER_SPLIT CTAs share one range.
-constexpr int GATHER_SPLIT = 4;
+// grid = (ranges, files).
 __global__ void __launch_bounds__(256) k_gather_newlines(ChunkDev c, int n_files) {
-  __shared__ uint32_t s_prefix;
+  __shared__ uint32_t s_part[8];
   const int file = blockIdx.y;
   if (file >= n_files) return;
-  const uint32_t range = blockIdx.x / GATHER_SPLIT, part = blockIdx.x % GATHER_SPLIT;
-  const uint32_t* rc = c.range_counts + (size_t)file * c.scan_grid;
-  if (threadIdx.x < 32) {
+  const uint32_t range = blockIdx.x, n_ranges = gridDim.x;
+  const uint32_t* rc = c.range_counts + (size_t)file * n_ranges;
+  {   // newlines in front of this range: all threads, independent loads
     uint32_t sum = 0;
-    for (uint32_t i = threadIdx.x; i < range; i += 32u) sum += rc[i];
+    for (uint32_t i = threadIdx.x; i < range; i += blockDim.x) sum += rc[i];
     sum = __reduce_add_sync(0xffffffffu, sum);
-    if (threadIdx.x == 0) s_prefix = sum;
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
   }
   __syncthreads();
-  const uint32_t prefix = s_prefix, n = min(rc[range], c.scan_cap);
+  uint32_t prefix = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) prefix += s_part[w];
+  const uint32_t n = min(rc[range], c.scan_cap);
   const uint32_t* __restrict__ src = (file == 0 ? c.stg2 : c.stg1) + (size_t)range * c.scan_cap;
   uint32_t* __restrict__ nl = file == 0 ? c.nl2 : c.nl1;
   bool overflow = false;
-  for (uint32_t i = part * blockDim.x + threadIdx.x; i < n; i += GATHER_SPLIT * blockDim.x) {
-    if (prefix + i < c.nl_cap) nl[prefix + i] = src[i];
-    else overflow = true;
+  for (uint32_t i0 = 0; i0 < n; i0 += 4u * blockDim.x) {   // four loads in flight per thread
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
+      v[k] = i < n ? src[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
+      if (i < n) {
+        if (prefix + i < c.nl_cap) nl[prefix + i] = v[k];
+        else overflow = true;
+      }
+    }
   }
   if (overflow) atomicOr(&c.status->error, ERR_NL_CAPACITY);
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) c.counts[file] = prefix + rc[range];   // every newline, stored or not
+  if (range == n_ranges - 1 && threadIdx.x == 0) c.counts[file] = prefix + rc[range];   // every newline, stored or not
 }
 
 // ------------------------------------------------------------------ K2

@@ -281,7 +281,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   // the mean share of a range plus a whole stage of newlines; lanes whose newline density is more skewed than
   // that are refused (MGK_ERR_CAPACITY), real FASTQ is nowhere near.
   ctx->scan_grid = (uint32_t)ctx->n_sm * 3u / (P.paired ? 2u : 1u);   // 3 CTAs per SM over both streams, one wave
-  ctx->scan_cap = (uint32_t)((4 * (ctx->cap_records * 4 + 4)) / ctx->scan_grid + SCAN_TILE + 64) & ~3u;
+  ctx->scan_cap = (uint32_t)((4 * (ctx->cap_records * 4 + 4)) / ((uint64_t)ctx->scan_grid * SCAN_WARPS) + SCAN_WTILE + 64) & ~3u;   // per range (one per warp)
   CUC(cudaFuncSetAttribute(k_scan_newlines, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_STAGES * SCAN_TILE));
   ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
   ctx->groups_max = (ctx->tiles_max + GROUP_TILES - 1) / GROUP_TILES;
@@ -365,9 +365,9 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
       CUC(dalloc(&s.nl1, ctx->cap_records * 4 + 16));
       CUC(cudaMemcpy(s.nl1, nl_sentinel, sizeof nl_sentinel, cudaMemcpyHostToDevice));
     }
-    CUC(dalloc(&s.stg2, (size_t)ctx->scan_grid * ctx->scan_cap));
-    if (P.paired) CUC(dalloc(&s.stg1, (size_t)ctx->scan_grid * ctx->scan_cap));
-    CUC(dalloc(&s.ctrl, 8 + 2 * (size_t)ctx->scan_grid));
+    CUC(dalloc(&s.stg2, (size_t)ctx->scan_grid * SCAN_WARPS * ctx->scan_cap));
+    if (P.paired) CUC(dalloc(&s.stg1, (size_t)ctx->scan_grid * SCAN_WARPS * ctx->scan_cap));
+    CUC(dalloc(&s.ctrl, 8 + 2 * (size_t)ctx->scan_grid * SCAN_WARPS));
     CUC(dalloc(&s.meta, ctx->cap_records + 1));
     CUC(dalloc(&s.tile_bins, (size_t)ctx->tiles_max * ctx->bins_stride));
     CUC(dalloc(&s.group_sums, (size_t)ctx->groups_max * B2));
@@ -450,7 +450,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   {
     const dim3 grid(ctx->scan_grid, P.paired ? 2 : 1);
     k_scan_newlines<<<grid, SCAN_THREADS, SCAN_STAGES * SCAN_TILE, st>>>(c, P.paired ? 2 : 1);
-    k_gather_newlines<<<dim3(grid.x * GATHER_SPLIT, grid.y), 256, 0, st>>>(c, P.paired ? 2 : 1);
+    k_gather_newlines<<<dim3(grid.x * SCAN_WARPS, grid.y), 256, 0, st>>>(c, P.paired ? 2 : 1);
     ctx->launches += 2;
   }
   CU(cudaEventRecord(s.ev[2], st));
@@ -689,10 +689,10 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
   uint32_t *d_nl = nullptr, *d_ctrl = nullptr, *d_stg = nullptr;
   Status* d_status = nullptr;
   const uint32_t grid = ctx->scan_grid;
-  const uint64_t tiles = (len + SCAN_TILE - 1) / SCAN_TILE, per = (tiles + grid - 1) / grid;
-  const uint32_t cap = (uint32_t)std::min<uint64_t>(per * SCAN_TILE + 4, 0xfffffff0u);   // a range cannot hold more newlines than bytes
+  const uint64_t ranges = (uint64_t)grid * SCAN_WARPS, tiles = (len + SCAN_WTILE - 1) / SCAN_WTILE, per = (tiles + ranges - 1) / ranges;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(per * SCAN_WTILE + 4, 0xfffffff0u);   // a range cannot hold more newlines than bytes
   int rc = MGK_OK;
-  std::vector<uint32_t> h_ctrl(8 + grid, 0);
+  std::vector<uint32_t> h_ctrl(8, 0);
   do {
 #define TRY(call)                                                                  \
   if ((call) != cudaSuccess) {                                                     \
@@ -701,11 +701,11 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
   }
     TRY(dalloc(&d_buf, len + 256));
     TRY(dalloc(&d_nl, capacity + 4));
-    TRY(dalloc(&d_stg, (size_t)grid * cap));
-    TRY(dalloc(&d_ctrl, 8 + (size_t)grid));
+    TRY(dalloc(&d_stg, (size_t)ranges * cap));
+    TRY(dalloc(&d_ctrl, 8 + (size_t)ranges));
     TRY(dalloc(&d_status, 1));
     TRY(cudaMemcpy(d_buf, buf, len, cudaMemcpyHostToDevice));
-    TRY(cudaMemset(d_ctrl, 0, (8 + (size_t)grid) * 4));
+    TRY(cudaMemset(d_ctrl, 0, (8 + (size_t)ranges) * 4));
     TRY(cudaMemcpy(d_status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice));
     ChunkDev c{};
     c.r2 = d_buf;
@@ -719,7 +719,7 @@ extern "C" int mgk_scan_newlines(mgk_ctx* ctx, const uint8_t* buf, uint64_t len,
     c.range_counts = d_ctrl + 8;
     c.status = d_status;
     k_scan_newlines<<<dim3(grid, 1), SCAN_THREADS, SCAN_STAGES * SCAN_TILE>>>(c, 1);
-    k_gather_newlines<<<dim3(grid * GATHER_SPLIT, 1), 256>>>(c, 1);
+    k_gather_newlines<<<dim3((uint32_t)ranges, 1), 256>>>(c, 1);
     ctx->launches += 2;
     TRY(cudaDeviceSynchronize());
     TRY(cudaMemcpy(h_ctrl.data(), d_ctrl, 32, cudaMemcpyDeviceToHost));
