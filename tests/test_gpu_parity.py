@@ -26,9 +26,20 @@ def test_newline_scan_stage(oracle_lib, gpu_lib):
     o = make_hotpath(oracle_lib, "orc_", spec)
     rng = np.random.default_rng(3)
     bufs = [np.zeros(0, np.uint8), np.full(1, 10, np.uint8), np.full(5000, 10, np.uint8), np.full(40000, 65, np.uint8)]
-    for n in (1, 15, 16, 17, 63, 64, 65, 16383, 16384, 16385, 16384 * 3 + 5, 1 << 20):
+    for n in (1, 15, 16, 17, 63, 64, 65, 2047, 2048, 2049, 4095, 4096, 4097, 16383, 16384, 16385, 16384 * 3 + 5, 1 << 20):
         b = rng.integers(32, 127, size=n, dtype=np.uint8)
         b[rng.random(n) < 0.02] = 10
+        bufs.append(b)
+    # every byte value (the flag arithmetic must not take 0x0b, 0x8a, 0x00 ... for a newline), dense newlines
+    b = rng.integers(0, 256, size=300000, dtype=np.uint8)
+    b[rng.random(b.size) < 0.05] = 10
+    bufs.append(b)
+    bufs.append(np.tile(np.array([10, 11, 0x8A, 9, 0x0A, 0x1A, 0x2A, 0x80, 0, 0x7F, 0xFF, 10, 10], np.uint8), 4001))
+    # one 4 KiB stage per scan warp of the whole grid, one byte either side (every range holds one tile or none)
+    k = g.scan_ranges() * 4096 if hasattr(g, "scan_ranges") else 1776 * 4096
+    for n in (k - 1, k, k + 1, k + 4096 + 3):
+        b = rng.integers(32, 127, size=n, dtype=np.uint8)
+        b[rng.random(n) < 0.011] = 10
         bufs.append(b)
     r1, r2 = synth.make_block(synth.CONFIG2, 0, 5000)
     bufs += [r1, r2]
