@@ -406,145 +406,8 @@ MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G,
   return pl;
 }
 
-// ---------------------------------------------------------------- emit
-// A record's rewritten header is a short list of (source pointer, length)
-// segments in FIXED slots (absent pieces have length 0), so the list lives in
-// registers: no dynamically indexed local array.
-constexpr int MAX_SEG = 16;
-struct SegList {
-  const uint8_t* p[MAX_SEG];
-  uint32_t n[MAX_SEG];
-};
-
-// Header segments of a matched record; which = 2 (barcode read) or 1 (paired read).
-MGK_HD void header_segments(const Params& P, const uint8_t* r2, const uint8_t* r1, const RecGeom& G, const RecPlan& pl,
-                            int bar_t, int umi_t, int which, SegList& s) {
-  const uint8_t* lit = P.consts + P.prefix_len;
-  const uint8_t* H = r2 + G.h2;
-  const uint32_t hl = G.s2 - G.h2, L = (uint32_t)P.L;
-  const uint8_t* bar = r2 + G.p2 - 1u - (uint32_t)P.BL;
-  const uint8_t* nsrc = which == 2 ? r2 + G.s2 - 2u : r1 + G.s1 - 2u;  // src/lib.rs:1275,1288,1302,1314
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int j = 0; j < MAX_SEG; ++j) {
-    s.p[j] = lit;
-    s.n[j] = 0;
-  }
-  const uint8_t* umi_p = lit;
-  uint32_t umi_n = 0;
-  if (umi_t >= 0) {
-    umi_p = bar + P.BL - P.tpl[umi_t].g[8];
-    umi_n = (uint32_t)P.tpl[umi_t].g[7];
-  }
-  if (P.out_mode == MGK_OUT_ILLUMINA) {
-    const uint32_t sep = hl - 3u;
-    s.p[0] = P.consts;          s.n[0] = (uint32_t)P.prefix_len;
-    s.p[1] = H + L + 1;         s.n[1] = 1;
-    s.p[2] = lit + LIT_COLON;   s.n[2] = 1;
-    s.p[3] = H + pl.z;          s.n[3] = sep - pl.z;
-    s.p[4] = lit + LIT_COLON;   s.n[4] = 1;
-    s.p[5] = H + pl.f1;         s.n[5] = L + 6u - pl.f1;
-    s.p[6] = lit + LIT_COLON;   s.n[6] = 1;
-    s.p[7] = H + pl.f2;         s.n[7] = L + 10u - pl.f2;
-    s.p[8] = lit + LIT_COLON;   s.n[8] = umi_t >= 0 ? 1u : 0u;
-    s.p[9] = umi_p;             s.n[9] = umi_n;
-    s.p[10] = lit + LIT_SPACE;  s.n[10] = 1;
-  } else {
-    if (which == 2) { s.p[0] = H;         s.n[0] = hl - 1u; }
-    else            { s.p[0] = r1 + G.h1; s.n[0] = G.s1 - G.h1 - 1u; }
-    if (P.out_mode != MGK_OUT_MGI_FULL_HEADER) return;
-    s.p[1] = lit + LIT_SPACE;   s.n[1] = 1;
-    s.p[2] = umi_p;             s.n[2] = umi_n;
-    s.p[3] = lit + LIT_SPACE;   s.n[3] = umi_t >= 0 ? 1u : 0u;
-  }
-  s.p[11] = nsrc;               s.n[11] = 1;
-  s.p[12] = lit + LIT_TAIL;     s.n[12] = 5;
-  if (bar_t >= 0) {
-    const TemplateDev& T = P.tpl[bar_t];
-    s.p[13] = bar + P.BL - T.g[2];  s.n[13] = (uint32_t)T.g[1];
-    s.p[14] = lit + LIT_PLUS;       s.n[14] = T.has_i5 ? 1u : 0u;
-    s.p[15] = bar + P.BL - T.g[5];  s.n[15] = T.has_i5 ? (uint32_t)T.g[4] : 0u;
-  }
-}
-
-// Lane `lane` of `nlanes` writes its share of the short segments, one byte per
-// lane per step (headers are ~60 B: two steps).
-MGK_HD uint32_t emit_segments(uint8_t* dst, const SegList& s, int lane, int nlanes) {
-  uint32_t total = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int j = 0; j < MAX_SEG; ++j) total += s.n[j];
-  for (uint32_t k = (uint32_t)lane; k < total; k += (uint32_t)nlanes) {
-    uint32_t start = 0;
-    const uint8_t* src = nullptr;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < MAX_SEG; ++j) {
-      if (src == nullptr && k < start + s.n[j]) src = s.p[j] + (k - start);
-      start += s.n[j];
-    }
-    dst[k] = (uint8_t)ldg_u8(src);
-  }
-  return total;
-}
-
-// Long verbatim span: every lane moves 16-byte units that are ALIGNED ON THE
-// DESTINATION (so the dominant traffic is full-width coalesced stores); the
-// source is read as the two aligned 16-byte vectors that cover the unit and
-// funnel-shifted.  Head/tail bytes that do not fill a destination unit are
-// written bytewise.  `src` must stay readable up to the next 16-byte boundary
-// after src+n (chunk buffers are padded).
-MGK_HD void copy_span(uint8_t* dst, const uint8_t* src, uint32_t n, int lane, int nlanes) {
-  const uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
-  const uint32_t h = head < n ? head : n;
-  for (uint32_t k = (uint32_t)lane; k < h; k += (uint32_t)nlanes) dst[k] = (uint8_t)ldg_u8(src + k);
-  if (n <= h) return;
-  const uint32_t units = (n - h) >> 4;
-  uint8_t* d = dst + h;
-  const uint8_t* s = src + h;
-  const uint32_t sh = (uint32_t)((uintptr_t)s & 15u);
-  const uint4* sv = (const uint4*)(s - sh);
-  if (sh == 0) {
-    for (uint32_t u = (uint32_t)lane; u < units; u += (uint32_t)nlanes) ((uint4*)d)[u] = ldg_v4(sv + u);
-  } else {
-    const uint32_t wsel = sh >> 2, bsh = (sh & 3u) * 8u;
-    for (uint32_t u = (uint32_t)lane; u < units; u += (uint32_t)nlanes) {
-      const uint4 a = ldg_v4(sv + u), b = ldg_v4(sv + u + 1);
-      // words a.x a.y a.z a.w b.x b.y b.z b.w ; take 5 starting at wsel
-      uint32_t w0, w1, w2, w3, w4;
-      if (wsel == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
-      else if (wsel == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
-      else if (wsel == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
-      else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
-      uint4 o;
-      if (bsh == 0) {
-        o.x = w0; o.y = w1; o.z = w2; o.w = w3;
-      } else {
-#if defined(__CUDA_ARCH__)
-        o.x = __funnelshift_r(w0, w1, bsh);
-        o.y = __funnelshift_r(w1, w2, bsh);
-        o.z = __funnelshift_r(w2, w3, bsh);
-        o.w = __funnelshift_r(w3, w4, bsh);
-#else
-        o.x = (w0 >> bsh) | (w1 << (32u - bsh));
-        o.y = (w1 >> bsh) | (w2 << (32u - bsh));
-        o.z = (w2 >> bsh) | (w3 << (32u - bsh));
-        o.w = (w3 >> bsh) | (w4 << (32u - bsh));
-#endif
-      }
-      ((uint4*)d)[u] = o;
-    }
-  }
-  const uint32_t done = h + (units << 4);
-  for (uint32_t k = done + (uint32_t)lane; k < n; k += (uint32_t)nlanes) dst[k] = (uint8_t)ldg_u8(src + k);
-}
-
 // ---------------------------------------------------------------- QC sums
-// sum_qc (src/lib.rs:458-474) over src[0..n): this lane's share, 16-byte
-// aligned vectors with out-of-range bytes masked.  Returns (sum, count>=63).
+// sum_qc (src/lib.rs:458-474): (sum of the quality bytes, how many are >= 63); the loops are in emit_logic.cuh
 struct Qc {
   uint32_t sum, high;
 };
@@ -560,78 +423,8 @@ MGK_HD uint32_t byte_sum(uint32_t x) {
   return (x & 0xff) + ((x >> 8) & 0xff) + ((x >> 16) & 0xff) + (x >> 24);
 #endif
 }
-MGK_HD uint32_t keep_bytes(uint32_t w, int lo, int hi) {  // keep bytes [lo,hi) of the word, 0<=lo<=hi<=4 clipped
-  if (lo < 0) lo = 0;
-  if (hi > 4) hi = 4;
-  if (hi <= lo) return 0u;
-  uint32_t mask = hi == 4 ? 0xffffffffu : ((1u << (8 * hi)) - 1u);
-  mask &= lo == 0 ? 0xffffffffu : ~((1u << (8 * lo)) - 1u);
-  return w & mask;
-}
-
-MGK_HD Qc qc_partial(const uint8_t* src, uint32_t n, int lane, int nlanes) {
-  Qc q;
-  q.sum = q.high = 0;
-  if (n == 0) return q;
-  const uint32_t sh = (uint32_t)((uintptr_t)src & 15u);
-  const uint4* sv = (const uint4*)(src - sh);
-  const uint32_t nvec = (sh + n + 15u) >> 4;
-  for (uint32_t v = (uint32_t)lane; v < nvec; v += (uint32_t)nlanes) {
-    uint4 a = ldg_v4(sv + v);
-    const int lo = (int)sh - (int)(v << 4);            // first valid byte inside this vector
-    const int hi = (int)(sh + n) - (int)(v << 4);      // one past the last valid byte
-    if (lo > 0 || hi < 16) {
-      a.x = keep_bytes(a.x, lo, hi);
-      a.y = keep_bytes(a.y, lo - 4, hi - 4);
-      a.z = keep_bytes(a.z, lo - 8, hi - 8);
-      a.w = keep_bytes(a.w, lo - 12, hi - 12);
-    }
-    q.sum += byte_sum(a.x) + byte_sum(a.y) + byte_sum(a.z) + byte_sum(a.w);
-    q.high += (uint32_t)(popc32(bytes_ge63(a.x)) + popc32(bytes_ge63(a.y)) + popc32(bytes_ge63(a.z)) + popc32(bytes_ge63(a.w)));
-  }
-  return q;
-}
-
 // ---------------------------------------------------------------- validate
-// check_read_content (src/lib.rs:476-509) + header equality (:1163-1178): this
-// lane's share of one pair; returns the lowest failing priority (1..7) or 0.
-//   1..3 paired read ('@', base, quality)  4 header mismatch  5..7 barcode read
-MGK_HD int validate_partial(const Params& P, const uint8_t* r2, const uint8_t* r1, const RecGeom& G, int lane, int nlanes) {
-  int worst = 0;
-  auto note = [&](int p) {
-    if (worst == 0 || p < worst) worst = p;
-  };
-  auto base_ok = [](uint32_t n) {
-    return n == 'A' || n == 'C' || n == 'G' || n == 'T' || n == 'N' || n == 'a' || n == 'c' || n == 'g' || n == 't' || n == 'n';
-  };
-  if (P.paired) {
-    if (lane == 0 && ldg_u8(r1 + G.h1) != '@') note(1);
-    for (uint32_t i = G.s1 + (uint32_t)lane; i + 1u < G.p1; i += (uint32_t)nlanes)
-      if (!base_ok(ldg_u8(r1 + i))) note(2);
-    for (uint32_t i = G.q1 + (uint32_t)lane; i < G.e1; i += (uint32_t)nlanes) {
-      const uint32_t q = ldg_u8(r1 + i);
-      if (q > 73u || q < 33u) note(3);
-    }
-    if (P.mgi_data) {
-      const uint32_t l1 = G.s1 - 2u - G.h1, l2 = G.s2 - 2u - G.h2;
-      if (l1 != l2) {
-        if (lane == 0) note(4);
-      } else {
-        for (uint32_t i = (uint32_t)lane; i < l1; i += (uint32_t)nlanes)
-          if (ldg_u8(r1 + G.h1 + i) != ldg_u8(r2 + G.h2 + i)) note(4);
-      }
-    }
-  }
-  if (lane == 0 && ldg_u8(r2 + G.h2) != '@') note(5);
-  for (uint32_t i = G.s2 + (uint32_t)lane; i + 1u < G.p2; i += (uint32_t)nlanes)
-    if (!base_ok(ldg_u8(r2 + i))) note(6);
-  for (uint32_t i = G.q2 + (uint32_t)lane; i < G.e2; i += (uint32_t)nlanes) {
-    const uint32_t q = ldg_u8(r2 + i);
-    if (q > 73u || q < 33u) note(7);
-  }
-  return worst;
-}
-
+// priority (validate_pair, emit_logic.cuh) -> MGK_VAL_* kind
 MGK_HD int validate_kind(int priority) {
   switch (priority) {
     case 1: case 5: return MGK_VAL_HEADER_AT;

@@ -1,20 +1,20 @@
 // sm_100a kernels of the demultiplex hot path.
 //
-//   K1 k_scan_newlines   record-boundary scan of both read streams: 16-byte vector
-//                        loads, SIMD-in-word '\n' detection, block scan, single-pass
-//                        decoupled look-back -> sorted newline positions
+//   K1 k_scan_newlines   record-boundary scan of both read streams: every warp streams its own
+//      k_gather_newlines range through a TMA-fed shared-memory ring, SIMD-in-word '\n' detection,
+//                        warp scan -> sorted newline positions
 //                        (replaces memchr_iter, /root/reference/src/file_utils.rs:95)
-//   K2 k_match_plan      one thread per read pair: barcode extract + 2-bit pack +
-//                        XOR/popc nearest-set match against the index table staged in
-//                        shared memory, output lengths, stable in-tile bin offsets
+//   K2 k_match_plan      one thread per read pair: exact-match hash probe of the raw index bytes,
+//                        misses by a whole warp (2-bit pack + XOR/popc nearest-set match against the
+//                        index table staged in shared memory), output lengths, stable in-tile bin offsets
 //                        (find_matching_sample src/lib.rs:223-443, update_mismatches :1212)
 //   K3 k_scan_*          per-bin exclusive scan over tiles -> order-preserving
 //                        destination of every record (multisplit)
-//   K4 k_scatter         one warp per read pair: header rewrite, barcode trim,
-//                        destination-aligned 16-byte stores, fused Q30/quality sums
+//   K4 k_emit            persistent: TMA-staged tiles, scalar roles (header rewrite, Q30/quality sums,
+//                        --validate), quarter-warp movers with destination-aligned 16-byte stores
 //                        (src/lib.rs:1188-1337, src/sample_data.rs:569-654)
 //
-// All four are HBM-bound integer/byte kernels; no tensor cores on purpose.
+// All of them are HBM-bound integer/byte kernels; no tensor cores on purpose.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -83,19 +83,6 @@ struct ChunkDev {
 };
 
 // ------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint32_t nl_flags(uint32_t w) {  // 0x80 in every byte that is '\n', exact
-  const uint32_t x = w ^ 0x0a0a0a0au;
-  return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-}
-
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __device__ __forceinline__ uint32_t device_n_records(const ChunkDev& c, const Params& P) {
   const uint32_t a = c.counts[0] >> 2;
@@ -902,7 +889,6 @@ constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushe
 // (the slot stride is a multiple of 4 words)
 constexpr uint32_t HDR_WARP_BYTES = 32u * HDR_SLOT_BYTES + 64u;
 constexpr uint32_t HDR_KIND_BYTES = (EMIT_NMAX / 32) * HDR_WARP_BYTES;
-constexpr uint32_t HDR_AREA_BYTES = 2u * HDR_KIND_BYTES;
 __host__ __device__ inline uint32_t hdr_slot(uint32_t k, uint32_t i) {
   return k * HDR_KIND_BYTES + (i >> 5) * HDR_WARP_BYTES + (i & 31u) * HDR_SLOT_BYTES + 4u * ((i >> 3) & 3u);
 }
