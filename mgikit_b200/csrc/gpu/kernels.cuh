@@ -932,12 +932,14 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __shared__ Params P;
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ StageDesc s_desc[2];
-  __shared__ uint32_t s_claim;   // cursor of the tile's list of bodies
+  __shared__ uint32_t s_claim[2][2];   // cursors of a tile's two work lists (bodies, staged headers), by tile parity
+  __shared__ uint32_t s_headers_built;  // header-builder warps that have finished their tile, counted over the whole launch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   copy_params_to_smem(&P, Pg);
   if (tid == 0) {
-    s_claim = 0;
+    s_claim[0][0] = s_claim[0][1] = s_claim[1][0] = s_claim[1][1] = 0;
+    s_headers_built = 0;
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1259,49 +1261,68 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
         }
       }
     }
+    if (warp < 2 * (EMIT_NMAX / 32)) {   // a header-builder warp is through with the tile: its slots may be read
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(&s_headers_built, 1u);
+      }
+    }
     const long long c5 = tick(c.prof);
     t_role += (unsigned long long)(c5 - c4);
-    // Every warp then draws rounds of four bodies from the tile's cursor until the list is exhausted (the next draw
-    // is in flight while a round is moved), so a warp joins whenever its other work is done; eight of the warps
-    // without a role make the next tile's descriptors after their first two rounds (its stage has landed by then).
+    // Every warp then draws rounds of four descriptors from the tile's cursors until both lists are exhausted (the
+    // next draw is in flight while a round is moved), so a warp joins whenever its other work is done: first the
+    // bodies; then, once all eight header-builder warps have signalled (they have, long before, except in a tile's
+    // last instants), the staged headers.  Eight of the warps without a role make the next tile's descriptors after
+    // their first two rounds (its stage has landed by then).  No CTA-wide barrier between bodies and headers.
     if (warp < EMIT_PRODUCER) {
-      auto claim_bodies = [&](uint32_t max_rounds) {
+      uint32_t* cursors = s_claim[k & 1u];
+      if (tid == 0) s_claim[(k + 1u) & 1u][0] = s_claim[(k + 1u) & 1u][1] = 0;   // untouched during this tile
+      auto claim = [&](uint32_t* cursor, uint32_t first, uint32_t max_rounds, bool headers) {
         const uint32_t l8 = (uint32_t)lane & 7u, q = (uint32_t)lane >> 3;
         uint32_t raw = 0;
-        if (lane == 0) raw = atomicAdd(&s_claim, 4u);
+        if (lane == 0) raw = atomicAdd(cursor, 4u);
         uint32_t cur = __shfl_sync(0xffffffffu, raw, 0);
         MGK_LOOP_ROLLED
         for (uint32_t r = 1; cur < 2u * EMIT_NMAX; ++r) {
           const bool more = r < max_rounds;
-          if (more && lane == 0) raw = atomicAdd(&s_claim, 4u);
+          if (more && lane == 0) raw = atomicAdd(cursor, 4u);
           const uint32_t it = cur + q;
           if (it % EMIT_NMAX < T.n) {
-            const uint4 pd = lds_v4(table_s + it * 16u);
-            if (pd.w) move_body(pd, l8);
+            const uint4 pd = lds_v4(table_s + (first + it) * 16u);
+            if (headers) {
+              if (pd.z) move_header(pd, l8);
+            } else if (pd.w) {
+              move_body(pd, l8);
+            }
           }
           if (!more) break;
           cur = __shfl_sync(0xffffffffu, raw, 0);
         }
       };
       if (desc_warp) {
-        claim_bodies(2u);
+        claim(&cursors[0], 0u, 2u, false);
         const long long c8 = tick(c.prof);
         mbar_wait(&s_bar[s ^ 1], ((k + 1u) >> 1) & 1u);
         if (s_desc[s ^ 1].n) make_descs(tile_view(s ^ 1), (k + 1u) & 1u, desc_t);
         __syncwarp();
         t_s1 += (unsigned long long)(tick(c.prof) - c8);
       }
-      claim_bodies(0xffffffffu);
+      claim(&cursors[0], 0u, 0xffffffffu, false);
+      const long long c6 = tick(c.prof);
+      t_mv += (unsigned long long)(c6 - c5);
+      if (lane == 0) {
+        const uint32_t want = (k + 1u) * 2u * (EMIT_NMAX / 32);
+        while (*reinterpret_cast<volatile uint32_t*>(&s_headers_built) < want) {
+        }
+        __threadfence_block();
+      }
+      __syncwarp();
+      const long long c7 = tick(c.prof);
+      t_b2 += (unsigned long long)(c7 - c6);
+      claim(&cursors[1], 2u * EMIT_NMAX, 0xffffffffu, true);
+      t_s3 += (unsigned long long)(tick(c.prof) - c7);
     }
-    const long long c6 = tick(c.prof);
-    t_mv += (unsigned long long)(c6 - c5);
-    __syncthreads();   // the staged headers are complete
-    const long long c7 = tick(c.prof);
-    t_b2 += (unsigned long long)(c7 - c6);
-    // ======== step 2: staged headers out
-    if (tid == 0) s_claim = 0;
-    if (warp < EMIT_PRODUCER) move_all(table_s, T.n, 2u * EMIT_NMAX, 4u * EMIT_NMAX, qw_all, 4u * EMIT_PRODUCER, true);
-    t_s3 += (unsigned long long)(tick(c.prof) - c7);
     __syncthreads();   // stage s and the header slots are free again; the next tile's descriptors are published
     if (P.report_level > 0 && (k % EMIT_FLUSH_TILES) == EMIT_FLUSH_TILES - 1u) {
       flush_stats();
