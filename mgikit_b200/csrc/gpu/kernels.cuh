@@ -934,12 +934,14 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __shared__ StageDesc s_desc[2];
   __shared__ uint32_t s_claim[2][2];   // cursors of a tile's two work lists (bodies, staged headers), by tile parity
   __shared__ uint32_t s_headers_built;  // header-builder warps that have finished their tile, counted over the whole launch
+  __shared__ uint32_t s_abort;          // errors of the earlier kernels, read once for the whole CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   copy_params_to_smem(&P, Pg);
   if (tid == 0) {
     s_claim[0][0] = s_claim[0][1] = s_claim[1][0] = s_claim[1][1] = 0;
     s_headers_built = 0;
+    s_abort = c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY | ERR_REC_TOO_LONG);
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   }
   const int32_t* s_writing = reinterpret_cast<const int32_t*>(smem + lay.writing);
   const uint32_t n_rec = device_n_records(c, P);
-  if (c.status->error & (ERR_OUT_CAPACITY | ERR_NL_CAPACITY | ERR_REC_TOO_LONG)) return;  // nothing safe to write
+  if (s_abort) return;  // nothing safe to write (one read: another CTA may be raising ERR_REC_TOO_LONG right now)
   // this CTA's units of EMIT_NMAX records: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
   // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk size.
   const uint32_t n_pt = (n_rec + EMIT_NMAX - 1) / EMIT_NMAX;
@@ -1169,22 +1171,6 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     const uint32_t owner = pa < hb ? pa : pa >= tail0 ? pa - tail0 : (pa - hb) >> 4;
     if (pa < n && (owner & 7u) == l8) g[pa] = (uint8_t)pv;
   };
-  // quarter-warp `qw` of `nqw` takes the descriptors first + qw, + nqw, ... of [first, end) of a table
-  auto move_all = [&](uint32_t table_s, uint32_t n_tile_rec, uint32_t first, uint32_t end, uint32_t qw, uint32_t nqw, bool headers) {
-    const uint32_t l8 = (uint32_t)lane & 7u;
-    MGK_LOOP_ROLLED
-    for (uint32_t it = first + qw; it < end; it += nqw)
-      if (it % EMIT_NMAX < n_tile_rec) {
-        const uint4 pd = lds_v4(table_s + it * 16u);
-        if (headers) {
-          if (pd.z) move_header(pd, l8);
-        } else if (pd.w) {
-          move_body(pd, l8);
-        }
-      }
-  };
-  const uint32_t qw_all = (uint32_t)warp * 4u + (uint32_t)(lane >> 3);                  // quarter-warp among all workers
-  const uint32_t qw_w = (uint32_t)(warp - EMIT_SWARPS) * 4u + (uint32_t)(lane >> 3);    // ... among the warps without a role
   const bool desc_warp = warp >= EMIT_SWARPS && warp < EMIT_SWARPS + 2 * (EMIT_NMAX / 32);
   const uint32_t desc_t = (uint32_t)(tid - EMIT_SWARPS * 32);
 
