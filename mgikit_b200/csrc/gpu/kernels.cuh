@@ -1299,8 +1299,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       t_mv += (unsigned long long)(c6 - c5);
       if (lane == 0) {
         const uint32_t want = (k + 1u) * 2u * (EMIT_NMAX / 32);
-        while (*reinterpret_cast<volatile uint32_t*>(&s_headers_built) < want) {
-        }
+        while (*reinterpret_cast<volatile uint32_t*>(&s_headers_built) < want) __nanosleep(40);   // do not take the LSU from the working warps
         __threadfence_block();
       }
       __syncwarp();
