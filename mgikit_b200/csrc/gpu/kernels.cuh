@@ -971,6 +971,10 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
     const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
     n_tile = max(1u, min((lay.cap - 256u) / mean, (uint32_t)EMIT_NMAX));
+    if (n_tile < (uint32_t)EMIT_NMAX) {   // a unit of EMIT_NMAX records in equal parts rather than a full tile and a sliver
+      const uint32_t parts = (EMIT_NMAX + n_tile - 1u) / n_tile;
+      n_tile = (EMIT_NMAX + parts - 1u) / parts;
+    }
   }
 
   // producer state (lane 0 of the producer warp)
