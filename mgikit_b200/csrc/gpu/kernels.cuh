@@ -959,26 +959,27 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   const int32_t* s_writing = reinterpret_cast<const int32_t*>(smem + lay.writing);
   const uint32_t n_rec = device_n_records(c, P);
   if (s_abort) return;  // nothing safe to write (one read: another CTA may be raising ERR_REC_TOO_LONG right now)
-  // this CTA's units of EMIT_NMAX records: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
-  // neighbouring tiles, so the pages they touch (input and every bin's output region) are few whatever the chunk size.
-  const uint32_t n_pt = (n_rec + EMIT_NMAX - 1) / EMIT_NMAX;
-  if (blockIdx.x >= n_pt) return;
+  if (n_rec == 0) return;
   const uint32_t bins_stride = (2u * (uint32_t)total + 3u) & ~3u;
 
-  // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are shrunk below)
-  uint32_t n_tile;
+  // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are shrunk below), and
+  // the unit of ownership: EMIT_NMAX records when a whole tile of them fits a stage, else a plan tile cut into equal
+  // parts (many samples or long records leave less room: three tiles of 86 are better than a tile of 117 and a sliver)
+  uint32_t n_tile, unit;
   {
     const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
     const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
     n_tile = max(1u, min((lay.cap - 256u) / mean, (uint32_t)EMIT_NMAX));
-    if (n_tile < (uint32_t)EMIT_NMAX) {   // a unit of EMIT_NMAX records in equal parts rather than a full tile and a sliver
-      const uint32_t parts = (EMIT_NMAX + n_tile - 1u) / n_tile;
-      n_tile = (EMIT_NMAX + parts - 1u) / parts;
-    }
+    unit = n_tile < (uint32_t)EMIT_NMAX ? (uint32_t)TILE_RECORDS : (uint32_t)EMIT_NMAX;
+    const uint32_t parts = (unit + n_tile - 1u) / n_tile;
+    n_tile = (unit + parts - 1u) / parts;
   }
+  // this CTA's units: blockIdx.x, + gridDim.x, ...  Interleaved: at any moment the CTAs of the grid work on
+  // neighbouring records, so the pages they touch (input and every bin's output region) are few whatever the chunk size.
+  if (blockIdx.x >= (n_rec + unit - 1u) / unit) return;
 
   // producer state (lane 0 of the producer warp)
-  uint32_t next_rec = blockIdx.x * EMIT_NMAX, start2 = 0, start1 = 0;
+  uint32_t next_rec = blockIdx.x * unit, start2 = 0, start1 = 0;
   bool fresh = true;   // next_rec opens a plan tile: its byte offsets come from the newline table
   auto produce = [&](int s) {   // lane 0 of the producer warp
     StageDesc& d = s_desc[s];
@@ -992,7 +993,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       start2 = c.nl2[(long long)4 * r0 - 1] + 1u;   // c.nl2[-1] is a sentinel -1: record 0 starts at byte 0
       start1 = paired ? c.nl1[(long long)4 * r0 - 1] + 1u : 0u;
     }
-    const uint32_t pt_end = min((r0 / EMIT_NMAX + 1u) * EMIT_NMAX, n_rec);
+    const uint32_t pt_end = min((r0 / unit + 1u) * unit, n_rec);
     uint32_t lim = min(r0 + n_tile, pt_end);
     const uint32_t base2 = start2 & ~15u, base1 = start1 & ~15u;
     uint32_t e2, e1, len2, len1, off1;
@@ -1028,7 +1029,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     bulk_g2s(st + lay.meta, c.meta + r0, meta_bytes, &s_bar[s]);
     bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / TILE_RECORDS) * bins_stride, bins_bytes, &s_bar[s]);
     fresh = lim == pt_end;
-    next_rec = fresh ? (r0 / EMIT_NMAX + gridDim.x) * EMIT_NMAX : lim;
+    next_rec = fresh ? (r0 / unit + gridDim.x) * unit : lim;
     start2 = e2;
     start1 = e1;
   };
