@@ -1265,7 +1265,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     // next draw is in flight while a round is moved), so a warp joins whenever its other work is done: first the
     // bodies; then, once all eight header-builder warps have signalled (they have, long before, except in a tile's
     // last instants), the staged headers.  Eight of the warps without a role make the next tile's descriptors after
-    // their first two rounds (its stage has landed by then).  No CTA-wide barrier between bodies and headers.
+    // their first three rounds (its stage has landed by then).  No CTA-wide barrier between bodies and headers.
     if (warp < EMIT_PRODUCER) {
       uint32_t* cursors = s_claim[k & 1u];
       if (tid == 0) s_claim[(k + 1u) & 1u][0] = s_claim[(k + 1u) & 1u][1] = 0;   // untouched during this tile
@@ -1292,7 +1292,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
         }
       };
       if (desc_warp) {
-        claim(&cursors[0], 0u, 2u, false);
+        claim(&cursors[0], 0u, 3u, false);
         const long long c8 = tick(c.prof);
         mbar_wait(&s_bar[s ^ 1], ((k + 1u) >> 1) & 1u);
         if (s_desc[s ^ 1].n) make_descs(tile_view(s ^ 1), (k + 1u) & 1u, desc_t);
