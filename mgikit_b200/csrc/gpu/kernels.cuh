@@ -883,6 +883,8 @@ constexpr int EMIT_SWARPS = EMIT_SROLES * EMIT_NMAX / 32;
 constexpr int EMIT_WWARPS = 11;
 constexpr int EMIT_PRODUCER = EMIT_SWARPS + EMIT_WWARPS;
 constexpr int EMIT_THREADS = (EMIT_PRODUCER + 1) * 32;
+static_assert(EMIT_WWARPS >= 2 * (EMIT_NMAX / 32), "the descriptor warps (one thread per (record, read)) are worker warps without a role");
+static_assert(EMIT_THREADS <= 1024 && EMIT_THREADS % 128 == 0, "one CTA per SM, whole warp-allocation granules");
 constexpr uint32_t EMIT_FLUSH_TILES = 48;    // QC accumulators (u32) are flushed this often
 // staging slot k (0 barcode read's header, 1 paired read's own full header) of record i; inside a warp's 32 records,
 // rows of 8 are skewed by one word so that the 32 lanes of a warp, writing the same byte of their headers, hit 32 banks
