@@ -1,0 +1,85 @@
+"""Randomised chunk-level cases (CPU): the device logic compiled by g++ against the oracle on run descriptions and
+records drawn at random -- template shapes, index lengths, flags, header digits, read lengths, barcode damage.  The
+fixed cases of cases.py pin what the reference's tests pin; this looks for what nobody thought of."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from mgikit_b200.plan import RunSpec, Sample
+from util import run_both
+
+TEMPLATES = [("i7{a}:i5{b}", True, False), ("i5{b}:i7{a}", True, False), ("i7{a}:um{u}:i5{b}", True, True),
+             ("um{u}:i7{a}", False, True), ("i7{a}", False, False), ("i7{a}:--3:i5{b}", True, False)]
+
+
+def _rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(alphabet[v] for v in rng.integers(0, len(alphabet), size=n))
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    shape, dual, has_umi = TEMPLATES[int(rng.integers(0, len(TEMPLATES)))]
+    a, b, u = int(rng.integers(6, 13)), int(rng.integers(6, 13)), int(rng.integers(4, 10))
+    tmpl = shape.format(a=a, b=b, u=u)
+    n_samples = int(rng.integers(2, 40))
+    seen, samples = set(), []
+    while len(samples) < n_samples:
+        i7, i5 = _rand_seq(rng, a), (_rand_seq(rng, b) if dual else ".")
+        if (i7, i5) in seen or (not dual and any(s.i7 == i7 for s in samples)):
+            continue
+        seen.add((i7, i5))
+        sid = f"S{len(samples) % max(1, n_samples - int(rng.integers(0, 3)))}"   # now and then two rows share an id
+        samples.append(Sample(sid, i7, i5))
+    paired = bool(rng.random() < 0.8)
+    out_mode = int(rng.integers(0, 3))
+    l_pos = int(rng.integers(3, 12))
+    spec = RunSpec(samples=samples, template=tmpl, i7_rc=bool(rng.random() < 0.3), i5_rc=bool(dual and rng.random() < 0.3),
+                   paired=paired, out_mode=out_mode, keep_barcode=bool(rng.random() < 0.2),
+                   report_level=int(rng.integers(0, 3)), mismatches=int(rng.integers(0, 4)),
+                   per_index_error=bool(rng.random() < 0.3), l_position=l_pos,
+                   illumina_prefix="@" + _rand_seq(rng, int(rng.integers(1, 30)), "ABCxyz019") + ":",
+                   max_chunk_bytes=1 << 20, max_chunk_records=4096)
+    # what the read carries: the sheet's index, reverse-complemented where the flag says the sheet is
+    comp = str.maketrans("ACGT", "TGCA")
+    rc = lambda s: s.translate(comp)[::-1]
+    items = [(it[:2], int(it[2:])) for it in tmpl.split(":")]
+    flow = _rand_seq(rng, l_pos - 1, "ABCDEFGHV0123456789")
+    recs2, recs1 = [], []
+    for i in range(int(rng.integers(1, 400))):
+        s = samples[int(rng.integers(0, n_samples))]
+        parts = []
+        for kind, n in items:
+            if kind == "i7":
+                parts.append(rc(s.i7) if spec.i7_rc else s.i7)
+            elif kind == "i5":
+                parts.append(rc(s.i5) if spec.i5_rc else s.i5)
+            else:
+                parts.append(_rand_seq(rng, n))
+        bar = list("".join(parts))
+        r = rng.random()
+        if r < 0.25:      # substitutions
+            for _ in range(int(rng.integers(1, 4))):
+                bar[int(rng.integers(0, len(bar)))] = "ACGTN"[int(rng.integers(0, 5))]
+        elif r < 0.30:    # something the dictionary alphabet does not have
+            bar[int(rng.integers(0, len(bar)))] = "acgtnX."[int(rng.integers(0, 7))]
+        elif r < 0.35:
+            bar = list(_rand_seq(rng, len(bar)))
+        bar = "".join(bar)
+        ins = _rand_seq(rng, int(rng.integers(0, 260)))
+        num = str(int(rng.integers(0, 10 ** int(rng.integers(1, 12))))).zfill(int(rng.integers(1, 14)))
+        h = f"@{flow}L{int(rng.integers(1, 5))}C{int(rng.integers(0, 1000)):03d}R{int(rng.integers(0, 1000)):03d}{num}"
+        q2 = "".join(chr(int(v)) for v in rng.integers(33, 74, size=len(ins) + len(bar)))
+        recs2.append(f"{h}/2\n{ins}{bar}\n+\n{q2}\n".encode())
+        r1s = _rand_seq(rng, int(rng.integers(1, 300)))
+        q1 = "".join(chr(int(v)) for v in rng.integers(33, 74, size=len(r1s)))
+        recs1.append(f"{h}/1\n{r1s}\n+\n{q1}\n".encode())
+    r2 = np.frombuffer(b"".join(recs2), np.uint8)
+    r1 = np.frombuffer(b"".join(recs1), np.uint8) if paired else None
+    return spec, [(r2, r1)]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_case_device_logic_matches_oracle(oracle_lib, emu_lib, seed):
+    spec, chunks = _case(1000 + seed)
+    run_both(oracle_lib, "orc_", emu_lib, "emu_", spec, chunks, what=f"fuzz seed {seed}: {spec.template} m={spec.mismatches} mode={spec.out_mode}")

@@ -141,3 +141,11 @@ def test_full_size_properties(gpu_lib):
     assert ids == sorted(ids)
     assert int(res.seg_len_r1.sum()) == res.out_r1_bytes and int(res.seg_len_r2.sum()) == res.out_r2_bytes
     g.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_cuda_matches_oracle_random_cases(oracle_lib, gpu_lib, seed):
+    """The randomised cases of test_fuzz_cpu.py through the kernels."""
+    from test_fuzz_cpu import _case
+    spec, chunks = _case(1000 + seed)
+    run_both(oracle_lib, "orc_", gpu_lib, "mgk_", spec, chunks, what=f"fuzz seed {seed}: {spec.template} m={spec.mismatches} mode={spec.out_mode}")
