@@ -83,3 +83,49 @@ def _case(seed):
 def test_random_case_device_logic_matches_oracle(oracle_lib, emu_lib, seed):
     spec, chunks = _case(1000 + seed)
     run_both(oracle_lib, "orc_", emu_lib, "emu_", spec, chunks, what=f"fuzz seed {seed}: {spec.template} m={spec.mismatches} mode={spec.out_mode}")
+
+
+def _mixed_case(seed):
+    """Several templates of one barcode length in one sheet (per-sample template and rc columns), with and without
+    --comprehensive-scan; the reads mix every template's layout and damaged barcodes."""
+    rng = np.random.default_rng(seed)
+    BL = 24
+    shapes = ["i78:um8:i58", "i58:i78:um8", "um16:i78", "i712:i512", "um8:i78:i58", "i78:--8:i58"]
+    picks = [shapes[int(v)] for v in rng.choice(len(shapes), size=int(rng.integers(2, 4)), replace=False)]
+    pool = [_rand_seq(rng, 12) for _ in range(10)]   # few index strings, shared between templates: collisions on purpose
+    samples, seen = [], set()
+    for k in range(int(rng.integers(3, 16))):
+        t = picks[int(rng.integers(0, len(picks)))]
+        items = [(it[:2], int(it[2:])) for it in t.split(":")]
+        l7 = next(n for kd, n in items if kd == "i7")
+        l5 = next((n for kd, n in items if kd == "i5"), 0)
+        i7 = pool[int(rng.integers(0, len(pool)))][:l7]
+        i5 = pool[int(rng.integers(0, len(pool)))][:l5] if l5 else "."
+        if (t, i7, i5) in seen or (not l5 and any(x[0] == t and x[1] == i7 for x in seen)):
+            continue
+        seen.add((t, i7, i5))
+        samples.append(Sample(f"M{k}", i7, i5, t, str(int(rng.integers(0, 2))), str(int(rng.integers(0, 2))) if l5 else "."))
+    if not samples:
+        samples.append(Sample("M0", pool[0][:8], pool[1][:8], "i78:um8:i58", "0", "0"))
+    spec = RunSpec(samples=samples, paired=True, out_mode=int(rng.integers(0, 3)), comprehensive_scan=bool(rng.random() < 0.5),
+                   mismatches=int(rng.integers(0, 3)), per_index_error=bool(rng.random() < 0.3), l_position=5,
+                   report_level=2, illumina_prefix="@I:R:FC02:", max_chunk_bytes=1 << 20, max_chunk_records=4096)
+    recs2, recs1 = [], []
+    for i in range(int(rng.integers(50, 500))):
+        bar = list("".join(pool[int(rng.integers(0, len(pool)))][:8] for _ in range(3)))
+        if rng.random() < 0.4:
+            for _ in range(int(rng.integers(1, 3))):
+                bar[int(rng.integers(0, BL))] = "ACGTN"[int(rng.integers(0, 5))]
+        bar = "".join(bar)
+        h = f"@FC02L1C{i % 900:03d}R{i % 77:03d}{i:08d}"
+        ins = _rand_seq(rng, int(rng.integers(0, 40)))
+        recs2.append(f"{h}/2\n{ins}{bar}\n+\n{'F' * (len(ins) + BL)}\n".encode())
+        recs1.append(f"{h}/1\nGGGGCCCCAAAATTTT\n+\n{'9' * 16}\n".encode())
+    return spec, [(np.frombuffer(b"".join(recs2), np.uint8), np.frombuffer(b"".join(recs1), np.uint8))]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_mixed_library_device_logic_matches_oracle(oracle_lib, emu_lib, seed):
+    spec, chunks = _mixed_case(5000 + seed)
+    run_both(oracle_lib, "orc_", emu_lib, "emu_", spec, chunks,
+             what=f"mixed fuzz seed {seed}: m={spec.mismatches} comp={spec.comprehensive_scan} mode={spec.out_mode}")

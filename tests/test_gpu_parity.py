@@ -149,3 +149,11 @@ def test_cuda_matches_oracle_random_cases(oracle_lib, gpu_lib, seed):
     from test_fuzz_cpu import _case
     spec, chunks = _case(1000 + seed)
     run_both(oracle_lib, "orc_", gpu_lib, "mgk_", spec, chunks, what=f"fuzz seed {seed}: {spec.template} m={spec.mismatches} mode={spec.out_mode}")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_cuda_matches_oracle_random_mixed_libraries(oracle_lib, gpu_lib, seed):
+    from test_fuzz_cpu import _mixed_case
+    spec, chunks = _mixed_case(5000 + seed)
+    run_both(oracle_lib, "orc_", gpu_lib, "mgk_", spec, chunks,
+             what=f"mixed fuzz seed {seed}: m={spec.mismatches} comp={spec.comprehensive_scan} mode={spec.out_mode}")
