@@ -42,7 +42,28 @@ def synthetic_variants():
             ("cfg2-keep", synth.CONFIG2, ["--keep-barcode"], 5000),
             ("cfg3-perindex", synth.CONFIG3, ["--per-index-error"], 5000),
             ("cfg2-report1", synth.CONFIG2, ["--report-level", "1"], 5000),
-            ("cfg2-noisy", small, ["--report-limit", "7"], 5000)]
+            ("cfg2-noisy", small, ["--report-limit", "7"], 5000)] + odd_lanes()
+
+
+def odd_lanes():
+    """Lanes nobody would sequence, to pin the corners against the reference's binary: template orders, short and
+    barcode-only reads, m = 0..3 (ambiguity), single-end dual index, flags in combination."""
+    L = synth.LaneSpec
+    noisy = dict(frac_one_mm=0.2, frac_two_mm=0.1, frac_random=0.1, frac_n=0.05)
+    return [("odd-i5-i7-umi-m2", L("odd1", 12, "i58:i78:um8", r1_len=75, r2_insert=60, mismatches=2, seed=61001, **noisy), [], 3000),
+            ("odd-umi16-i7", L("odd2", 10, "um16:i78", r1_len=50, r2_insert=40, seed=61002, **noisy), [], 3000),
+            ("odd-single-end-dual-rc", L("odd3", 16, "i78:i58", r1_len=0, r2_insert=100, i5_rc=True, seed=61003, **noisy), [], 3000),
+            ("odd-m0", L("odd4", 6, "i712:i512", r1_len=30, r2_insert=30, mismatches=0, seed=61004, **noisy), [], 3000),
+            ("odd-m3-per-index", L("odd5", 8, "i710:i510", r1_len=40, r2_insert=35, mismatches=3, seed=61005, **noisy),
+             ["--per-index-error"], 3000),
+            ("odd-full-header-umi", L("odd6", 9, "i78:um8:i58", r1_len=60, r2_insert=45, mismatches=1, seed=61006, **noisy),
+             ["--disable-illumina", "--mgi-full-header"], 3000),
+            ("odd-keep-mgi", L("odd7", 7, "i710:i510", r1_len=33, r2_insert=21, seed=61007, **noisy),
+             ["--disable-illumina", "--keep-barcode"], 3000),
+            ("odd-barcode-only-read", L("odd8", 11, "i78:i58", r1_len=90, r2_insert=0, seed=61008, **noisy), [], 3000),
+            ("odd-report0-validate", L("odd9", 5, "um4:i76:i56", r1_len=25, r2_insert=17, mismatches=2, seed=61009, **noisy),
+             ["--report-level", "0", "--validate"], 3000),
+            ("odd-long-reads", L("odd10", 14, "i710:i510", r1_len=301, r2_insert=250, seed=61010, **noisy), ["--comprehensive-scan"], 2000)]
 
 
 def main():
