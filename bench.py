@@ -166,6 +166,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    try:   # run (and first-touch the pinned buffers) on the cores next to this rank's GPU: on a two-socket box the
+           # end-to-end leg is bound by the host side of the copies
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        print(f"[bench] rank {rank}: {len(os.sched_getaffinity(0))} of {len(all_cpus)} cores (those next to GPU {local})", file=sys.stderr)
+    except Exception as e:   # not fatal: the default placement is what every run before this had
+        print(f"[bench] rank {rank}: default core placement ({type(e).__name__}: {e})", file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -337,6 +348,7 @@ def main():
     cpu = None
     if not a.no_cpu_baseline and a.gpus == 1:
         try:
+            os.sched_setaffinity(0, all_cpus)   # the reference gets every core of the box
             cpu = cpu_run(lane, a.cpu_sample_pairs, 2, 1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # report, never hide
