@@ -8,11 +8,14 @@
 //     the quality sums.  ONE THREAD PER (record, role): build_header() front / tail,
 //     qc_pair(), validate_pair() — every lane of a warp carries a different record.
 //   * bulk bytes: an output record is at most three byte ranges (header | "\n" sequence |
-//     "\n+\n" qualities), see plan_read().  A HALF-WARP moves one range with copy_piece():
-//     16-byte stores aligned on the destination, fully coalesced, fed by unaligned reads of
-//     S (aligned words + funnel shift), the < 16 bytes at either end one byte per lane.
-// The functions take the lane as an argument and use no warp intrinsic, so the CPU
-// emulation runs the very same code with the lanes looped.
+//     "\n+\n" qualities), see plan_read() / read_piece().  On the GPU quarter-warps move them
+//     (kernels.cuh: move_pair_lane / move_small_lane, PTX): 16-byte stores aligned on the
+//     destination, fully coalesced, fed by unaligned reads of S (aligned words + funnel shift),
+//     the < 16 bytes at either end byte by byte.  copy_piece() below states the same byte
+//     movement in plain C++ (lanes looped) for the CPU emulation, which therefore checks WHAT is
+//     moved WHERE (plans, pieces, headers, patch), not the PTX movers; those are checked by the
+//     GPU parity tests.
+// Everything else here takes no warp intrinsic, so the CPU emulation runs the very same code.
 //
 // What it restates (reference = /root/reference):
 //   write_illumina_header        src/sample_data.rs:569-654, call site src/lib.rs:1240-1293
@@ -62,8 +65,8 @@ MGK_HD uint32_t put_byte(uint32_t w, int i, uint32_t v) {  // byte i of the word
   return (w & ~(0xffu << sh)) | (v << sh);
 }
 
-// ---------------------------------------------------------------- one byte range, one half-warp
-// Lane l16 (0..15) of a half-warp writes its share of dst[0 .. n) = S[src .. src+n), with output
+// ---------------------------------------------------------------- one byte range (CPU emulation of the movers)
+// Lane l16 (0..15) of sixteen writes its share of dst[0 .. n) = S[src .. src+n), with output
 // byte `patch_at` (>= n: none) replaced by patch_val.  Lane u takes the 16-byte units u, u+16, ...
 // of the destination-aligned middle; lane l the l-th byte in front of it and the l-th after it.
 MGK_HD void copy_piece(uint8_t* dst, const uint8_t* S, uint32_t src, uint32_t n, int l16, uint32_t patch_at, uint32_t patch_val) {

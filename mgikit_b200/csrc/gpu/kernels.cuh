@@ -1199,9 +1199,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     const uint32_t table_s = desc_s + (k & 1u) * DESC_TABLE;
     const long long c4 = c2;
 
-    // ======== step 1: scalar roles; the bodies straight out of the staged input; the next tile's descriptors
+    // ======== scalar roles; then the bodies straight out of the staged input, the next tile's descriptors, the headers
     if (warp < EMIT_SWARPS) {
-      // ---- step 2a, one thread per (record, role)
+      // one thread per (record, role)
       const int role = warp / (EMIT_NMAX / 32);
       const uint32_t i = (uint32_t)tid % EMIT_NMAX;
       if (i < T.n) {

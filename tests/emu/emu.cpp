@@ -147,7 +147,7 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     G.h2 += b2; G.s2 += b2; G.p2 += b2; G.q2 += b2; G.e2 += b2;
     G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
     uint8_t* dst[3] = {nullptr, o1 + c->off1[(size_t)R.bin] + R.d1, o2 + c->off2[(size_t)R.bin] + R.d2};
-    // what k_emit does for one pair: header halves by scalar roles, byte ranges by half-warps (lanes looped)
+    // what k_emit does for one pair: header halves by scalar roles, byte ranges by copy_piece (lanes looped; the kernel's PTX movers do the same bytes)
     ReadPlan plan[3];
     plan[2] = plan_read(P, G, 2, R.mo.sample, R.mo.bar_t, R.pl.len2);
     plan[1] = plan_read(P, G, 1, R.mo.sample, R.mo.bar_t, P.paired ? R.pl.len1 : 0u);
@@ -170,7 +170,7 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
         }
       }
     }
-    for (int which = 2; which >= 1; --which) {   // half-warps: byte ranges
+    for (int which = 2; which >= 1; --which) {   // byte ranges
       const ReadPlan& r = plan[which];
       if (r.len == 0) continue;
       for (int k = 0; k < 2; ++k) {
