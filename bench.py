@@ -3,10 +3,13 @@
 bit-exact; HBM GB/s as a fraction of peak).
 
 A step = one pass of the whole hot path (record scan -> match -> bin scan -> scatter+QC)
-over one batch of synthetic config-2 read pairs (96 samples, dual 10 bp indexes, 150 bp
-pairs, mismatches=1).  `value` is measured with the batch already resident in HBM
-(CUDA events on the launching stream); `e2e` goes through the public C ABI with pinned
-HOST buffers, H2D and D2H copies inside the timed region.
+over one batch of synthetic read pairs: `--chunks-per-step` chunks of `--pairs` pairs.
+N = 1 runs BASELINE config 2 (96 samples, dual 10 bp indexes, 150 bp pairs, m=1), N > 1
+config 5 (384 samples; chunks sharded by rank, one NCCL all-reduce of the counter tables).
+`value` is measured with the batch already resident in HBM (CUDA events on the launching
+streams); `e2e` goes through the public C ABI with pinned HOST buffers, H2D and D2H copies
+inside the timed region, next to a copy-only leg over the same buffers (`copy_ceiling`);
+`e2e_files` is the drop-in CLI on .fq.gz files next to the reference binary on the same files.
 
   python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
   python bench.py --impl reference ...                     (the reference's CPU binary)
@@ -36,12 +39,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1 << 21, help="read pairs per step per GPU (1.5 GB of text: > 10x L2)")
-    ap.add_argument("--e2e-chunk-pairs", type=int, default=1 << 20, help="end to end, a step's batch goes through the C ABI in chunks of at most this many pairs")
+    ap.add_argument("--pairs", type=int, default=1 << 21, help="read pairs per chunk (1.5 GB of text: > 10x L2)")
+    ap.add_argument("--chunks-per-step", type=int, default=32,
+                    help="chunks per step and GPU: long enough steps that the device-timed span is >= 0.5 s")
+    ap.add_argument("--e2e-chunk-pairs", type=int, default=1 << 20, help="end to end, a chunk goes through the C ABI in pieces of at most this many pairs")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400000)
+    ap.add_argument("--file-pairs", type=int, default=10_000_000, help="read pairs of the .fq.gz lane of the file-level leg (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
+
+
+def workload(lane, gpus):
+    from mgikit_b200 import synth
+    which = {"cfg2": "configs[1]", "cfg5": "configs[4]"}[lane.name[:4]]
+    r1_rec, r2_rec = synth.record_bytes(lane)
+    return (f"BASELINE {which}: synthetic MGI paired-end lane, {lane.n_samples} samples, dual 10bp indexes ({lane.template}), "
+            f"150bp+150bp(+20bp barcode), mismatches={lane.mismatches}, Illumina-format output"
+            + ("" if gpus == 1 else f", sharded over {gpus} GPUs with an NCCL all-reduce of the report tables")), r1_rec, r2_rec
 
 
 # ------------------------------------------------------------------ clocks
@@ -130,18 +146,82 @@ def cpu_run(lane, n_pairs, steps, warmup):
         shutil.rmtree(d, ignore_errors=True)
 
 
+# ------------------------------------------------------------------ resident runs (any lane)
+def resident_run(hp, dev_args, n_chunks, flags):
+    """n_chunks submissions of the resident block, two in flight; returns (per-kernel ms rows, last result)."""
+    rows, res = [], None
+    for k in range(n_chunks):
+        hp.submit(k, dev_args[0], dev_args[1], flags)
+        if k >= 1:
+            res = hp.collect(device_out=True)
+            rows.append(hp.last_timings())
+            hp.release(k - 1)
+    res = hp.collect(device_out=True)
+    rows.append(hp.last_timings())
+    hp.release(n_chunks - 1)
+    return rows, res
+
+
+def serial_run(hp, dev_args, n_chunks, flags):
+    """One chunk in flight at a time: per-kernel CUDA-event times that no other launch overlaps."""
+    rows = []
+    for k in range(n_chunks):
+        hp.submit(k, dev_args[0], dev_args[1], flags)
+        hp.collect(device_out=True)
+        rows.append(hp.last_timings())
+        hp.release(k)
+    return rows
+
+
+def short_lane_line(lane, n, device, peak):
+    """other_configs: a short resident run of another BASELINE configuration (same CUDA-event method)."""
+    import numpy as np
+    import torch
+    from mgikit_b200 import synth
+    from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
+    from util import make_hotpath
+    r1, r2 = synth.make_block(lane, 0, n)
+    in_bytes = r2.size + (r1.size if r1 is not None else 0)
+    spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size if r1 is not None else 0, r2.size) + 4096, max_chunk_records=n + 64,
+                          n_slots=2, device=device)
+    hp = make_hotpath(load_gpu_library(), "mgk_", spec)
+    try:
+        d2 = torch.from_numpy(r2).cuda()
+        d1 = torch.from_numpy(r1).cuda() if r1 is not None and r1.size else None
+        dev_args = ((d2.data_ptr(), d2.numel()), (d1.data_ptr(), d1.numel()) if d1 is not None else None)
+        flags = MGK_IN_DEVICE | MGK_OUT_DEVICE
+        resident_run(hp, dev_args, 4, flags)
+        k_ms = np.array(serial_run(hp, dev_args, 6, flags)[1:])
+        hp.span_ms()
+        n_chunks = 24
+        _, res = resident_run(hp, dev_args, n_chunks, flags)
+        span = hp.span_ms()
+        out_bytes = res.out_r2_bytes + res.out_r1_bytes
+        emit_ms = float(k_ms[:, 3].mean())
+        achieved = (in_bytes + out_bytes) / (emit_ms * 1e-3) / 1e9
+        return {"lane": lane.name, "units_per_chunk": n, "unit": "read pairs/s" if lane.paired else "reads/s",
+                "value": n * n_chunks / (span * 1e-3), "bytes_per_unit": {"in": in_bytes / n, "out": out_bytes / n},
+                "kernel_ms": {"scan_newlines": float(k_ms[:, 0].mean()), "match_plan": float(k_ms[:, 1].mean()),
+                              "bin_scan": float(k_ms[:, 2].mean()), "emit_qc": emit_ms, "chunk": float(k_ms[:, 4].mean())},
+                "roofline": {"kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
+                "whole_path_frac": ((in_bytes + out_bytes) * n_chunks / (span * 1e-3) / 1e9) / peak}
+    finally:
+        hp.close()
+
+
 def main():
     a = parse()
     from mgikit_b200 import synth
-    lane = synth.CONFIG2
+    lane = synth.CONFIG2 if a.gpus == 1 else synth.CONFIG5
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    r1_rec, r2_rec = synth.record_bytes(lane)
-    config = {"workload": "BASELINE configs[1]: synthetic MGI paired-end lane, 96 samples, dual 10bp indexes (i710:i510), "
-                          "150bp+150bp(+20bp barcode), mismatches=1, Illumina-format output",
-              "pairs_per_step_per_gpu": a.pairs, "input_bytes_per_pair": r1_rec + r2_rec,
-              "l2_policy": f"each step streams {(r1_rec + r2_rec) * a.pairs >> 20} MiB in + about as much out per GPU (>> 126 MB L2); "
+    what, r1_rec, r2_rec = workload(lane, a.gpus)
+    cps = max(1, a.chunks_per_step)
+    step_pairs = a.pairs * cps
+    config = {"workload": what, "pairs_per_step_per_gpu": step_pairs, "chunks_per_step": cps, "pairs_per_chunk": a.pairs,
+              "input_bytes_per_pair": r1_rec + r2_rec,
+              "l2_policy": f"every chunk streams {(r1_rec + r2_rec) * a.pairs >> 20} MiB in + about as much out per GPU (>> 126 MB L2); "
                            "no explicit flush needed",
               "parallelism": f"{a.gpus} GPU(s), read chunks sharded by rank, one NCCL allreduce of the counter tables"}
 
@@ -160,7 +240,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
+    from mgikit_b200.capi import CLI_BIN, MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
     from util import make_hotpath
 
     if not torch.cuda.is_available():
@@ -185,11 +265,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     n = a.pairs
     r1, r2 = synth.make_block(lane, rank, n)          # every rank its own block of the lane (weak scaling)
     in_bytes = r1.size + r2.size
     spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size, r2.size) + 4096, max_chunk_records=n + 64, n_slots=2, device=local)
-    hp = make_hotpath(load_gpu_library(), "mgk_", spec)
+    lib = load_gpu_library()
+    hp = make_hotpath(lib, "mgk_", spec)
     if world > 1:   # NCCL communicator of the library itself, id shared through torch.distributed
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -199,40 +286,32 @@ def main():
 
     d2, d1 = torch.from_numpy(r2).cuda(), torch.from_numpy(r1).cuda()
     dev_args = ((d2.data_ptr(), d2.numel()), (d1.data_ptr(), d1.numel()))
+    RES = MGK_IN_DEVICE | MGK_OUT_DEVICE
 
-    def run_resident(steps):
-        """K steps, two chunks in flight, inputs and outputs stay in HBM."""
-        per_kernel = []
-        out_bytes = 0
-        for k in range(steps):
-            hp.submit(k, dev_args[0], dev_args[1], MGK_IN_DEVICE | MGK_OUT_DEVICE)
-            if k >= 1:
-                res = hp.collect(device_out=True)
-                per_kernel.append(hp.last_timings())
-                out_bytes = res.out_r2_bytes + res.out_r1_bytes
-                hp.release(k - 1)
-        res = hp.collect(device_out=True)
-        per_kernel.append(hp.last_timings())
-        out_bytes = res.out_r2_bytes + res.out_r1_bytes
-        hp.release(steps - 1)
-        if world > 1:
-            hp.nccl_allreduce_counters()
-        return per_kernel, out_bytes, res
-
-    def run_serial(steps):
-        """One chunk in flight at a time: per-kernel CUDA-event times that no other launch overlaps."""
-        per_kernel = []
-        for k in range(steps):
-            hp.submit(k, dev_args[0], dev_args[1], MGK_IN_DEVICE | MGK_OUT_DEVICE)
-            hp.collect(device_out=True)
-            per_kernel.append(hp.last_timings())
-            hp.release(k)
-        return per_kernel
+    def merged_tables_check(expected_reads):
+        """The one collective of the path: every rank's share of the two report tables, summed by the library's NCCL
+        all-reduce, must equal the element-wise sum of the shares as gathered independently with torch.distributed
+        (ReportManager::update, src/report_manager.rs:377-435), on every rank."""
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hp.nccl_allreduce_counters()
+        ms = (time.perf_counter() - t0) * 1e3
+        stats, mism = hp.counters()
+        rs, rm = hp.reduced_counters()
+        mine = torch.from_numpy(np.concatenate([stats.ravel(), mism.ravel()]).astype(np.int64)).cuda()
+        shares = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(shares, mine)
+        want = torch.stack(shares).sum(dim=0).cpu().numpy().astype(np.uint64)
+        got = np.concatenate([rs.ravel(), rm.ravel()])
+        assert np.array_equal(got, want), f"rank {rank}: all-reduced report tables differ from the sum of the per-rank tables"
+        assert int(rm[:, 1:].sum()) == expected_reads, "merged counter tables do not add up to the reads processed"
+        assert int(mism[:, 1:].sum()) == expected_reads // world, "this rank's counter tables do not add up to its reads"
+        return ms
 
     # ---- resident (kernel path) timing
     hp.reset_counters()
-    run_resident(max(a.warmup, 3))
-    serial_kernel = run_serial(max(3, min(a.steps, 10)))[1:]
+    resident_run(hp, dev_args, max(a.warmup, 3) * min(cps, 4), RES)
+    serial_kernel = serial_run(hp, dev_args, max(4, min(a.steps, 10)), RES)[1:]
     hp.span_ms()
     hp.span_ms()
     hp.reset_counters()
@@ -242,79 +321,117 @@ def main():
         sampler.start()
     launches0 = hp.launch_count()
     t0 = time.perf_counter()
-    per_kernel, out_bytes, last = run_resident(a.steps)
+    per_kernel, last = resident_run(hp, dev_args, a.steps * cps, RES)
     span = hp.span_ms()
     barrier()
     wall = time.perf_counter() - t0
     launches = hp.launch_count() - launches0
-    stats, mism = hp.counters()
-    total_expected = n * a.steps * (world if world > 1 else 1)
-    assert int(mism[:, 1:].sum()) == total_expected, "counter tables do not add up to the reads processed"
+    out_bytes = last.out_r2_bytes + last.out_r1_bytes
     assert last.n_records == n
-    t = torch.tensor([span], dtype=torch.float64, device="cuda")
+    allreduce_ms = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    span_max = float(t.item())
-    value = n * a.steps * world / (span_max * 1e-3)
+        allreduce_ms = merged_tables_check(n * a.steps * cps * world)
+    else:
+        assert int(hp.counters()[1][:, 1:].sum()) == n * a.steps * cps, "counter tables do not add up to the reads processed"
+    span_max = max_over_ranks(span)
+    value = n * a.steps * cps * world / (span_max * 1e-3)
 
-    # ---- end to end through the C ABI: pinned host in, pinned host out
+    # ---- end to end through the C ABI: pinned host in, pinned host out; and the copies alone over the same buffers
     e2e = None
     if not a.no_e2e:
         h2 = torch.from_numpy(r2).pin_memory()
         h1 = torch.from_numpy(r1).pin_memory()
-        host_args = ((h2.data_ptr(), h2.numel()), (h1.data_ptr(), h1.numel()))
-
-        # a step's batch goes through the ABI in chunks of at most --e2e-chunk-pairs (records have a fixed size in the
-        # synthetic lane, so the cuts are at record boundaries): (pointer, bytes) of both reads per chunk
+        # a chunk goes through the ABI in pieces of at most --e2e-chunk-pairs (records have a fixed size in the
+        # synthetic lane, so the cuts are at record boundaries): (pointer, bytes) of both reads per piece
         assert r2.size == n * r2_rec and r1.size == n * r1_rec
         n_sub = max(1, -(-n // a.e2e_chunk_pairs))
         cuts = [n * j // n_sub for j in range(n_sub + 1)]
         sub_args = [((h2.data_ptr() + cuts[j] * r2_rec, (cuts[j + 1] - cuts[j]) * r2_rec),
                      (h1.data_ptr() + cuts[j] * r1_rec, (cuts[j + 1] - cuts[j]) * r1_rec)) for j in range(n_sub)]
+        per_step_pieces = cps * n_sub
 
         def run_e2e(steps):
             d2h = 0
-            per_step = 0
-            for k in range(steps * n_sub):
+            pieces = steps * per_step_pieces
+            for k in range(pieces):
                 hp.submit(k, sub_args[k % n_sub][0], sub_args[k % n_sub][1], 0)
                 if k >= 1:
                     res = hp.collect(device_out=True)      # results are in pinned host memory; no python copy
-                    per_step += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
+                    d2h += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
                     hp.release(k - 1)
-                    if k % n_sub == 0:
-                        d2h, per_step = per_step, 0
             res = hp.collect(device_out=True)
-            per_step += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
-            d2h = per_step
-            hp.release(steps * n_sub - 1)
+            d2h += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
+            hp.release(pieces - 1)
             if world > 1:
                 hp.nccl_allreduce_counters()
-            return d2h
-        run_e2e(max(2, min(a.warmup, 3)))
+            return d2h // steps
+        run_e2e(1)
         barrier()
         t0 = time.perf_counter()
         d2h = run_e2e(a.steps)
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * a.steps * world / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(in_bytes),
-               "d2h_bytes_per_step": int(d2h), "timing": "host clock between barrier+synchronize, max over ranks; pinned buffers, "
-                                                          f"{n_sub} chunk(s) per step, 2 chunks in flight"}
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": n * cps * a.steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes * cps),
+               "d2h_bytes_per_step": int(d2h), "seconds": dt,
+               "timing": "host clock between barrier+synchronize, max over ranks; pinned buffers, "
+                         f"{per_step_pieces} pieces of {cuts[1]} pairs per step, 2 in flight"}
+
+        # copy-only leg: the same pinned input buffers and piece sizes, one cudaMemcpyAsync per piece and direction
+        # (H2D of the text on one stream, D2H of as many bytes as the path returns on another), no kernels: what the
+        # box's host<->device DMA gives this rank while every other rank does the same
+        piece_out = (d2h // per_step_pieces + 4095) & ~4095
+        dev_in2 = torch.empty(max(x[0][1] for x in sub_args), dtype=torch.uint8, device="cuda")
+        dev_in1 = torch.empty(max(x[1][1] for x in sub_args), dtype=torch.uint8, device="cuda")
+        dev_out = torch.empty(piece_out, dtype=torch.uint8, device="cuda")
+        host_out = [torch.empty(piece_out, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def run_copies(steps):
+            for k in range(steps * per_step_pieces):
+                j = k % n_sub
+                with torch.cuda.stream(s_in):
+                    dev_in2[:sub_args[j][0][1]].copy_(h2[cuts[j] * r2_rec:cuts[j + 1] * r2_rec], non_blocking=True)
+                    dev_in1[:sub_args[j][1][1]].copy_(h1[cuts[j] * r1_rec:cuts[j + 1] * r1_rec], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    host_out[k & 1].copy_(dev_out, non_blocking=True)
+            torch.cuda.synchronize()
+        copy_steps = max(1, min(a.steps, 4))
+        run_copies(1)
+        barrier()
+        t0 = time.perf_counter()
+        run_copies(copy_steps)
+        barrier()
+        dtc = max_over_ranks(time.perf_counter() - t0)
+        ceiling = n * cps * copy_steps * world / dtc
+        e2e["copy_ceiling"] = {"value": ceiling, "unit": UNIT, "h2d_gbs": in_bytes * cps * copy_steps * world / dtc / 1e9,
+                               "d2h_gbs": piece_out * per_step_pieces * copy_steps * world / dtc / 1e9, "steps": copy_steps,
+                               "what": "cudaMemcpyAsync only (same pinned buffers, same piece sizes, both directions at once, all ranks at once)"}
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / ceiling
+        del dev_in2, dev_in1, dev_out, host_out, h2, h1
 
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (resident and end to end)
+
+    # ---- N = 2: the product CLI with --gpus 2 (one process, two contexts, mgk_allreduce_counters) against the
+    # reference's goldens, executed by rank 0 while rank 1 waits (tests/test_multi_gpu.py runs the same check)
+    multi_cli = None
+    if world == 2:
+        if rank == 0:
+            import multigpu_check
+            try:
+                multi_cli = {"ok": True, "files_compared": multigpu_check.cli_matches_goldens(CLI_BIN, 2)}
+            except AssertionError as e:
+                multi_cli = {"ok": False, "error": str(e)[:400]}
+        barrier()
+
     def teardown():
-        """Every rank leaves the same way: NCCL communicators (the library's and torch's) are destroyed collectively;
-        a watchdog ends the process if a peer is already gone."""
-        import threading
-        threading.Timer(30.0, lambda: os._exit(0)).start()
+        """Every rank leaves the same way and through normal interpreter shutdown: the library's communicator goes with
+        its context, torch's process group is destroyed collectively."""
         if world > 1:
             dist.barrier()
         hp.close()
         if world > 1:
             dist.destroy_process_group()
         sys.stdout.flush()
-        os._exit(0)
 
     if rank != 0:
         teardown()
@@ -329,22 +446,43 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    k_ms = np.array(serial_kernel)                   # [steps][scan, match, binscan, emit, whole], one chunk in flight
+    k_ms = np.array(serial_kernel)                   # [chunks][scan, match, binscan, emit, whole], one chunk in flight
     algo_bytes = in_bytes + out_bytes                # every input byte read once, every output byte written once
     scatter_ms = float(k_ms[:, 3].mean())
     achieved = algo_bytes / (scatter_ms * 1e-3) / 1e9
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of k_emit from the committed ncu capture, scaled per pair
+    traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of k_emit from a committed ncu capture
     try:
         with open(os.path.join(ROOT, "profiles", "k_emit_traffic.json")) as f:
             tr = json.load(f)
         traffic = int(tr["dram_bytes_per_launch"] * (n / tr["pairs_per_launch"]))
+        traffic_src = tr.get("source", "profiles/k_emit_traffic.json") + " (ncu capture of that build, scaled to this launch; not measured in this run)"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_emit", "timing": "CUDA events on the launching stream, one chunk in flight", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+    roofline = {"bound": "hbm", "kernel": "k_emit", "timing": "CUDA events on the launching stream, one chunk in flight", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
                 "kernel_ms": {"scan_newlines": float(k_ms[:, 0].mean()), "match_plan": float(k_ms[:, 1].mean()),
                               "bin_scan": float(k_ms[:, 2].mean()), "emit_qc": scatter_ms, "chunk": float(k_ms[:, 4].mean())},
-                "whole_path_frac": (algo_bytes * a.steps / (span_max * 1e-3) / 1e9) / peak}
+                "whole_path_frac": (algo_bytes * a.steps * cps / (span_max * 1e-3) / 1e9) / peak}
+
+    other = None
+    if a.gpus == 1 and not a.no_other_configs:   # the BASELINE configurations that are not the headline, tracked round over round
+        other = {}
+        for key, ln in (("cfg3", synth.CONFIG3), ("cfg4", synth.CONFIG4), ("cfg5", synth.CONFIG5)):
+            try:
+                other[key] = short_lane_line(ln, 1 << 20, local, peak)
+            except Exception as e:
+                other[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    files = None
+    if a.gpus == 1 and a.file_pairs > 0:
+        try:
+            os.sched_setaffinity(0, all_cpus)
+            import file_bench
+            files = file_bench.run(lane, a.file_pairs, CLI_BIN, reference_binary()[0])
+        except Exception as e:
+            files = {"error": f"{type(e).__name__}: {e}"[:400]}
+
     cpu = None
     if not a.no_cpu_baseline and a.gpus == 1:
         try:
@@ -356,9 +494,20 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": span_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "wall_s_resident": wall}
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_resident": wall, "device_span_s": span_max * 1e-3}
+    if allreduce_ms is not None:
+        line["allreduce"] = {"ms": allreduce_ms, "bytes": int(hp.total * (10 + hp.mism_w) * 8),
+                             "checked": "reduced tables == element-wise sum of the per-rank tables, on every rank"}
+    if other is not None:
+        line["other_configs"] = other
+    if files is not None:
+        line["e2e_files"] = files
+    if multi_cli is not None:
+        line["cli_gpus2_parity"] = multi_cli
     print(json.dumps(line), flush=True)
     teardown()
+    if multi_cli is not None and not multi_cli["ok"]:
+        raise SystemExit("the product CLI with --gpus 2 does not reproduce the goldens: " + multi_cli["error"])
 
 
 if __name__ == "__main__":

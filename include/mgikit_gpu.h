@@ -97,7 +97,14 @@ typedef struct {
 } mgk_config;
 
 /* mgk_submit flags */
-#define MGK_IN_DEVICE   1u   /* r2/r1 are device pointers (already resident in HBM) */
+#define MGK_IN_DEVICE   1u   /* r2/r1 are device pointers (already resident in HBM): 16-byte aligned, and
+                                the caller's allocation must stay READABLE for MGK_DEVICE_INPUT_SLACK
+                                bytes past r*_len -- the kernels fetch whole 16-byte units (bulk copies
+                                round a tail up, index probes load aligned words); the content of the
+                                slack is never used.  Checked against the allocation's range where the
+                                driver reports it (MGK_ERR_ARG).  Host buffers need no slack: the
+                                library's own device copies are padded.                              */
+#define MGK_DEVICE_INPUT_SLACK 32
 #define MGK_OUT_DEVICE  2u   /* leave out_r2/out_r1 in HBM (result pointers are device pointers) */
 
 typedef struct mgk_ctx mgk_ctx;
@@ -164,6 +171,11 @@ int mgk_reset_counters(mgk_ctx* ctx);
  * (src/report_manager.rs:377-416) across ranks, as one NCCL sum over NVLink.
  * (a) one process, n contexts on n devices: */
 int mgk_allreduce_counters(mgk_ctx* const* ctxs, int n);
+/* Both variants are out of place: the running tables (mgk_counters) keep this
+ * context's own share, so more chunks may follow and the merge may be repeated;
+ * the sum over all ranks is read here (same layout; MGK_ERR_STATE before the
+ * first merge).                                                               */
+int mgk_reduced_counters(mgk_ctx* ctx, uint64_t* stats, uint64_t* mism);
 /* (b) one process per GPU (torchrun): rank 0 makes the id, every rank joins. */
 #define MGK_NCCL_ID_BYTES 128
 int mgk_nccl_unique_id(uint8_t id[MGK_NCCL_ID_BYTES]);

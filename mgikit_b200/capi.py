@@ -54,7 +54,7 @@ class MgkResult(C.Structure):
 
 # every entry point include/mgikit_gpu.h declares
 ABI_SYMBOLS = ["create", "destroy", "last_error", "submit", "collect", "release", "counters", "reset_counters",
-               "allreduce_counters", "nccl_unique_id", "nccl_join", "nccl_allreduce_counters", "host_alloc",
+               "allreduce_counters", "reduced_counters", "nccl_unique_id", "nccl_join", "nccl_allreduce_counters", "host_alloc",
                "host_free", "last_timings", "span_ms", "launch_count", "scan_newlines", "match_barcodes"]
 
 
@@ -167,6 +167,15 @@ class HotPath:
         stats = np.zeros((self.total, MGK_N_STATS), dtype=np.uint64)
         mism = np.zeros((self.total, self.mism_w), dtype=np.uint64)
         self._check(self._f("counters")(self.ctx, stats.ctypes.data, mism.ctypes.data))
+        return stats, mism
+
+    def reduced_counters(self):
+        """Sum over all ranks as left by the last counter all-reduce (the running tables stay local)."""
+        stats = np.zeros((self.total, MGK_N_STATS), dtype=np.uint64)
+        mism = np.zeros((self.total, self.mism_w), dtype=np.uint64)
+        fn = self._f("reduced_counters")
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(fn(self.ctx, stats.ctypes.data, mism.ctypes.data))
         return stats, mism
 
     def reset_counters(self):

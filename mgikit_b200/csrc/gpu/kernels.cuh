@@ -659,6 +659,9 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
   uint32_t* mism_acc = mism_smem ? bin_acc + B2 : nullptr;
   if (mism_acc)
     for (int i = threadIdx.x; i < total * P.mism_w; i += blockDim.x) mism_acc[i] = 0;
+  // a scan range that overflowed its staging run leaves holes in the newline table: nothing below may build
+  // addresses from it (the error was raised by an earlier launch on this stream, so the read is uniform)
+  if (c.status->error & ERR_NL_CAPACITY) return;
   const uint32_t raw2 = c.counts[0] >> 2, raw1 = P.paired ? c.counts[1] >> 2 : raw2;
   const uint32_t n_rec = device_n_records(c, P);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -781,6 +784,7 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
 // ------------------------------------------------------------------ K3
 // (a) bytes per (group of 64 tiles, bin)
 __global__ void k_scan_groups(const Params* __restrict__ Pg, ChunkDev c) {
+  if (c.status->error & ERR_NL_CAPACITY) return;   // no plan was made (k_match_plan)
   const int B2 = 2 * Pg->total;
   const uint32_t n_rec = device_n_records(c, *Pg);
   const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
@@ -797,6 +801,7 @@ __global__ void k_scan_groups(const Params* __restrict__ Pg, ChunkDev c) {
 
 // (b) one CTA: exclusive scan over groups per bin, then over bins -> segment table
 __global__ void __launch_bounds__(1024) k_scan_bins(const Params* __restrict__ Pg, ChunkDev c) {
+  if (c.status->error & ERR_NL_CAPACITY) return;
   const int total = Pg->total, B2 = 2 * total;
   const uint32_t n_rec = device_n_records(c, *Pg);
   const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
@@ -840,6 +845,7 @@ __global__ void __launch_bounds__(1024) k_scan_bins(const Params* __restrict__ P
 
 // (c) absolute destination of every (tile, bin) run
 __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
+  if (c.status->error & ERR_NL_CAPACITY) return;   // no plan was made (k_match_plan)
   const int total = Pg->total, B2 = 2 * total;
   const uint32_t n_rec = device_n_records(c, *Pg);
   const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;

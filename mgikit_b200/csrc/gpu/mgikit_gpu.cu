@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -46,6 +47,7 @@ struct Slot {
   std::vector<uint64_t> off2, len2v, off1, len1v;
   ChunkDev cd{};
   float ms[5] = {0, 0, 0, 0, 0};
+  bool in_span = false;   // ev[5] was recorded since the span was opened
 };
 
 }  // namespace
@@ -59,6 +61,8 @@ struct mgk_ctx {
   uint64_t* d_hkeys = nullptr;
   uint8_t* d_consts = nullptr;
   unsigned long long *d_stats = nullptr, *d_mism = nullptr, *d_prof = nullptr;
+  unsigned long long *d_red_stats = nullptr, *d_red_mism = nullptr;   // result of the last counter all-reduce
+  bool reduced = false;
   Status* h_status_init = nullptr;
   int total = 0, mism_w = 0;
   uint64_t cap_bytes = 0, cap_records = 0, out_cap = 0;
@@ -73,7 +77,7 @@ struct mgk_ctx {
   uint64_t launches = 0;
   float last_ms[5] = {0, 0, 0, 0, 0};
   ncclComm_t comm = nullptr;
-  cudaEvent_t span_begin = nullptr, span_end = nullptr;
+  cudaEvent_t span_begin = nullptr;
   bool span_open = false;
   char err[512] = "";
 };
@@ -125,9 +129,8 @@ struct NcclApi {
 
 NcclApi* nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
       api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (api.lib) break;
@@ -148,8 +151,28 @@ NcclApi* nccl_api() {
         api.lib = nullptr;
       }
     }
-  }
+  });
   return api.lib ? &api : nullptr;
+}
+
+// MGK_IN_DEVICE: is [p, p + len + slack) inside the allocation p belongs to?  true when the driver cannot tell.
+bool device_range_ok(const uint8_t* p, uint64_t len) {
+  if (!p || !len) return true;
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<range_fn>(f);
+    cudaGetLastError();
+  });
+  if (!fn) return true;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return true;
+  return (unsigned long long)(uintptr_t)p + len + MGK_DEVICE_INPUT_SLACK <= base + size;
 }
 
 }  // namespace
@@ -178,9 +201,9 @@ extern "C" void mgk_destroy(mgk_ctx* ctx) {
   cudaFree(ctx->d_params); cudaFree(ctx->d_codes); cudaFree(ctx->d_pairs); cudaFree(ctx->d_xlat);
   cudaFree(ctx->d_hkeys); cudaFree(ctx->d_hids);
   cudaFree(ctx->d_writing); cudaFree(ctx->d_consts); cudaFree(ctx->d_stats); cudaFree(ctx->d_mism);
+  cudaFree(ctx->d_red_stats); cudaFree(ctx->d_red_mism);
   cudaFreeHost(ctx->h_status_init);
   if (ctx->span_begin) cudaEventDestroy(ctx->span_begin);
-  if (ctx->span_end) cudaEventDestroy(ctx->span_end);
   if (ctx->comm) {
     NcclApi* n = nccl_api();
     if (n && n->CommDestroy) n->CommDestroy(ctx->comm);
@@ -254,6 +277,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   CUC(dalloc(&ctx->d_consts, consts.size()));
   CUC(dalloc(&ctx->d_stats, (size_t)P.total * MGK_N_STATS));
   CUC(dalloc(&ctx->d_mism, (size_t)P.total * P.mism_w));
+  CUC(dalloc(&ctx->d_red_stats, (size_t)P.total * MGK_N_STATS));
+  CUC(dalloc(&ctx->d_red_mism, (size_t)P.total * P.mism_w));
   CUC(dalloc(&ctx->d_params, 1));
   CUC(cudaMemcpy(ctx->d_codes, codes.data(), codes.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   CUC(cudaMemcpy(ctx->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -339,7 +364,6 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     CUC(cudaMemset(ctx->d_prof, 0, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 6 * 8));
   }
   CUC(cudaEventCreate(&ctx->span_begin));
-  CUC(cudaEventCreate(&ctx->span_end));
   CUC(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status_init), sizeof(Status), cudaHostAllocDefault));
   memset(ctx->h_status_init, 0, sizeof(Status));
   ctx->h_status_init->fmt_record = ~0ull;
@@ -412,8 +436,13 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   if (r2_len > ctx->cap_bytes || r1_len > ctx->cap_bytes)
     return fail(ctx, MGK_ERR_CAPACITY, "mgk_submit: chunk of %llu/%llu bytes exceeds max_chunk_bytes %llu", (unsigned long long)r2_len,
                 (unsigned long long)r1_len, (unsigned long long)ctx->cap_bytes);
-  if ((flags & MGK_IN_DEVICE) && ((((uintptr_t)r2) | ((uintptr_t)r1)) & 15u))
-    return fail(ctx, MGK_ERR_ARG, "mgk_submit: device input pointers must be 16-byte aligned");
+  if (flags & MGK_IN_DEVICE) {
+    if ((((uintptr_t)r2) | ((uintptr_t)r1)) & 15u) return fail(ctx, MGK_ERR_ARG, "mgk_submit: device input pointers must be 16-byte aligned");
+    // the kernels fetch whole 16-byte units (bulk copies, word loads): the caller's allocation must stay readable
+    // for MGK_DEVICE_INPUT_SLACK bytes past the text (include/mgikit_gpu.h); checked where the driver can tell
+    if (!device_range_ok(r2, r2_len) || !device_range_ok(r1, r1_len))
+      return fail(ctx, MGK_ERR_ARG, "mgk_submit: a device input buffer ends less than %d readable bytes after its text", MGK_DEVICE_INPUT_SLACK);
+  }
   int si = -1;
   for (size_t i = 0; i < ctx->slots.size(); ++i)
     if (ctx->slots[i].state == 0) {
@@ -470,7 +499,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   k_emit<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_emit), EMIT_THREADS, ctx->lay.total_bytes, st>>>(ctx->d_params, c, ctx->lay);
   ctx->launches += 5;
   CU(cudaEventRecord(s.ev[5], st));
-  CU(cudaEventRecord(ctx->span_end, st));
+  s.in_span = true;
   CU(cudaMemcpyAsync(s.h_status, s.status, sizeof(Status), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(s.h_seg, s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(s.ev_status, st));
@@ -497,7 +526,12 @@ extern "C" int mgk_collect(mgk_ctx* ctx, mgk_result* res) {
   if (hs.error & ERR_PANIC)
     return fail(ctx, MGK_ERR_FORMAT, "chunk %llu: a read hits a sample-sheet combination on which the reference panics (stale template dictionary)",
                 (unsigned long long)s.seq);
-  if (hs.error & (ERR_NL_CAPACITY | ERR_REC_CAPACITY))
+  if (hs.error & ERR_NL_CAPACITY)
+    return fail(ctx, MGK_ERR_CAPACITY,
+                "chunk %llu: more line ends than the record tables hold (over max_chunk_records = %llu, or one 1/%u-th of the chunk carries "
+                "more than four times its share of them)",
+                (unsigned long long)s.seq, (unsigned long long)ctx->cap_records, ctx->scan_grid * (uint32_t)SCAN_WARPS);
+  if (hs.error & ERR_REC_CAPACITY)
     return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu holds more records than max_chunk_records = %llu", (unsigned long long)s.seq,
                 (unsigned long long)ctx->cap_records);
   if (hs.error & ERR_OUT_CAPACITY) return fail(ctx, MGK_ERR_CAPACITY, "chunk %llu: output does not fit the output buffer", (unsigned long long)s.seq);
@@ -569,6 +603,7 @@ extern "C" int mgk_reset_counters(mgk_ctx* ctx) {
   if (!ctx) return MGK_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
   CU(cudaDeviceSynchronize());
+  ctx->reduced = false;
   CU(cudaMemset(ctx->d_stats, 0, (size_t)ctx->total * MGK_N_STATS * 8));
   CU(cudaMemset(ctx->d_mism, 0, (size_t)ctx->total * ctx->mism_w * 8));
   return MGK_OK;
@@ -580,40 +615,70 @@ extern "C" int mgk_reset_counters(mgk_ctx* ctx) {
     if (r_ != ncclSuccess) return fail(ctx, MGK_ERR_NCCL, "%s: %s", #call, n->GetErrorString ? n->GetErrorString(r_) : "nccl error"); \
   } while (0)
 
+// The merge is out of place: the running tables of every context stay what they were (so more chunks can follow and
+// the merge can be repeated), the sum over the ranks lands in the context's `reduced` tables (mgk_reduced_counters).
 extern "C" int mgk_allreduce_counters(mgk_ctx* const* ctxs, int n_ctx) {
   if (!ctxs || n_ctx < 1 || !ctxs[0]) return MGK_ERR_ARG;
   mgk_ctx* ctx = ctxs[0];
-  if (n_ctx == 1) return MGK_OK;
+  const size_t ns = (size_t)ctx->total * MGK_N_STATS, nm = (size_t)ctx->total * ctx->mism_w;
+  for (int i = 0; i < n_ctx; ++i)
+    if (!ctxs[i] || ctxs[i]->total != ctx->total || ctxs[i]->mism_w != ctx->mism_w) return fail(ctx, MGK_ERR_ARG, "contexts describe different runs");
+  if (n_ctx == 1) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(ctx->d_red_stats, ctx->d_stats, ns * 8, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(ctx->d_red_mism, ctx->d_mism, nm * 8, cudaMemcpyDeviceToDevice));
+    ctx->reduced = true;
+    return MGK_OK;
+  }
   NcclApi* n = nccl_api();
   if (!n) return fail(ctx, MGK_ERR_NCCL, "libnccl.so.2 can not be loaded");
   std::vector<int> devs((size_t)n_ctx);
-  for (int i = 0; i < n_ctx; ++i) {
-    if (!ctxs[i] || ctxs[i]->total != ctx->total || ctxs[i]->mism_w != ctx->mism_w) return fail(ctx, MGK_ERR_ARG, "contexts describe different runs");
-    devs[(size_t)i] = ctxs[i]->device;
-  }
-  std::vector<ncclComm_t> comms((size_t)n_ctx);
+  for (int i = 0; i < n_ctx; ++i) devs[(size_t)i] = ctxs[i]->device;
+  std::vector<ncclComm_t> comms((size_t)n_ctx, nullptr);
   NC(n->CommInitAll(comms.data(), n_ctx, devs.data()));
+  auto drop_comms = [&] {
+    for (int i = 0; i < n_ctx; ++i)
+      if (comms[(size_t)i] && n->CommDestroy) {
+        cudaSetDevice(ctxs[i]->device);
+        n->CommDestroy(comms[(size_t)i]);
+      }
+  };
   for (int i = 0; i < n_ctx; ++i) {
     cudaSetDevice(ctxs[i]->device);
     cudaDeviceSynchronize();
   }
-  NC(n->GroupStart());
-  for (int i = 0; i < n_ctx; ++i) {
-    n->AllReduce(ctxs[i]->d_stats, ctxs[i]->d_stats, (size_t)ctx->total * MGK_N_STATS, ncclUint64, ncclSum, comms[(size_t)i], 0);
-    n->AllReduce(ctxs[i]->d_mism, ctxs[i]->d_mism, (size_t)ctx->total * ctx->mism_w, ncclUint64, ncclSum, comms[(size_t)i], 0);
+  ncclResult_t bad = ncclSuccess;
+  ncclResult_t r = n->GroupStart();
+  if (r != ncclSuccess) bad = r;
+  for (int i = 0; i < n_ctx && bad == ncclSuccess; ++i) {
+    r = n->AllReduce(ctxs[i]->d_stats, ctxs[i]->d_red_stats, ns, ncclUint64, ncclSum, comms[(size_t)i], 0);
+    if (r != ncclSuccess) bad = r;
+    r = n->AllReduce(ctxs[i]->d_mism, ctxs[i]->d_red_mism, nm, ncclUint64, ncclSum, comms[(size_t)i], 0);
+    if (r != ncclSuccess) bad = r;
   }
-  NC(n->GroupEnd());
+  r = n->GroupEnd();
+  if (r != ncclSuccess && bad == ncclSuccess) bad = r;
+  cudaError_t ce = cudaSuccess;
   for (int i = 0; i < n_ctx; ++i) {
     cudaSetDevice(ctxs[i]->device);
-    cudaDeviceSynchronize();
-    if (n->CommDestroy) n->CommDestroy(comms[(size_t)i]);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) ce = e;
   }
-  // every context now holds the run total; keep only rank 0's copy additive
-  for (int i = 1; i < n_ctx; ++i) {
-    cudaSetDevice(ctxs[i]->device);
-    cudaMemset(ctxs[i]->d_stats, 0, (size_t)ctx->total * MGK_N_STATS * 8);
-    cudaMemset(ctxs[i]->d_mism, 0, (size_t)ctx->total * ctx->mism_w * 8);
-  }
+  drop_comms();
+  if (bad != ncclSuccess) return fail(ctx, MGK_ERR_NCCL, "counter all-reduce: %s", n->GetErrorString ? n->GetErrorString(bad) : "nccl error");
+  if (ce != cudaSuccess) return fail(ctx, MGK_ERR_CUDA, "counter all-reduce: %s", cudaGetErrorString(ce));
+  for (int i = 0; i < n_ctx; ++i) ctxs[i]->reduced = true;
+  return MGK_OK;
+}
+
+extern "C" int mgk_reduced_counters(mgk_ctx* ctx, uint64_t* stats, uint64_t* mism) {
+  if (!ctx) return MGK_ERR_ARG;
+  if (!ctx->reduced) return fail(ctx, MGK_ERR_STATE, "mgk_reduced_counters: no counter all-reduce has run on this context");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  if (stats) CU(cudaMemcpy(stats, ctx->d_red_stats, (size_t)ctx->total * MGK_N_STATS * 8, cudaMemcpyDeviceToHost));
+  if (mism) CU(cudaMemcpy(mism, ctx->d_red_mism, (size_t)ctx->total * ctx->mism_w * 8, cudaMemcpyDeviceToHost));
   return MGK_OK;
 }
 
@@ -647,10 +712,13 @@ extern "C" int mgk_nccl_allreduce_counters(mgk_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   CU(cudaDeviceSynchronize());
   NC(n->GroupStart());
-  n->AllReduce(ctx->d_stats, ctx->d_stats, (size_t)ctx->total * MGK_N_STATS, ncclUint64, ncclSum, ctx->comm, 0);
-  n->AllReduce(ctx->d_mism, ctx->d_mism, (size_t)ctx->total * ctx->mism_w, ncclUint64, ncclSum, ctx->comm, 0);
+  const ncclResult_t r1 = n->AllReduce(ctx->d_stats, ctx->d_red_stats, (size_t)ctx->total * MGK_N_STATS, ncclUint64, ncclSum, ctx->comm, 0);
+  const ncclResult_t r2 = n->AllReduce(ctx->d_mism, ctx->d_red_mism, (size_t)ctx->total * ctx->mism_w, ncclUint64, ncclSum, ctx->comm, 0);
   NC(n->GroupEnd());
+  NC(r1);
+  NC(r2);
   CU(cudaDeviceSynchronize());
+  ctx->reduced = true;
   return MGK_OK;
 }
 
@@ -674,8 +742,16 @@ extern "C" int mgk_span_ms(mgk_ctx* ctx, float* ms) {
   *ms = 0.f;
   if (!ctx->span_open) return MGK_OK;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaEventSynchronize(ctx->span_end));
-  CU(cudaEventElapsedTime(ms, ctx->span_begin, ctx->span_end));
+  // chunks in flight run on independent streams and may finish out of order: the span ends with the LAST of the
+  // end-of-kernels events recorded since it was opened
+  for (auto& s : ctx->slots) {
+    if (!s.in_span) continue;
+    float t = 0.f;
+    CU(cudaEventSynchronize(s.ev[5]));
+    CU(cudaEventElapsedTime(&t, ctx->span_begin, s.ev[5]));
+    if (t > *ms) *ms = t;
+    s.in_span = false;
+  }
   ctx->span_open = false;
   return MGK_OK;
 }

@@ -79,6 +79,15 @@ inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, 
     T.n_i7 = s.n_i7;
     T.n_i5 = s.has_i5 ? s.n_i5 : 0;
     if (T.n_i7 < 0 || T.n_i5 < 0 || !s.pair_sample) { why = "a template has no index table"; return false; }
+    // the 2-bit codes and the raw-byte hash agree only on [ACGT] (the sample sheet's own alphabet,
+    // src/sample_manager.rs:362-372): anything else would silently pack as another base
+    auto acgt = [](const char* p, size_t n) {
+      for (size_t i = 0; i < n; ++i)
+        if (p[i] != 'A' && p[i] != 'C' && p[i] != 'G' && p[i] != 'T') return false;
+      return true;
+    };
+    if ((T.n_i7 && !s.i7) || (T.n_i5 && !s.i5)) { why = "a template has no index table"; return false; }
+    if (!acgt(s.i7, (size_t)T.n_i7 * T.g[1]) || !acgt(s.i5, (size_t)T.n_i5 * T.g[4])) { why = "index tables must hold [ACGT] only"; return false; }
     T.wide = (T.g[1] > 16 || (T.has_i5 && T.g[4] > 16)) ? 1 : 0;
     T.off_i7 = (int)tb.codes.size();
     for (int i = 0; i < T.n_i7; ++i) tb.codes.push_back(pack_index_host(s.i7 + (size_t)i * T.g[1], T.g[1]));

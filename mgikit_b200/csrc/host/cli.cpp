@@ -160,7 +160,7 @@ int cli_main(int argc, char** argv, const Backend& be) {
     usage();
     return 2;
   }
-  if (command != "demultiplex" && command != "demultiplex") {
+  if (command != "demultiplex") {
     std::fprintf(stderr, "error: only the `demultiplex` command is provided by this build (got '%s'); "
                          "use the reference mgikit for template/report/reformat\n", command.c_str());
     return 2;

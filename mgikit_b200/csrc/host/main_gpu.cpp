@@ -13,10 +13,11 @@ int b_collect(void* c, mgk_result* r) { return mgk_collect((mgk_ctx*)c, r); }
 int b_release(void* c, uint64_t s) { return mgk_release((mgk_ctx*)c, s); }
 int b_counters(void* c, uint64_t* a, uint64_t* b) { return mgk_counters((mgk_ctx*)c, a, b); }
 int b_allreduce(void* const* c, int n) { return mgk_allreduce_counters((mgk_ctx* const*)c, n); }
+int b_reduced(void* c, uint64_t* a, uint64_t* b) { return mgk_reduced_counters((mgk_ctx*)c, a, b); }
 }  // namespace
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cuda-sm_100a", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, mgk_host_alloc, mgk_host_free};
+                              b_release, b_counters, b_allreduce, b_reduced, mgk_host_alloc, mgk_host_free};
   return mgikit::cli_main(argc, argv, be);
 }

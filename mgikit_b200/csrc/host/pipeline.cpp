@@ -478,11 +478,14 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     while (!fifo.empty()) finish_oldest();
 
     // ReportManager::update across workers (src/lib.rs:819-827) == sum over devices
-    if (G > 1 && be.allreduce(ctxs.data(), G) != MGK_OK)
-      throw Fatal(std::string("counter all-reduce failed: ") + be.last_error(ctxs[0]));
     std::vector<uint64_t> stats((size_t)total * MGK_N_STATS), mism((size_t)total * (size_t)(2 * m + 2));
-    if (be.counters(ctxs[0], stats.data(), mism.data()) != MGK_OK)
+    if (G > 1) {
+      if (be.allreduce(ctxs.data(), G) != MGK_OK) throw Fatal(std::string("counter all-reduce failed: ") + be.last_error(ctxs[0]));
+      if (be.reduced_counters(ctxs[0], stats.data(), mism.data()) != MGK_OK)
+        throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[0]));
+    } else if (be.counters(ctxs[0], stats.data(), mism.data()) != MGK_OK) {
       throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[0]));
+    }
     report.add_counters(stats.data(), mism.data());
   } catch (...) {
     destroy_all();

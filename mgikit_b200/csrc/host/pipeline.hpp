@@ -28,6 +28,7 @@ struct Backend {
   int (*release)(void*, uint64_t);
   int (*counters)(void*, uint64_t*, uint64_t*);
   int (*allreduce)(void* const*, int);
+  int (*reduced_counters)(void*, uint64_t*, uint64_t*);
   void* (*host_alloc)(size_t);
   void (*host_free)(void*);
 };

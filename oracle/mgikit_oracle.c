@@ -205,6 +205,9 @@ struct orc_ctx {
   int S, total, BL, mism_w;
   uint64_t* stats; /* [total][10] */
   uint64_t* mism;  /* [total][2m+2] */
+  uint64_t* red_stats; /* result of the last orc_allreduce_counters */
+  uint64_t* red_mism;
+  int reduced;
   /* result slots: cfg.n_slots chunks may be submitted before the first is released */
   struct oslot* slots;
   int n_slots;
@@ -259,6 +262,8 @@ int orc_create(const mgk_config* cfg, orc_ctx** out) {
   c->BL = c->tpl[0].g[9]; /* src/lib.rs:878-879 */
   c->stats = (uint64_t*)calloc((size_t)c->total * MGK_N_STATS, sizeof(uint64_t));
   c->mism = (uint64_t*)calloc((size_t)c->total * (size_t)c->mism_w, sizeof(uint64_t));
+  c->red_stats = (uint64_t*)calloc((size_t)c->total * MGK_N_STATS, sizeof(uint64_t));
+  c->red_mism = (uint64_t*)calloc((size_t)c->total * (size_t)c->mism_w, sizeof(uint64_t));
   c->n_slots = cfg->n_slots < 1 ? 1 : (cfg->n_slots > 8 ? 8 : cfg->n_slots);
   c->slots = (struct oslot*)calloc((size_t)c->n_slots, sizeof(struct oslot));
   for (int k = 0; k < c->n_slots; ++k) {
@@ -298,6 +303,8 @@ void orc_destroy(orc_ctx* c) {
   }
   free(c->slots);
   free(c->tpl);
+  free(c->red_stats);
+  free(c->red_mism);
   free(c->stats);
   free(c->mism);
   free(c->writing);
@@ -798,19 +805,33 @@ int orc_reset_counters(orc_ctx* c) {
   return MGK_OK;
 }
 
-/* ReportManager::update(), src/report_manager.rs:377-416, over n worker states */
+/* ReportManager::update(), src/report_manager.rs:377-416, over n worker states.  Out of place like
+ * mgk_allreduce_counters: every context keeps its own share, the sum is read with orc_reduced_counters. */
 int orc_allreduce_counters(orc_ctx* const* ctxs, int n) {
   if (n < 1) return MGK_ERR_ARG;
   const orc_ctx* c0 = ctxs[0];
   const size_t ns = (size_t)c0->total * MGK_N_STATS, nm = (size_t)c0->total * (size_t)c0->mism_w;
-  for (int r = 1; r < n; ++r) {
-    for (size_t i = 0; i < ns; ++i) ctxs[0]->stats[i] += ctxs[r]->stats[i];
-    for (size_t i = 0; i < nm; ++i) ctxs[0]->mism[i] += ctxs[r]->mism[i];
+  memset(ctxs[0]->red_stats, 0, ns * sizeof(uint64_t));
+  memset(ctxs[0]->red_mism, 0, nm * sizeof(uint64_t));
+  for (int r = 0; r < n; ++r) {
+    for (size_t i = 0; i < ns; ++i) ctxs[0]->red_stats[i] += ctxs[r]->stats[i];
+    for (size_t i = 0; i < nm; ++i) ctxs[0]->red_mism[i] += ctxs[r]->mism[i];
   }
   for (int r = 1; r < n; ++r) {
-    memcpy(ctxs[r]->stats, ctxs[0]->stats, ns * sizeof(uint64_t));
-    memcpy(ctxs[r]->mism, ctxs[0]->mism, nm * sizeof(uint64_t));
+    memcpy(ctxs[r]->red_stats, ctxs[0]->red_stats, ns * sizeof(uint64_t));
+    memcpy(ctxs[r]->red_mism, ctxs[0]->red_mism, nm * sizeof(uint64_t));
   }
+  for (int r = 0; r < n; ++r) ctxs[r]->reduced = 1;
+  return MGK_OK;
+}
+
+int orc_reduced_counters(orc_ctx* c, uint64_t* stats, uint64_t* mism) {
+  if (!c->reduced) {
+    snprintf(c->err, sizeof c->err, "orc_reduced_counters: no counter all-reduce has run on this context");
+    return MGK_ERR_STATE;
+  }
+  if (stats) memcpy(stats, c->red_stats, sizeof(uint64_t) * (size_t)c->total * MGK_N_STATS);
+  if (mism) memcpy(mism, c->red_mism, sizeof(uint64_t) * (size_t)c->total * (size_t)c->mism_w);
   return MGK_OK;
 }
 

@@ -35,6 +35,7 @@ int orc_release(orc_ctx* ctx, uint64_t seq);
 int orc_counters(orc_ctx* ctx, uint64_t* stats, uint64_t* mism);
 int orc_reset_counters(orc_ctx* ctx);
 int orc_allreduce_counters(orc_ctx* const* ctxs, int n);
+int orc_reduced_counters(orc_ctx* ctx, uint64_t* stats, uint64_t* mism);
 void* orc_host_alloc(size_t bytes);
 void orc_host_free(void* p);
 int orc_scan_newlines(orc_ctx* ctx, const uint8_t* buf, uint64_t len,

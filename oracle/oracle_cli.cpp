@@ -16,10 +16,11 @@ int b_collect(void* c, mgk_result* r) { return orc_collect((orc_ctx*)c, r); }
 int b_release(void* c, uint64_t s) { return orc_release((orc_ctx*)c, s); }
 int b_counters(void* c, uint64_t* a, uint64_t* b) { return orc_counters((orc_ctx*)c, a, b); }
 int b_allreduce(void* const* c, int n) { return orc_allreduce_counters((orc_ctx* const*)c, n); }
+int b_reduced(void* c, uint64_t* a, uint64_t* b) { return orc_reduced_counters((orc_ctx*)c, a, b); }
 }  // namespace
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cpu-oracle", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, orc_host_alloc, orc_host_free};
+                              b_release, b_counters, b_allreduce, b_reduced, orc_host_alloc, orc_host_free};
   return mgikit::cli_main(argc, argv, be);
 }

@@ -26,12 +26,13 @@ int b_collect(void* c, mgk_result* r) { return emu_collect((emu_ctx*)c, r); }
 int b_release(void* c, uint64_t s) { return emu_release((emu_ctx*)c, s); }
 int b_counters(void* c, uint64_t* a, uint64_t* b) { return emu_counters((emu_ctx*)c, a, b); }
 int b_allreduce(void* const*, int) { return MGK_ERR_ARG; }
+int b_reduced(void*, uint64_t*, uint64_t*) { return MGK_ERR_ARG; }
 void* b_alloc(size_t n) { return malloc(n); }
 void b_free(void* p) { free(p); }
 }  // namespace
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cpu-emulation-of-device-logic", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, b_alloc, b_free};
+                              b_release, b_counters, b_allreduce, b_reduced, b_alloc, b_free};
   return mgikit::cli_main(argc, argv, be);
 }

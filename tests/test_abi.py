@@ -28,7 +28,7 @@ def test_gpu_library_exports_every_declared_symbol():
 
 def test_oracle_mirrors_the_abi(oracle_lib):
     for s in ["create", "destroy", "last_error", "submit", "collect", "release", "counters", "reset_counters",
-              "allreduce_counters", "host_alloc", "host_free", "scan_newlines", "match_barcodes"]:
+              "allreduce_counters", "reduced_counters", "host_alloc", "host_free", "scan_newlines", "match_barcodes"]:
         assert hasattr(oracle_lib, "orc_" + s)
 
 
