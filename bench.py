@@ -179,16 +179,16 @@ def short_lane_line(lane, n, device, peak):
     import torch
     from mgikit_b200 import synth
     from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
-    from util import make_hotpath
+    from util import device_copy, make_hotpath
     r1, r2 = synth.make_block(lane, 0, n)
     in_bytes = r2.size + (r1.size if r1 is not None else 0)
     spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size if r1 is not None else 0, r2.size) + 4096, max_chunk_records=n + 64,
                           n_slots=2, device=device)
     hp = make_hotpath(load_gpu_library(), "mgk_", spec)
     try:
-        d2 = torch.from_numpy(r2).cuda()
-        d1 = torch.from_numpy(r1).cuda() if r1 is not None and r1.size else None
-        dev_args = ((d2.data_ptr(), d2.numel()), (d1.data_ptr(), d1.numel()) if d1 is not None else None)
+        d2, a2 = device_copy(r2)
+        d1, a1 = device_copy(r1) if r1 is not None and r1.size else (None, None)
+        dev_args = (a2, a1)
         flags = MGK_IN_DEVICE | MGK_OUT_DEVICE
         resident_run(hp, dev_args, 4, flags)
         k_ms = np.array(serial_run(hp, dev_args, 6, flags)[1:])
@@ -241,7 +241,7 @@ def main():
     import torch
     import torch.distributed as dist
     from mgikit_b200.capi import CLI_BIN, MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
-    from util import make_hotpath
+    from util import device_copy, make_hotpath
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
@@ -284,8 +284,8 @@ def main():
         dist.broadcast(uid, 0)
         hp.nccl_join(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
-    d2, d1 = torch.from_numpy(r2).cuda(), torch.from_numpy(r1).cuda()
-    dev_args = ((d2.data_ptr(), d2.numel()), (d1.data_ptr(), d1.numel()))
+    (d2, a2), (d1, a1) = device_copy(r2), device_copy(r1)
+    dev_args = (a2, a1)
     RES = MGK_IN_DEVICE | MGK_OUT_DEVICE
 
     def merged_tables_check(expected_reads):

@@ -7,6 +7,7 @@
 #include <map>
 
 #include "log.hpp"
+#include "template_cmd.hpp"
 
 namespace mgikit {
 
@@ -66,6 +67,24 @@ const Opt OPTS[] = {
     {"chunk-size", 0, true, "67108864", nullptr},
 };
 
+// `template` subcommand, src/main.rs:400-511
+const Opt TEMPLATE_OPTS[] = {
+    {"input", 'i', true, "", nullptr},
+    {"read2", 'r', true, "", "2"},
+    {"read1", 'f', true, "", "1"},
+    {"sample-sheet", 's', true, nullptr, nullptr},
+    {"info-file", 0, true, "", nullptr},
+    {"output", 'o', true, "", nullptr},
+    {"barcode-length", 0, true, "0", nullptr},
+    {"popular-template", 0, false, "false", nullptr},
+    {"no-umi", 0, false, "false", nullptr},
+    {"testing-reads", 0, true, "5000", nullptr},
+    {"max-umi-len", 0, true, "10", nullptr},
+    {"in-r1-file-suf", 0, true, "_read_1.fq.gz", nullptr},
+    {"in-r2-file-suf", 0, true, "_read_2.fq.gz", nullptr},
+    {"log-level", 'l', true, "info", nullptr},
+};
+
 void print_logo() {
   std::printf("\n");
   std::printf("        MGIKIT  -  B200 hot path\n");
@@ -73,7 +92,8 @@ void print_logo() {
 }
 
 void usage() {
-  std::printf("MGIKIT - MGI data demultipexing kit (B200 hot path).\n\nUsage: mgikit demultiplex [OPTIONS] --sample-sheet <FILE>\n\nOptions:\n");
+  std::printf("MGIKIT - MGI data demultipexing kit (B200 hot path).\n\nUsage: mgikit demultiplex [OPTIONS] --sample-sheet <FILE>\n"
+              "       mgikit template [OPTIONS] --sample-sheet <FILE>   (barcode template detection)\n\nOptions of demultiplex:\n");
   for (const auto& o : OPTS) {
     if (o.short_name) std::printf("  -%c, --%s", o.short_name, o.long_name);
     else std::printf("      --%s", o.long_name);
@@ -93,18 +113,33 @@ size_t parse_usize(const std::string& name, const std::string& v) {
 }  // namespace
 
 int cli_main(int argc, char** argv, const Backend& be) {
+  // the subcommand decides the option table: it is the first word that is neither an option nor the value of the
+  // global -l/--log-level in front of it
+  bool is_template = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "-l" || a == "--log-level") {
+      ++i;
+      continue;
+    }
+    if (!a.empty() && a[0] == '-') continue;
+    is_template = a == "template";
+    break;
+  }
+  const Opt* table = is_template ? TEMPLATE_OPTS : OPTS;
+  const size_t n_table = is_template ? sizeof(TEMPLATE_OPTS) / sizeof(Opt) : sizeof(OPTS) / sizeof(Opt);
   std::map<std::string, std::string> val;
-  for (const auto& o : OPTS)
-    if (o.def) val[o.long_name] = o.def;
+  for (size_t k = 0; k < n_table; ++k)
+    if (table[k].def) val[table[k].long_name] = table[k].def;
   std::string command;
-  auto find_long = [](const std::string& n) -> const Opt* {
-    for (const auto& o : OPTS)
-      if (n == o.long_name || (o.alias && n == o.alias)) return &o;
+  auto find_long = [&](const std::string& n) -> const Opt* {
+    for (size_t k = 0; k < n_table; ++k)
+      if (n == table[k].long_name || (table[k].alias && n == table[k].alias)) return &table[k];
     return nullptr;
   };
-  auto find_short = [](char c) -> const Opt* {
-    for (const auto& o : OPTS)
-      if (o.short_name == c) return &o;
+  auto find_short = [&](char c) -> const Opt* {
+    for (size_t k = 0; k < n_table; ++k)
+      if (table[k].short_name == c) return &table[k];
     return nullptr;
   };
   for (int i = 1; i < argc; ++i) {
@@ -160,9 +195,9 @@ int cli_main(int argc, char** argv, const Backend& be) {
     usage();
     return 2;
   }
-  if (command != "demultiplex") {
-    std::fprintf(stderr, "error: only the `demultiplex` command is provided by this build (got '%s'); "
-                         "use the reference mgikit for template/report/reformat\n", command.c_str());
+  if (command != "demultiplex" && command != "template") {
+    std::fprintf(stderr, "error: this build provides the `demultiplex` and `template` commands (got '%s'); "
+                         "use the reference mgikit for report/reformat\n", command.c_str());
     return 2;
   }
   if (!val.count("sample-sheet")) {
@@ -172,6 +207,32 @@ int cli_main(int argc, char** argv, const Backend& be) {
   set_log_level(val["log-level"]);
   auto flag = [&](const char* n) { return val[n] == "true"; };
   const auto t0 = std::chrono::steady_clock::now();
+  if (command == "template") {
+    try {
+      TemplateArgs ta;
+      ta.input_dir = val["input"];
+      ta.read1 = val["read1"];
+      ta.read2 = val["read2"];
+      ta.sample_sheet = val["sample-sheet"];
+      ta.info_file = val["info-file"];
+      ta.output = val["output"];
+      ta.r1_suffix = val["in-r1-file-suf"];
+      ta.r2_suffix = val["in-r2-file-suf"];
+      ta.barcode_length = parse_usize("barcode-length", val["barcode-length"]);
+      ta.testing_reads = parse_usize("testing-reads", val["testing-reads"]);
+      ta.max_umi_length = parse_usize("max-umi-len", val["max-umi-len"]);
+      ta.popular_template = flag("popular-template");
+      ta.add_umi = !flag("no-umi");
+      run_template(ta);
+    } catch (const std::exception& e) {
+      std::fflush(stdout);
+      std::fprintf(stderr, "mgikit error: %s\n", e.what());
+      return 101;
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    log_info("Exection time is " + std::to_string((long)secs) + " seconds.");
+    return 0;
+  }
   try {
     // initiate_demultiplexing(), src/lib.rs:1606-1856
     SampleSheet sheet = load_sample_manager(val["sample-sheet"], val["template"], flag("i7-rc"), flag("i5-rc"),

@@ -52,6 +52,8 @@ const std::string& col(const std::vector<std::string>& vals, size_t i) {
   return vals[i];
 }
 
+}  // namespace
+
 // load_sample_sheet(), src/sample_manager.rs:290-456
 std::vector<std::array<std::string, 7>> load_sample_sheet(const std::string& path) {
   std::ifstream f(path, std::ios::binary);
@@ -127,6 +129,8 @@ std::vector<std::array<std::string, 7>> load_sample_sheet(const std::string& pat
   if (rows.empty()) throw Fatal("Sample sheet seems to be empty! No sample is found!");
   return rows;
 }
+
+namespace {
 
 int find_or_add(std::vector<std::string>& v, const std::string& s) {
   for (size_t i = 0; i < v.size(); ++i)

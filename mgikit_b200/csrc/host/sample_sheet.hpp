@@ -47,6 +47,9 @@ struct SampleSheet {
   int barcode_length() const { return templates[0].geometry[9]; }
 };
 
+// load_sample_sheet (src/sample_manager.rs:290-456): the rows as written, no pseudo samples
+std::vector<std::array<std::string, 7>> load_sample_sheet(const std::string& path);
+
 // SampleManager::new (src/sample_manager.rs:38-113)
 SampleSheet load_sample_manager(const std::string& path, const std::string& tmpl, bool i7_rc,
                                 bool i5_rc, const std::string& undetermined_label,

@@ -66,9 +66,39 @@ def odd_lanes():
             ("odd-long-reads", L("odd10", 14, "i710:i510", r1_len=301, r2_insert=250, seed=61010, **noisy), ["--comprehensive-scan"], 2000)]
 
 
+def template_cases():
+    """testing_template (tests/integration_test.rs:73-160): (name, fixture set, sample sheet, extra flags, expected file)."""
+    out = []
+    for ds in (1, 2, 3, 7):
+        ds_in = 1 if ds == 7 else ds
+        sheet = "input/ds01/sample_sheet-ds07.tsv" if ds == 7 else f"input/ds0{ds_in}/sample_sheet.tsv"
+        extra = ["--barcode-length", "20" if ds == 3 else "0"] + ([] if ds in (2, 3) else ["--popular-template"])
+        out.append((f"template-ds0{ds}", f"input/ds0{ds_in}/L01/FC0{ds_in}_L01_read_1.fq.gz", f"input/ds0{ds_in}/L01/FC0{ds_in}_L01_read_2.fq.gz",
+                    sheet, extra, f"expected/ds0{ds}/sample_sheet_expected.tsv"))
+    return out
+
+
+def synthetic_template_variants():
+    """(name, lane, reads, flags of `mgikit template`): the reference binary's own answer is recorded."""
+    return [("tpl-cfg4", synth.CONFIG4, 20000, ["--testing-reads", "10000", "--barcode-length", "8"]),
+            ("tpl-cfg2", synth.CONFIG2, 6000, []),
+            ("tpl-cfg3-popular", synth.CONFIG3, 6000, ["--popular-template", "--testing-reads", "3000"]),
+            ("tpl-cfg3-no-umi", synth.CONFIG3, 6000, ["--no-umi", "--barcode-length", "28"])]
+
+
+def run_template(binary, lane, n, flags, d):
+    r1, r2, sheet = lanes.write_lane(lane, n, d)
+    args = ["template", "-f", r1] + (["-r", r2] if r2 else []) + ["-s", sheet, "-o", os.path.join(d, "tpl", "sheet")] + list(flags)
+    lanes.run_binary(binary, args)
+    with open(os.path.join(d, "tpl", "sheet_template.tsv"), "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
 def main():
     cases = M.all_cases()
     needed = set()
+    for _, r1, r2, sheet, _, expected in template_cases():
+        needed.update([r1, r2, sheet, expected])
     for c in cases:
         it = iter(c.args)
         for a in it:
@@ -113,7 +143,14 @@ def main():
         shutil.rmtree(d)
     with open(os.path.join(HERE, "synthetic_reference.json"), "w") as f:
         json.dump(syn, f, indent=0, sort_keys=True)
-    print(f"{len(matrix)} fixture cases, {len(syn)} synthetic lanes")
+    tpl = {}
+    for name, lane, n, flags in synthetic_template_variants():
+        d = tempfile.mkdtemp(prefix="golden_")
+        tpl[name] = {"n_pairs": n, "flags": flags, "template_tsv": run_template(REF_BIN, lane, n, flags, d)}
+        shutil.rmtree(d)
+    with open(os.path.join(HERE, "template_reference.json"), "w") as f:
+        json.dump(tpl, f, indent=0, sort_keys=True)
+    print(f"{len(matrix)} fixture cases, {len(syn)} synthetic lanes, {len(tpl)} template lanes")
 
 
 if __name__ == "__main__":

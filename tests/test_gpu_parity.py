@@ -8,7 +8,7 @@ import pytest
 import cases
 from mgikit_b200 import synth
 from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE
-from util import assert_same_counters, assert_same_result, make_hotpath, run_both
+from util import assert_same_counters, assert_same_result, device_copy, make_hotpath, run_both
 
 pytestmark = pytest.mark.gpu
 ALL = cases.all_cases()
@@ -80,11 +80,11 @@ def test_device_resident_and_double_buffered(oracle_lib, gpu_lib):
     g = make_hotpath(gpu_lib, "mgk_", spec)
     o = make_hotpath(oracle_lib, "orc_", spec)
     blocks = [synth.make_block(lane, b, n) for b in range(4)]
-    dev = [(torch.from_numpy(r2).cuda(), torch.from_numpy(r1).cuda()) for r1, r2 in blocks]
+    dev = [(device_copy(r2), device_copy(r1)) for r1, r2 in blocks]
     results = {}
     for k in range(len(blocks)):
-        d2, d1 = dev[k]
-        g.submit(k, (d2.data_ptr(), d2.numel()), (d1.data_ptr(), d1.numel()), MGK_IN_DEVICE | MGK_OUT_DEVICE)
+        (_, a2), (_, a1) = dev[k]
+        g.submit(k, a2, a1, MGK_IN_DEVICE | MGK_OUT_DEVICE)
         if k >= 1:
             results[k - 1] = g.collect(device_out=True)
             _fetch(results[k - 1])
@@ -157,3 +157,28 @@ def test_cuda_matches_oracle_random_mixed_libraries(oracle_lib, gpu_lib, seed):
     spec, chunks = _mixed_case(5000 + seed)
     run_both(oracle_lib, "orc_", gpu_lib, "mgk_", spec, chunks,
              what=f"mixed fuzz seed {seed}: m={spec.mismatches} comp={spec.comprehensive_scan} mode={spec.out_mode}")
+
+
+def test_device_input_without_slack_is_refused(gpu_lib):
+    """MGK_IN_DEVICE contract (include/mgikit_gpu.h): the allocation must stay readable MGK_DEVICE_INPUT_SLACK bytes
+    past the text; a buffer that ends with its text is refused, not over-read."""
+    import ctypes
+
+    from mgikit_b200.capi import MgkError
+    lane = synth.CONFIG2
+    r1, r2 = synth.make_block(lane, 0, 512)
+    spec = synth.run_spec(lane, max_chunk_bytes=1 << 20, max_chunk_records=600)
+    g = make_hotpath(gpu_lib, "mgk_", spec)
+    cudart = ctypes.CDLL("libcudart.so.12")
+    size = (r2.size + 511) & ~511                     # cudaMalloc'd ranges are what cuMemGetAddressRange reports
+    p = ctypes.c_void_p()
+    assert cudart.cudaMalloc(ctypes.byref(p), ctypes.c_size_t(size)) == 0
+    try:
+        (_, a1) = device_copy(r1)
+        tight = (p.value + size - r2.size) & ~15      # text ends within 16 bytes of the allocation's end
+        with pytest.raises(MgkError) as e:
+            g.submit(0, (tight, p.value + size - tight), a1, MGK_IN_DEVICE)
+        assert e.value.code == -1 and "readable bytes" in str(e.value)
+    finally:
+        cudart.cudaFree(p)
+        g.close()

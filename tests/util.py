@@ -60,3 +60,12 @@ def run_both(lib_a, pre_a, lib_b, pre_b, spec: RunSpec, chunks, what=""):
     finally:
         ha.close()
         hb.close()
+
+
+def device_copy(arr):
+    """A uint8 array copied to the current CUDA device with the readable slack MGK_IN_DEVICE asks for
+    (include/mgikit_gpu.h: MGK_DEVICE_INPUT_SLACK bytes past the text); returns (tensor that owns it, (ptr, len))."""
+    import torch
+    t = torch.empty(arr.size + 64, dtype=torch.uint8, device="cuda")
+    t[:arr.size].copy_(torch.from_numpy(arr))
+    return t, (t.data_ptr(), arr.size)

@@ -12,7 +12,7 @@ import torch
 
 from mgikit_b200 import synth
 from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
-from util import make_hotpath
+from util import device_copy, make_hotpath
 
 which = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
@@ -20,10 +20,8 @@ lane = {2: synth.CONFIG2, 3: synth.CONFIG3, 4: synth.CONFIG4, 5: synth.CONFIG5}[
 r1, r2 = synth.make_block(lane, 0, n)
 spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size if r1 is not None else 0, r2.size) + 4096, max_chunk_records=n + 64, n_slots=2)
 hp = make_hotpath(load_gpu_library(), "mgk_", spec)
-d2 = torch.from_numpy(r2).cuda()
-d1 = torch.from_numpy(r1).cuda() if r1 is not None and r1.size else None
-a2 = (d2.data_ptr(), d2.numel())
-a1 = (d1.data_ptr(), d1.numel()) if d1 is not None else None
+d2, a2 = device_copy(r2)
+d1, a1 = device_copy(r1) if r1 is not None and r1.size else (None, None)
 rows = []
 for k in range(8):
     hp.submit(k, a2, a1, MGK_IN_DEVICE | MGK_OUT_DEVICE)
