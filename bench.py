@@ -283,6 +283,7 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(hp.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         hp.nccl_join(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        hp.nccl_allreduce_counters()   # connection setup happens on the first collective: not part of any timing below
 
     (d2, a2), (d1, a1) = device_copy(r2), device_copy(r1)
     dev_args = (a2, a1)

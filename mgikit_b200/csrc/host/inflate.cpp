@@ -1,0 +1,542 @@
+#include "inflate.hpp"
+
+#include <cstring>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace mgikit {
+
+namespace {
+
+// decode-table entry
+//   bits 0-4   code bits to consume (subtable pointer: index bits of the subtable)
+//   bits 8-11  extra bits that follow the code (lengths, distances)
+//   bit 12 literal, 13 end of block, 14 subtable pointer, 15 not a code (incomplete set)
+//   bits 16-31 literal byte / length base / distance base / offset of the subtable
+constexpr uint32_t E_LIT = 1u << 12, E_EOB = 1u << 13, E_SUB = 1u << 14, E_BAD = 1u << 15;
+constexpr uint32_t E_SPECIAL = E_EOB | E_SUB | E_BAD;
+
+const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+const uint8_t CLEN_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+inline uint64_t load64(const uint8_t* p) {
+  uint64_t v;
+  memcpy(&v, p, 8);
+  return v;
+}
+
+inline unsigned reverse_bits(unsigned code, unsigned len) {
+  unsigned r = 0;
+  for (unsigned i = 0; i < len; ++i) {
+    r = (r << 1) | (code & 1u);
+    code >>= 1;
+  }
+  return r;
+}
+
+// Canonical Huffman code -> decode table.  lens[sym] in 0..15; entry_of(sym) gives the entry without its code
+// length.  Returns false for an over-subscribed set, and for an incomplete one unless it is a single 1-bit code
+// or (allow_empty) no code at all -- the sets zlib accepts (inftrees.c).
+template <typename F>
+bool build_table(const uint8_t* lens, unsigned n, uint32_t* table, unsigned primary_bits, size_t table_cap, bool allow_empty, F entry_of) {
+  unsigned count[16] = {0};
+  for (unsigned s = 0; s < n; ++s) count[lens[s]]++;
+  unsigned max_len = 15;
+  while (max_len > 0 && count[max_len] == 0) --max_len;
+  const size_t primary = (size_t)1 << primary_bits;
+  if (max_len == 0) {
+    if (!allow_empty) return false;
+    for (size_t i = 0; i < primary; ++i) table[i] = E_BAD | 1u;
+    return true;
+  }
+  int left = 1;
+  for (unsigned l = 1; l <= 15; ++l) {
+    left <<= 1;
+    left -= (int)count[l];
+    if (left < 0) return false;
+  }
+  if (left > 0 && max_len != 1) return false;
+  const unsigned sub_bits = max_len > primary_bits ? max_len - primary_bits : 0;
+  for (size_t i = 0; i < primary; ++i) table[i] = E_BAD | 1u;
+  unsigned next_code[16], code = 0;
+  for (unsigned l = 1; l <= 15; ++l) {
+    code = (code + count[l - 1]) << 1;
+    next_code[l] = code;
+  }
+  count[0] = 0;
+  size_t sub_next = primary;
+  for (unsigned l = 1; l <= max_len; ++l) {   // by length, then by symbol: canonical order
+    if (!count[l]) continue;
+    for (unsigned s = 0; s < n; ++s) {
+      if (lens[s] != l) continue;
+      const unsigned rev = reverse_bits(next_code[l]++, l);
+      const uint32_t e = entry_of(s) | l;
+      if (l <= primary_bits) {
+        for (size_t i = rev; i < primary; i += (size_t)1 << l) table[i] = e;
+      } else {
+        const size_t slot = rev & (primary - 1);
+        if (!(table[slot] & E_SUB)) {
+          if (sub_next + ((size_t)1 << sub_bits) > table_cap) return false;
+          table[slot] = E_SUB | sub_bits | ((uint32_t)sub_next << 16);
+          for (size_t i = 0; i < ((size_t)1 << sub_bits); ++i) table[sub_next + i] = E_BAD | 1u;
+          sub_next += (size_t)1 << sub_bits;
+        }
+        uint32_t* sub = table + (table[slot] >> 16);
+        for (size_t i = rev >> primary_bits; i < ((size_t)1 << sub_bits); i += (size_t)1 << (l - primary_bits)) sub[i] = e;
+      }
+    }
+  }
+  return true;
+}
+
+inline uint32_t litlen_entry(unsigned s) {
+  if (s < 256) return E_LIT | (s << 16);
+  if (s == 256) return E_EOB;
+  if (s > 285) return E_BAD;   // 286, 287 take part in the code but never appear in valid data
+  return ((uint32_t)LEN_BASE[s - 257] << 16) | ((uint32_t)LEN_EXTRA[s - 257] << 8);
+}
+inline uint32_t dist_entry(unsigned s) {
+  if (s > 29) return E_BAD;
+  return ((uint32_t)DIST_BASE[s] << 16) | ((uint32_t)DIST_EXTRA[s] << 8);
+}
+
+}  // namespace
+
+void Inflater::reset(const uint8_t* in, size_t n) {
+  in_begin_ = in_next_ = in;
+  in_end_ = in + n;
+  bitbuf_ = 0;
+  bitcnt_ = 0;
+  state_ = ST_HEADER;
+  final_ = false;
+  stored_left_ = 0;
+  err_ = "";
+}
+
+bool Inflater::build_tables(const uint8_t* lens, unsigned n_lit, unsigned n_dist) {
+  if (lens[256] == 0) {
+    err_ = "invalid code -- missing end-of-block";
+    return false;
+  }
+  if (!build_table(lens, n_lit, lit_, LIT_BITS, sizeof lit_ / sizeof lit_[0], false, litlen_entry)) {
+    err_ = "invalid literal/lengths set";
+    return false;
+  }
+  if (!build_table(lens + n_lit, n_dist, dist_, DIST_BITS, sizeof dist_ / sizeof dist_[0], true, dist_entry)) {
+    err_ = "invalid distances set";
+    return false;
+  }
+  return true;
+}
+
+// Block header, byte-wise refills (once per block).
+Inflater::Status Inflater::read_block_header() {
+  uint64_t bb = bitbuf_;
+  unsigned bc = bitcnt_;
+  const uint8_t* in = in_next_;
+  auto need = [&](unsigned n) {
+    while (bc < n && in < in_end_) {
+      bb |= (uint64_t)*in++ << bc;
+      bc += 8;
+    }
+    return bc >= n;
+  };
+  auto take = [&](unsigned n) {
+    const unsigned v = (unsigned)(bb & ((1ull << n) - 1));
+    bb >>= n;
+    bc -= n;
+    return v;
+  };
+  auto leave = [&](Status s) {
+    bitbuf_ = bb;
+    bitcnt_ = bc;
+    in_next_ = in;
+    return s;
+  };
+  // the branch-free refill of the block loop leaves look-ahead bits above bitcnt: they are the bytes at in_next,
+  // and OR-ing those bytes in again is harmless; drop them so that `need` starts from a clean buffer
+  bb &= bc >= 64 ? ~0ull : ((1ull << bc) - 1);
+  if (!need(3)) return leave(TRUNCATED);
+  final_ = take(1) != 0;
+  const unsigned type = take(2);
+  if (type == 0) {
+    take(bc & 7);                 // to the byte boundary
+    in -= bc >> 3;                // whole bytes still in the bit buffer go back
+    bb = 0;
+    bc = 0;
+    if (in_end_ - in < 4) return leave(TRUNCATED);
+    const unsigned len = in[0] | (in[1] << 8), nlen = in[2] | (in[3] << 8);
+    if ((len ^ 0xffffu) != nlen) {
+      err_ = "invalid stored block lengths";
+      return leave(BAD_DATA);
+    }
+    in += 4;
+    stored_left_ = len;
+    state_ = ST_STORED;
+    return leave(DONE);
+  }
+  uint8_t lens[288 + 32];
+  unsigned n_lit, n_dist;
+  if (type == 1) {
+    n_lit = 288;
+    n_dist = 32;
+    for (unsigned i = 0; i < 144; ++i) lens[i] = 8;
+    for (unsigned i = 144; i < 256; ++i) lens[i] = 9;
+    for (unsigned i = 256; i < 280; ++i) lens[i] = 7;
+    for (unsigned i = 280; i < 288; ++i) lens[i] = 8;
+    for (unsigned i = 0; i < 32; ++i) lens[288 + i] = 5;
+  } else if (type == 2) {
+    if (!need(14)) return leave(TRUNCATED);
+    n_lit = take(5) + 257;
+    n_dist = take(5) + 1;
+    const unsigned n_clen = take(4) + 4;
+    if (n_lit > 286 || n_dist > 30) {
+      err_ = "too many length or distance symbols";
+      return leave(BAD_DATA);
+    }
+    uint8_t clens[19] = {0};
+    for (unsigned i = 0; i < n_clen; ++i) {
+      if (!need(3)) return leave(TRUNCATED);
+      clens[CLEN_ORDER[i]] = (uint8_t)take(3);
+    }
+    uint32_t ctab[128];
+    if (!build_table(clens, 19, ctab, 7, 128, false, [](unsigned s) { return (uint32_t)s << 16; })) {
+      err_ = "invalid code lengths set";
+      return leave(BAD_DATA);
+    }
+    unsigned i = 0;
+    while (i < n_lit + n_dist) {
+      need(7 + 7);
+      const uint32_t e = ctab[bb & 127];
+      if ((e & E_BAD) || (e & 31u) > bc) {
+        if (bc < 7 && in >= in_end_) return leave(TRUNCATED);
+        err_ = "invalid code lengths set";
+        return leave(BAD_DATA);
+      }
+      take(e & 31u);
+      const unsigned sym = e >> 16;
+      if (sym < 16) {
+        lens[i++] = (uint8_t)sym;
+        continue;
+      }
+      unsigned rep, val = 0;
+      const unsigned xb = sym == 16 ? 2 : sym == 17 ? 3 : 7;
+      if (bc < xb && !need(xb)) return leave(TRUNCATED);
+      if (sym == 16) {
+        if (i == 0) {
+          err_ = "invalid bit length repeat";
+          return leave(BAD_DATA);
+        }
+        val = lens[i - 1];
+        rep = 3 + take(2);
+      } else if (sym == 17) {
+        rep = 3 + take(3);
+      } else {
+        rep = 11 + take(7);
+      }
+      if (i + rep > n_lit + n_dist) {
+        err_ = "invalid bit length repeat";
+        return leave(BAD_DATA);
+      }
+      while (rep--) lens[i++] = (uint8_t)val;
+    }
+  } else {
+    err_ = "invalid block type";
+    return leave(BAD_DATA);
+  }
+  if (!build_tables(lens, n_lit, n_dist)) return leave(BAD_DATA);
+  state_ = ST_CODES;
+  return leave(DONE);
+}
+
+// The symbols of one compressed block.  FAST: at least 16 input bytes and 300 output bytes are left (checked per
+// symbol group), refills are branch-free 8-byte loads, copies may overshoot by up to 15 bytes.  !FAST: byte-wise
+// refills with bounds, exact copies, suspension when fewer than 258 output bytes are left.
+template <bool FAST>
+Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+  uint64_t bb = bitbuf_;
+  unsigned bc = bitcnt_;
+  const uint8_t* in = in_next_;
+  uint8_t* out = *out_next;
+  const uint32_t* lit = lit_;
+  const uint32_t* dst = dist_;
+  Status st = DONE;
+#define MGK_LEAVE(s) \
+  do {               \
+    st = (s);        \
+    goto leave;      \
+  } while (0)
+  for (;;) {
+    if (FAST) {
+      if (in_end_ - in < 16 || out_end - out < 300) MGK_LEAVE(NEED_OUTPUT);   // the caller goes on with the careful loop
+      bb |= load64(in) << bc;
+      in += (63 - bc) >> 3;
+      bc |= 56;
+    } else {
+      if (out_end - out < 258) MGK_LEAVE(NEED_OUTPUT);
+      while (bc <= 56 && in < in_end_) {
+        bb |= (uint64_t)*in++ << bc;
+        bc += 8;
+      }
+    }
+    uint32_t e = lit[bb & ((1u << LIT_BITS) - 1)];
+    if (FAST && (e & E_LIT)) {   // up to three literals per refill (3 x 15 bits)
+      bb >>= e & 31u;
+      bc -= e & 31u;
+      *out++ = (uint8_t)(e >> 16);
+      e = lit[bb & ((1u << LIT_BITS) - 1)];
+      if (e & E_LIT) {
+        bb >>= e & 31u;
+        bc -= e & 31u;
+        *out++ = (uint8_t)(e >> 16);
+        e = lit[bb & ((1u << LIT_BITS) - 1)];
+        if (e & E_LIT) {
+          bb >>= e & 31u;
+          bc -= e & 31u;
+          *out++ = (uint8_t)(e >> 16);
+          continue;
+        }
+      }
+    }
+    if (e & E_SPECIAL) {
+      if (e & E_SUB) e = lit[(e >> 16) + ((bb >> LIT_BITS) & ((1u << (e & 31u)) - 1))];
+      if (e & E_BAD) {
+        if (!FAST && bc < 15 && in >= in_end_) MGK_LEAVE(TRUNCATED);
+        err_ = "invalid literal/length code";
+        MGK_LEAVE(BAD_DATA);
+      }
+    }
+    if (!FAST && (e & 31u) + ((e >> 8) & 15u) > bc) MGK_LEAVE(TRUNCATED);
+    bb >>= e & 31u;
+    bc -= e & 31u;
+    if (e & E_LIT) {
+      *out++ = (uint8_t)(e >> 16);
+      continue;
+    }
+    if (e & E_EOB) {
+      state_ = final_ ? ST_DONE : ST_HEADER;
+      MGK_LEAVE(DONE);
+    }
+    unsigned xb = (e >> 8) & 15u;
+    const unsigned len = (e >> 16) + (unsigned)(bb & ((1u << xb) - 1));
+    bb >>= xb;
+    bc -= xb;
+    if (FAST) {
+      bb |= load64(in) << bc;
+      in += (63 - bc) >> 3;
+      bc |= 56;
+    } else {
+      while (bc <= 56 && in < in_end_) {
+        bb |= (uint64_t)*in++ << bc;
+        bc += 8;
+      }
+    }
+    uint32_t d = dst[bb & ((1u << DIST_BITS) - 1)];
+    if (d & E_SPECIAL) {
+      if (d & E_SUB) d = dst[(d >> 16) + ((bb >> DIST_BITS) & ((1u << (d & 31u)) - 1))];
+      if (d & E_BAD) {
+        if (!FAST && bc < 15 && in >= in_end_) MGK_LEAVE(TRUNCATED);
+        err_ = "invalid distance code";
+        MGK_LEAVE(BAD_DATA);
+      }
+    }
+    xb = (d >> 8) & 15u;
+    if (!FAST && (d & 31u) + xb > bc) MGK_LEAVE(TRUNCATED);
+    bb >>= d & 31u;
+    bc -= d & 31u;
+    const size_t dist = (d >> 16) + (size_t)(bb & ((1u << xb) - 1));
+    bb >>= xb;
+    bc -= xb;
+    if (dist > (size_t)(out - out_begin)) {
+      err_ = "invalid distance too far back";
+      MGK_LEAVE(BAD_DATA);
+    }
+    const uint8_t* src = out - dist;
+    uint8_t* end = out + len;
+    if (FAST && dist >= 8) {
+      memcpy(out, src, 8);
+      memcpy(out + 8, src + 8, 8);
+      if (len > 16) {
+        out += 16;
+        src += 16;
+        do {
+          memcpy(out, src, 8);
+          out += 8;
+          src += 8;
+        } while (out < end);
+      }
+    } else if (dist == 1) {
+      memset(out, *src, len);
+    } else {
+      while (out < end) *out++ = *src++;
+    }
+    out = end;
+  }
+leave:
+#undef MGK_LEAVE
+  bitbuf_ = bb;
+  bitcnt_ = bc;
+  in_next_ = in;
+  *out_next = out;
+  return st;
+}
+
+Inflater::Status Inflater::run(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+  for (;;) {
+    switch (state_) {
+      case ST_DONE:
+        return DONE;
+      case ST_HEADER: {
+        const Status s = read_block_header();
+        if (s != DONE) return s;
+        break;
+      }
+      case ST_STORED: {
+        const size_t room = (size_t)(out_end - *out_next), have = (size_t)(in_end_ - in_next_);
+        const size_t n = stored_left_ < room ? (stored_left_ < have ? stored_left_ : have) : (room < have ? room : have);
+        memcpy(*out_next, in_next_, n);
+        *out_next += n;
+        in_next_ += n;
+        stored_left_ -= n;
+        if (stored_left_) return have == n && have < room ? TRUNCATED : NEED_OUTPUT;
+        state_ = final_ ? ST_DONE : ST_HEADER;
+        break;
+      }
+      case ST_CODES: {
+        Status s = block_loop<true>(out_begin, out_next, out_end);
+        if (s == NEED_OUTPUT) s = block_loop<false>(out_begin, out_next, out_end);   // near an end of input or output
+        if (s != DONE) return s;
+        break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- gzip framing
+size_t GzipMember::header_length(const uint8_t* p, size_t n) {
+  if (n < 10) return (size_t)-1;
+  if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xe0)) return 0;
+  const unsigned flg = p[3];
+  size_t at = 10;
+  if (flg & 4) {   // FEXTRA
+    if (n < at + 2) return (size_t)-1;
+    at += 2 + (p[at] | ((size_t)p[at + 1] << 8));
+    if (n < at) return (size_t)-1;
+  }
+  for (unsigned f = 8; f <= 16; f <<= 1) {   // FNAME, FCOMMENT: zero-terminated
+    if (!(flg & f)) continue;
+    while (at < n && p[at]) ++at;
+    if (at >= n) return (size_t)-1;
+    ++at;
+  }
+  if (flg & 2) at += 2;   // FHCRC
+  return at <= n ? at : (size_t)-1;
+}
+
+// ---------------------------------------------------------------- CRC-32
+namespace {
+
+uint32_t g_crc_table[8][256];
+struct CrcInit {
+  CrcInit() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+      g_crc_table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
+  }
+} g_crc_init;
+
+uint32_t crc32_slice8(uint32_t c, const uint8_t* p, size_t n) {   // c is the running (inverted) register
+  while (n >= 8) {
+    const uint64_t v = load64(p) ^ c;
+    c = g_crc_table[7][v & 0xff] ^ g_crc_table[6][(v >> 8) & 0xff] ^ g_crc_table[5][(v >> 16) & 0xff] ^ g_crc_table[4][(v >> 24) & 0xff] ^
+        g_crc_table[3][(v >> 32) & 0xff] ^ g_crc_table[2][(v >> 40) & 0xff] ^ g_crc_table[1][(v >> 48) & 0xff] ^ g_crc_table[0][v >> 56];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ g_crc_table[0][(c ^ *p++) & 0xff];
+  return c;
+}
+
+#if defined(__x86_64__)
+// Folding by carry-less multiplication (Gopal et al., "Fast CRC computation for generic polynomials using
+// PCLMULQDQ"), constants of the reflected gzip polynomial.  n >= 64, n % 16 == 0.
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul(uint32_t c, const uint8_t* p, size_t n) {
+  const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4);
+  const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0);
+  const __m128i k5k0 = _mm_set_epi64x(0, 0x0163cd6124);
+  const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641);
+  __m128i x1 = _mm_loadu_si128((const __m128i*)(p + 0)), x2 = _mm_loadu_si128((const __m128i*)(p + 16));
+  __m128i x3 = _mm_loadu_si128((const __m128i*)(p + 32)), x4 = _mm_loadu_si128((const __m128i*)(p + 48));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)c));
+  p += 64;
+  n -= 64;
+  while (n >= 64) {
+    const __m128i a1 = _mm_clmulepi64_si128(x1, k1k2, 0x00), a2 = _mm_clmulepi64_si128(x2, k1k2, 0x00);
+    const __m128i a3 = _mm_clmulepi64_si128(x3, k1k2, 0x00), a4 = _mm_clmulepi64_si128(x4, k1k2, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, k1k2, 0x11);
+    x2 = _mm_clmulepi64_si128(x2, k1k2, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, k1k2, 0x11);
+    x4 = _mm_clmulepi64_si128(x4, k1k2, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, a1), _mm_loadu_si128((const __m128i*)(p + 0)));
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, a2), _mm_loadu_si128((const __m128i*)(p + 16)));
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, a3), _mm_loadu_si128((const __m128i*)(p + 32)));
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, a4), _mm_loadu_si128((const __m128i*)(p + 48)));
+    p += 64;
+    n -= 64;
+  }
+#define MGK_FOLD(next)                                          \
+  do {                                                          \
+    const __m128i a_ = _mm_clmulepi64_si128(x1, k3k4, 0x00);    \
+    x1 = _mm_clmulepi64_si128(x1, k3k4, 0x11);                  \
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, (next)), a_);          \
+  } while (0)
+  MGK_FOLD(x2);
+  MGK_FOLD(x3);
+  MGK_FOLD(x4);
+  while (n >= 16) {
+    MGK_FOLD(_mm_loadu_si128((const __m128i*)p));
+    p += 16;
+    n -= 16;
+  }
+#undef MGK_FOLD
+  const __m128i mask = _mm_setr_epi32(~0, 0, ~0, 0);
+  __m128i t = _mm_clmulepi64_si128(x1, k3k4, 0x10);
+  x1 = _mm_xor_si128(_mm_srli_si128(x1, 8), t);
+  t = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, mask);
+  x1 = _mm_xor_si128(_mm_clmulepi64_si128(x1, k5k0, 0x00), t);
+  t = _mm_and_si128(x1, mask);
+  t = _mm_clmulepi64_si128(t, poly, 0x10);
+  t = _mm_and_si128(t, mask);
+  t = _mm_clmulepi64_si128(t, poly, 0x00);
+  x1 = _mm_xor_si128(x1, t);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+}  // namespace
+
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n) {
+  uint32_t c = ~crc;
+#if defined(__x86_64__)
+  static const bool have_clmul = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+  if (have_clmul && n >= 64) {
+    const size_t body = n & ~(size_t)15;
+    c = crc32_clmul(c, p, body);
+    p += body;
+    n -= body;
+  }
+#endif
+  return ~crc32_slice8(c, p, n);
+}
+
+}  // namespace mgikit

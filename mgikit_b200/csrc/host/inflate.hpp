@@ -1,0 +1,67 @@
+// Table-driven inflate (RFC 1951) + gzip member framing (RFC 1952) for the input side of the
+// pump.  Replaces flate2::MultiGzDecoder of the reference's reader threads
+// (/root/reference/src/file_utils.rs:231-233, :99-164, :239-373, :542-638).
+//
+// Design: 64-bit bit buffer with a branch-free refill, an 11-bit primary literal/length table
+// (literals resolved two or three per refill: FASTQ out of `gzip -1` is literal-heavy), an
+// 8-bit primary distance table, subtables for the long codes, word-wide match copies.  A
+// stream can be suspended at a symbol boundary when the output buffer is full and resumed
+// into the next buffer (the caller carries the last 32 KiB over), so a member of any size
+// streams through fixed-size buffers; members of a multi-member file decode in parallel.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+namespace mgikit {
+
+constexpr size_t INFLATE_WINDOW = 32768;   // how far a match may reach back
+
+class Inflater {
+ public:
+  enum Status { DONE = 0, NEED_OUTPUT = 1, BAD_DATA = 2, TRUNCATED = 3 };
+
+  // [in, in + n) holds the raw deflate stream (it may be followed by anything); nothing outside is read
+  void reset(const uint8_t* in, size_t n);
+  // Decodes into [*out_next, out_end).  [out_begin, *out_next) must hold what the stream produced before
+  // (all of it, or at least its last INFLATE_WINDOW bytes).  NEED_OUTPUT: fewer than 258 bytes are left in
+  // the buffer at a symbol boundary; call again with a new buffer.
+  Status run(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end);
+  // bytes of input consumed up to the end of the final block (valid after DONE)
+  size_t consumed() const { return (size_t)(in_next_ - in_begin_) - (bitcnt_ >> 3); }
+  const char* error() const { return err_; }
+
+ private:
+  template <bool FAST>
+  Status block_loop(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end);
+  Status read_block_header();
+  bool build_tables(const uint8_t* lens, unsigned n_lit, unsigned n_dist);
+
+  const uint8_t *in_begin_ = nullptr, *in_next_ = nullptr, *in_end_ = nullptr;
+  uint64_t bitbuf_ = 0;
+  unsigned bitcnt_ = 0;
+  enum { ST_HEADER, ST_STORED, ST_CODES, ST_DONE } state_ = ST_HEADER;
+  bool final_ = false;
+  size_t stored_left_ = 0;
+  const char* err_ = "";
+  // decode tables: entry layout in inflate.cpp
+  static constexpr unsigned LIT_BITS = 11, DIST_BITS = 8;
+  uint32_t lit_[(1u << LIT_BITS) + 1024];    // primary + subtables (at most 288 long codes' worth)
+  uint32_t dist_[(1u << DIST_BITS) + 512];
+};
+
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n);   // gzip CRC-32 (PCLMULQDQ folding when the CPU has it)
+
+// One gzip member: header parsing, the deflate stream, CRC-32 + ISIZE check.
+struct GzipMember {
+  // Parses the header at [p, p + n); returns its length, 0 if this is not a gzip (deflate) member header,
+  // or (size_t)-1 if it is cut off.
+  static size_t header_length(const uint8_t* p, size_t n);
+  // magic + method + reserved flag bits: cheap test of a candidate member start
+  static bool plausible(const uint8_t* p, size_t n) {
+    return n >= 18 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 0xe0) == 0;
+  }
+};
+
+}  // namespace mgikit
