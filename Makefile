@@ -14,7 +14,7 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xp
 CXXFLAGS  := -O2 -std=c++17 -Wall -Wextra -pthread -fPIC
 H         := mgikit_b200/csrc/host
 G         := mgikit_b200/csrc/gpu
-HOST_SRC  := $(H)/cli.cpp $(H)/pipeline.cpp $(H)/report.cpp $(H)/run_info.cpp $(H)/sample_sheet.cpp $(H)/log.cpp $(H)/template_cmd.cpp
+HOST_SRC  := $(H)/cli.cpp $(H)/pipeline.cpp $(H)/report.cpp $(H)/run_info.cpp $(H)/sample_sheet.cpp $(H)/log.cpp $(H)/template_cmd.cpp $(H)/inflate.cpp $(H)/gz_reader.cpp
 HOST_HDR  := $(wildcard $(H)/*.hpp) include/mgikit_gpu.h
 GPU_SRC   := $(wildcard $(G)/*.cu)
 GPU_HDR   := $(wildcard $(G)/*.cuh) include/mgikit_gpu.h

@@ -65,6 +65,8 @@ const Opt OPTS[] = {
     {"log-level", 'l', true, "info", nullptr},
     {"gpus", 0, true, "1", nullptr},
     {"chunk-size", 0, true, "67108864", nullptr},
+    {"slots", 0, true, "4", nullptr},
+    {"host-gzip", 0, false, "false", nullptr},
 };
 
 // `template` subcommand, src/main.rs:400-511
@@ -296,6 +298,9 @@ int cli_main(int argc, char** argv, const Backend& be) {
     opt.threads = (int)parse_usize("threads", val["threads"]);
     opt.gpus = (int)parse_usize("gpus", val["gpus"]);
     opt.chunk_bytes = parse_usize("chunk-size", val["chunk-size"]);
+    opt.slots = (int)parse_usize("slots", val["slots"]);
+    opt.reader_threads = (int)parse_usize("reader-threads", val["reader-threads"]);
+    opt.host_gzip = flag("host-gzip");
     log_info("Reporting level is: " + std::to_string(opt.report_level));
     run_demultiplex(be, sheet, run, opt);
   } catch (const std::exception& e) {

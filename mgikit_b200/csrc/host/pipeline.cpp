@@ -8,10 +8,13 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <map>
+#include <unordered_map>
 #include <memory>
 #include <mutex>
 #include <thread>
 
+#include "gz_reader.hpp"
 #include "log.hpp"
 
 namespace mgikit {
@@ -19,6 +22,8 @@ namespace mgikit {
 namespace {
 
 // ---------------------------------------------------------------- thread pool
+// Plain task queue: the codec tasks of several chunks are in flight at once, nobody waits for a chunk's tasks as a
+// group (the last task of a chunk hands the chunk on).
 class ThreadPool {
  public:
   explicit ThreadPool(int n) {
@@ -32,47 +37,31 @@ class ThreadPool {
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
-  // run fn(i) for i in [0,n), return when all are done; first exception is rethrown
-  void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
-    if (n == 0) return;
-    std::unique_lock<std::mutex> lk(mu_);
-    fn_ = &fn;
-    next_ = 0;
-    total_ = n;
-    done_ = 0;
-    error_ = nullptr;
-    cv_.notify_all();
-    done_cv_.wait(lk, [this] { return done_ == total_; });
-    fn_ = nullptr;
-    if (error_) std::rethrow_exception(error_);
+  void submit(std::function<void()> fn) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(fn));
+    }
+    cv_.notify_one();
   }
 
  private:
   void loop() {
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
-      cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < total_); });
-      if (stop_) return;
-      const size_t i = next_++;
-      const auto* fn = fn_;
+      cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+      if (q_.empty()) return;   // stop_ and drained
+      std::function<void()> fn = std::move(q_.front());
+      q_.pop_front();
       lk.unlock();
-      std::exception_ptr err;
-      try {
-        (*fn)(i);
-      } catch (...) {
-        err = std::current_exception();
-      }
+      fn();   // tasks catch their own exceptions
       lk.lock();
-      if (err && !error_) error_ = err;
-      if (++done_ == total_) done_cv_.notify_all();
     }
   }
   std::vector<std::thread> workers_;
   std::mutex mu_;
-  std::condition_variable cv_, done_cv_;
-  const std::function<void(size_t)>* fn_ = nullptr;
-  size_t next_ = 0, total_ = 0, done_ = 0;
-  std::exception_ptr error_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
   bool stop_ = false;
 };
 
@@ -85,13 +74,14 @@ struct Block {
   std::string error;
 };
 
-// One reader thread per input file: gunzip into pinned buffers, cut every
-// block after exactly `records_per_block` records (fill_send_buffers,
-// src/file_utils.rs:99-164: truncate to batch_size*4 lines, carry the tail).
+// One assembler thread per input file on top of the member-parallel gunzip (gz_reader.hpp): decoded pieces are
+// copied into pinned buffers and every block is cut after exactly `records_per_block` records (fill_send_buffers,
+// src/file_utils.rs:99-164: truncate to batch_size*4 lines, carry the tail).  The pieces arrive with their newline
+// counts, so only the piece a cut falls into is scanned.
 class BlockReader {
  public:
-  BlockReader(const std::string& path, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be)
-      : path_(path), cap_(capacity), rpb_(records_per_block), be_(be) {
+  BlockReader(const std::string& path, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be, int decode_threads)
+      : path_(path), cap_(capacity), rpb_(records_per_block), be_(be), decode_threads_(decode_threads) {
     for (int i = 0; i < n_buffers; ++i) {
       auto* p = (uint8_t*)be_.host_alloc(cap_);
       if (!p) throw Fatal("can not allocate chunk buffers");
@@ -140,82 +130,107 @@ class BlockReader {
     free_.pop_front();
     return p;
   }
-  void run() {
-    gzFile g = gzopen(path_.c_str(), "rb");
-    if (!g) {
-      Block b;
-      b.last = true;
-      b.error = "Could not open the file";
-      push(b);
-      return;
-    }
-    gzbuffer(g, 1u << 20);
-    std::vector<uint8_t> carry;
-    bool eof = false;
-    while (!eof || !carry.empty()) {
-      uint8_t* buf = take();
-      if (!buf) break;
-      size_t have = carry.size();
-      if (have) memcpy(buf, carry.data(), have);
-      carry.clear();
-      while (!eof && have < cap_) {
-        const size_t want = std::min(cap_ - have, (size_t)1 << 30);
-        int got = gzread(g, buf + have, (unsigned)want);
-        if (got < 0) {
-          Block b;
-          b.last = true;
-          b.error = "corrupt gzip input: " + path_;
-          push(b);
-          gzclose(g);
-          return;
-        }
-        if (got == 0) {
-          eof = true;
-          if (have && buf[have - 1] != '\n' && have < cap_) buf[have++] = '\n';
-          break;
-        }
-        have += (size_t)got;
-      }
-      // cut after the (4*rpb_)-th newline, or after the last 4k-th one
-      size_t lines = 0, cut = 0;
-      const uint8_t* s = buf;
-      const uint8_t* end = buf + have;
-      while (s < end && lines < 4 * rpb_) {
-        const uint8_t* q = (const uint8_t*)memchr(s, '\n', (size_t)(end - s));
-        if (!q) break;
-        ++lines;
-        s = q + 1;
-        if ((lines & 3) == 0) cut = (size_t)(s - buf);
-      }
-      Block b;
-      b.data = buf;
-      b.len = cut;
-      b.n_records = lines / 4;
-      if (cut < have) carry.assign(buf + cut, buf + have);
-      if (b.n_records == 0) {
-        if (!eof) {
-          b.error = "a read record does not fit into one chunk buffer; increase the chunk size";
-          b.last = true;
-          push(b);
-          break;
-        }
-        carry.clear();  // trailing partial record at end of file: nothing more to pair
-      }
-      b.last = eof && carry.empty();
-      push(b);
-      if (b.last) {
-        gzclose(g);
-        return;
-      }
-    }
-    gzclose(g);
+  void fail(const std::string& why) {
     Block b;
     b.last = true;
+    b.error = why;
     push(b);
+  }
+  void run() {
+    try {
+      GzReader gz(path_, decode_threads_);
+      GzPiece piece;           // the piece being copied out, from `at` on
+      size_t at = 0, piece_nl = 0;
+      bool have_piece = false, eof = false;
+      std::vector<uint8_t> carry;
+      size_t carry_nl = 0;
+      const size_t target = 4 * rpb_;
+      while (!eof || !carry.empty() || have_piece) {
+        uint8_t* buf = take();
+        if (!buf) break;
+        size_t have = carry.size(), lines = carry_nl;
+        if (have) memcpy(buf, carry.data(), have);
+        carry.clear();
+        carry_nl = 0;
+        while (lines < target && have < cap_) {
+          if (!have_piece) {
+            if (eof || !gz.next(piece)) {
+              eof = true;
+              break;
+            }
+            have_piece = true;
+            at = 0;
+            piece_nl = piece.newlines;
+          }
+          const size_t left = piece.len - at;
+          size_t take_n = left, take_nl = piece_nl;
+          if (lines + piece_nl > target) {   // the cut falls into this piece: up to the newline that completes the block
+            const uint8_t* s = piece.data + at;
+            size_t need = target - lines;
+            take_nl = need;
+            while (need) {
+              s = (const uint8_t*)memchr(s, '\n', (size_t)(piece.data + piece.len - s)) + 1;
+              --need;
+            }
+            take_n = (size_t)(s - (piece.data + at));
+          }
+          if (take_n > cap_ - have) {   // buffer full first (records longer than the first one): whatever fits
+            take_n = cap_ - have;
+            take_nl = 0;
+            for (const uint8_t *s = piece.data + at, *e = s + take_n; (s = (const uint8_t*)memchr(s, '\n', (size_t)(e - s))) != nullptr; ++s) ++take_nl;
+          }
+          memcpy(buf + have, piece.data + at, take_n);
+          have += take_n;
+          lines += take_nl;
+          at += take_n;
+          piece_nl -= take_nl;
+          if (at == piece.len) {
+            gz.recycle(piece);
+            have_piece = false;
+          }
+        }
+        if (eof && have && buf[have - 1] != '\n' && have < cap_) {
+          buf[have++] = '\n';
+          ++lines;
+        }
+        Block b;
+        b.data = buf;
+        size_t cut = have;
+        if (lines == target || (eof && (lines & 3) == 0)) {
+          b.n_records = lines / 4;
+        } else {   // full buffer or ragged end of file: back to the last newline that closes a record
+          size_t n = 0, last4 = 0;
+          for (const uint8_t *s = buf, *e = buf + have; (s = (const uint8_t*)memchr(s, '\n', (size_t)(e - s))) != nullptr; ++s)
+            if ((++n & 3) == 0) last4 = (size_t)(s - buf) + 1;
+          cut = last4;
+          b.n_records = n / 4;
+          carry_nl = n - 4 * b.n_records;
+        }
+        b.len = cut;
+        if (cut < have) carry.assign(buf + cut, buf + have);
+        if (b.n_records == 0) {
+          if (!(eof && !have_piece)) {
+            fail("a read record does not fit into one chunk buffer; increase the chunk size");
+            return;
+          }
+          carry.clear();  // trailing partial record at end of file: nothing more to pair
+          carry_nl = 0;
+        }
+        b.last = eof && !have_piece && carry.empty();
+        push(b);
+        if (b.last) return;
+      }
+      Block b;
+      b.last = true;
+      push(b);
+    } catch (const std::exception& e) {
+      fail(e.what());
+    }
   }
   std::string path_;
   size_t cap_, rpb_;
   const Backend& be_;
+  int decode_threads_;
   std::vector<uint8_t*> all_;
   std::deque<uint8_t*> free_;
   std::deque<Block> ready_;
@@ -269,27 +284,76 @@ void gzip_member(const uint8_t* src, size_t n, int level, std::vector<uint8_t>& 
 }
 
 // write_data(), src/sample_data.rs:492-503: open(append)/write/close
-void append_file(const std::string& path, const std::vector<uint8_t>& data) {
+void append_file(const std::string& path, const uint8_t* data, size_t n) {
   FILE* f = fopen(path.c_str(), "ab");
   if (!f) throw Fatal("couldn't create output");
-  const size_t w = fwrite(data.data(), 1, data.size(), f);
+  const size_t w = fwrite(data, 1, n, f);
   fclose(f);
-  if (w != data.size()) throw Fatal("couldn't flush output");
+  if (w != n) throw Fatal("couldn't flush output");
 }
 
-void compress_append(const uint8_t* src, size_t n, int level, const std::string& path) {
+void compress_segment(const uint8_t* src, size_t n, int level, std::vector<uint8_t>& out) {
   const size_t piece = (size_t)1 << 30;  // zlib counts in 32 bit
+  out.clear();
   std::vector<uint8_t> z;
   for (size_t off = 0; off < n; off += piece) {
     gzip_member(src + off, std::min(piece, n - off), level, z);
-    append_file(path, z);
+    if (off == 0 && n <= piece) {
+      out.swap(z);
+      return;
+    }
+    out.insert(out.end(), z.begin(), z.end());
   }
 }
 
-struct InFlight {
-  uint64_t seq;
-  int ctx;
+// One chunk on its way through the host side: submitted -> collected -> codec tasks -> committed -> released.
+struct ChunkJob {
+  uint64_t seq = 0;
+  int ctx = 0;
   Block b2, b1;
+  mgk_result res{};
+  struct Part {
+    const uint8_t* p;
+    size_t n;
+    const std::string* path;
+    std::vector<uint8_t> z;   // gzip member(s) made on the host; empty when the device already made them
+  };
+  std::vector<Part> parts;
+  std::unordered_map<std::string, uint64_t> und, amb;   // this chunk's share of the barcode histograms
+  std::atomic<int> pending{0};
+  std::mutex err_mu;
+  std::string error;
+};
+
+template <typename T>
+class Channel {
+ public:
+  void push(T v) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(v));
+    }
+    cv_.notify_all();
+  }
+  bool try_pop(T& v) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (q_.empty()) return false;
+    v = std::move(q_.front());
+    q_.pop_front();
+    return true;
+  }
+  T pop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [this] { return !q_.empty(); });
+    T v = std::move(q_.front());
+    q_.pop_front();
+    return v;
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
 };
 
 }  // namespace
@@ -356,7 +420,7 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
   const size_t rpb = std::max<size_t>(1, (size_t)(0.95 * (double)chunk_bytes / (double)rec_len));
   plan.cfg.max_chunk_bytes = chunk_bytes;
   plan.cfg.max_chunk_records = rpb + 16;
-  plan.cfg.n_slots = 2;
+  plan.cfg.n_slots = std::max(2, std::min(8, opt.slots));
 
   const int G = std::max(1, opt.gpus);
   std::vector<void*> ctxs((size_t)G, nullptr);
@@ -378,104 +442,208 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
 
   int n_threads = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
   if (n_threads < 1) n_threads = 1;
-  log_info("Hot path: " + std::string(be.name) + " on " + std::to_string(G) + " device(s); chunk = " +
-           std::to_string(rpb) + " reads; host codec threads = " + std::to_string(n_threads));
+  // the device makes the gzip members itself at the default level; any other level is zlib on the host threads
+  const bool device_gzip = be.gzip_flag != 0 && opt.compression_level == 1 && !opt.host_gzip;
+  const uint32_t submit_flags = device_gzip ? be.gzip_flag : 0u;
+  const int decode_threads = std::max(1, opt.reader_threads > 0 ? opt.reader_threads : n_threads / (paired ? 2 : 1));
+  log_info("Hot path: " + std::string(be.name) + " on " + std::to_string(G) + " device(s); chunk = " + std::to_string(rpb) +
+           " reads; host threads: " + std::to_string(decode_threads) + " inflate per input file, " + std::to_string(n_threads) +
+           (device_gzip ? " for the output (gzip members are made on the device)" : " deflate"));
 
   ReportData report(total, m);
   try {
-    const int max_in_flight = G * plan.cfg.n_slots;
+    const int slots = plan.cfg.n_slots;
+    const int max_in_flight = G * slots;
     const int n_buffers = max_in_flight + 2;
-    BlockReader rd2(run.barcode_reads, chunk_bytes, rpb, n_buffers, be);
+    BlockReader rd2(run.barcode_reads, chunk_bytes, rpb, n_buffers, be, decode_threads);
     std::unique_ptr<BlockReader> rd1;
-    if (paired) rd1.reset(new BlockReader(run.paired_reads, chunk_bytes, rpb, n_buffers, be));
-    ThreadPool pool(n_threads);
+    if (paired) rd1.reset(new BlockReader(run.paired_reads, chunk_bytes, rpb, n_buffers, be, decode_threads));
 
-    std::deque<InFlight> fifo;
     const bool single_template = sheet.templates.size() == 1;
     const auto& g0 = sheet.templates[0].geometry;
+    Channel<ChunkJob*> to_commit, finished;
+    std::atomic<bool> failed{false};
 
-    auto finish_oldest = [&] {
-      InFlight f = fifo.front();
+    // ---- committer: appends the chunks' members to the sample files in chunk order (per-sample order == input
+    // order for any number of devices) and merges the barcode histograms; then hands the chunk back to the pump
+    std::thread committer([&] {
+      std::map<uint64_t, ChunkJob*> waiting;
+      uint64_t next_seq = 0;
+      for (;;) {
+        ChunkJob* j = to_commit.pop();
+        if (!j) break;
+        waiting[j->seq] = j;
+        while (!waiting.empty() && waiting.begin()->first == next_seq) {
+          ChunkJob* c = waiting.begin()->second;
+          waiting.erase(waiting.begin());
+          ++next_seq;
+          if (c->error.empty() && !failed.load()) {
+            try {
+              for (auto& part : c->parts)   // write_data(), src/sample_data.rs:492-503: open(append)/write/close
+                append_file(*part.path, part.z.empty() ? part.p : part.z.data(), part.z.empty() ? part.n : part.z.size());
+              for (auto& kv : c->und) report.undetermined_barcodes[kv.first] += kv.second;
+              for (auto& kv : c->amb) report.ambiguous_barcodes[kv.first] += kv.second;
+            } catch (const std::exception& e) {
+              c->error = e.what();
+            }
+          }
+          if (!c->error.empty()) failed.store(true);
+          finished.push(c);
+        }
+      }
+    });
+    ThreadPool pool(n_threads);
+
+    auto last_task_done = [&](ChunkJob* j) {
+      if (j->pending.fetch_sub(1) == 1) to_commit.push(j);
+    };
+    auto task_error = [&](ChunkJob* j, const std::string& why) {
+      std::lock_guard<std::mutex> lk(j->err_mu);
+      if (j->error.empty()) j->error = why;
+    };
+
+    std::deque<ChunkJob*> fifo;                    // submitted, not collected (oldest first)
+    std::vector<int> busy((size_t)G, 0);           // slots of a context that are not free (submitted .. released)
+    std::vector<int> uncollected((size_t)G, 0);
+    size_t held = 0;                               // collected, not yet released
+
+    auto collect_oldest = [&] {
+      ChunkJob* j = fifo.front();
       fifo.pop_front();
-      void* ctx = ctxs[(size_t)f.ctx];
-      mgk_result res;
+      --uncollected[(size_t)j->ctx];
+      void* ctx = ctxs[(size_t)j->ctx];
+      ++held;
+      mgk_result& res = j->res;
       if (be.collect(ctx, &res) != MGK_OK) throw Fatal(std::string("hot path failed: ") + be.last_error(ctx));
       if (res.validate_error != MGK_VAL_OK) {
         static const char* what[] = {"", "Read header must starts with '@'!",
                                      "Seqeunce bases need to be in [A, C, G, T, a, c, g, t, N, n]!",
                                      "Quality score must be between [0 and 40]!", "Headers seem to be in differnet orders"};
         throw Fatal(std::string(what[res.validate_error]) + " (read " + std::to_string(res.validate_record) +
-                    " of chunk " + std::to_string(f.seq) + ")");
+                    " of chunk " + std::to_string(j->seq) + ")");
       }
-      if (res.n_records != f.b2.n_records || res.consumed_r2 != f.b2.len || (paired && res.consumed_r1 != f.b1.len))
+      if (res.n_records != j->b2.n_records || res.consumed_r2 != j->b2.len || (paired && res.consumed_r1 != j->b1.len))
         throw Fatal("Something wrong in the input files!");
-      // undetermined / ambiguous barcode histograms, src/lib.rs:1048-1088
-      for (uint64_t k = 0; k < res.n_unassigned; ++k) {
-        const uint32_t v = res.unassigned[k];
-        const uint8_t* bar = f.b2.data + (v & 0x7fffffffu);
-        std::string label;
-        if (single_template) {
-          label.assign((const char*)bar + BL - g0[2], (size_t)g0[1]);
-          if (g0[3] == 1) {
-            label.push_back('+');
-            label.append((const char*)bar + BL - g0[5], (size_t)g0[4]);
-          }
-        } else {
-          label.assign((const char*)bar, (size_t)BL);
-        }
-        if (v & 0x80000000u) report.ambiguous_barcodes[label] += 1;
-        else report.undetermined_barcodes[label] += 1;
-      }
-      // per-sample segments -> gzip members -> append (compress_and_write, src/sample_data.rs:180-207)
-      struct Task {
-        const uint8_t* p;
-        size_t n;
-        const std::string* path;
-      };
-      std::vector<Task> tasks;
+      // per-sample segments -> gzip members (compress_and_write, src/sample_data.rs:180-207), one task each
       for (int b = 0; b < total; ++b) {
         if (res.seg_len_r2[b]) {
           if (files[(size_t)b].barcode_path.empty()) throw Fatal("Read must attached to a specific sample!");
-          tasks.push_back({res.out_r2 + res.seg_off_r2[b], (size_t)res.seg_len_r2[b], &files[(size_t)b].barcode_path});
+          j->parts.push_back({res.out_r2 + res.seg_off_r2[b], (size_t)res.seg_len_r2[b], &files[(size_t)b].barcode_path, {}});
         }
         if (paired && res.seg_len_r1[b]) {
           if (files[(size_t)b].paired_path.empty()) throw Fatal("Read must attached to a specific sample!");
-          tasks.push_back({res.out_r1 + res.seg_off_r1[b], (size_t)res.seg_len_r1[b], &files[(size_t)b].paired_path});
+          j->parts.push_back({res.out_r1 + res.seg_off_r1[b], (size_t)res.seg_len_r1[b], &files[(size_t)b].paired_path, {}});
         }
       }
-      pool.parallel_for(tasks.size(), [&](size_t i) {
-        compress_append(tasks[i].p, tasks[i].n, opt.compression_level, *tasks[i].path);
-      });
-      if (be.release(ctx, f.seq) != MGK_OK) throw Fatal(std::string("hot path failed: ") + be.last_error(ctx));
-      rd2.give_back(f.b2.data);
-      if (paired) rd1->give_back(f.b1.data);
+      const bool histogram = res.n_unassigned > 0;
+      const size_t n_codec = device_gzip ? 0 : j->parts.size();
+      j->pending.store((int)n_codec + (histogram ? 1 : 0) + 1);
+      if (histogram)   // undetermined / ambiguous barcode histograms, src/lib.rs:1048-1088
+        pool.submit([&, j] {
+          try {
+            const mgk_result& r = j->res;
+            std::string label;
+            for (uint64_t k = 0; k < r.n_unassigned; ++k) {
+              const uint32_t v = r.unassigned[k];
+              const uint8_t* bar = j->b2.data + (v & 0x7fffffffu);
+              if (single_template) {
+                label.assign((const char*)bar + BL - g0[2], (size_t)g0[1]);
+                if (g0[3] == 1) {
+                  label.push_back('+');
+                  label.append((const char*)bar + BL - g0[5], (size_t)g0[4]);
+                }
+              } else {
+                label.assign((const char*)bar, (size_t)BL);
+              }
+              ((v & 0x80000000u) ? j->amb : j->und)[label] += 1;
+            }
+          } catch (const std::exception& e) {
+            task_error(j, e.what());
+          }
+          last_task_done(j);
+        });
+      for (size_t i = 0; i < n_codec; ++i)
+        pool.submit([&, j, i] {
+          try {
+            if (!failed.load()) compress_segment(j->parts[i].p, j->parts[i].n, opt.compression_level, j->parts[i].z);
+          } catch (const std::exception& e) {
+            task_error(j, e.what());
+          }
+          last_task_done(j);
+        });
+      last_task_done(j);   // the chunk's own count: it moves on even when it has no task at all
+    };
+    auto release = [&](ChunkJob* j) {
+      void* ctx = ctxs[(size_t)j->ctx];
+      const std::string err = j->error;
+      const int rc = be.release(ctx, j->seq);
+      rd2.give_back(j->b2.data);
+      if (paired) rd1->give_back(j->b1.data);
+      --busy[(size_t)j->ctx];
+      --held;
+      delete j;
+      if (!err.empty()) throw Fatal(err);
+      if (rc != MGK_OK) throw Fatal(std::string("hot path failed: ") + be.last_error(ctx));
     };
 
-    uint64_t seq = 0;
-    for (;;) {
-      Block b2 = rd2.next();
-      Block b1;
-      if (paired) b1 = rd1->next();
-      if (!b2.error.empty()) throw Fatal(b2.error);
-      if (paired && !b1.error.empty()) throw Fatal(b1.error);
-      if (paired && b2.n_records != b1.n_records) throw Fatal("Something wrong in the input files!");  // src/lib.rs:1490-1494
-      if (b2.n_records > 0) {
-        if ((int)fifo.size() == max_in_flight) finish_oldest();
+    std::string pump_error;
+    try {
+      uint64_t seq = 0;
+      bool input_done = false;
+      while (!input_done || !fifo.empty() || held) {
+        ChunkJob* done = nullptr;
+        while (finished.try_pop(done)) release(done);
         const int g = (int)(seq % (uint64_t)G);
-        if (be.submit(ctxs[(size_t)g], seq, b2.data, b2.len, paired ? b1.data : nullptr, paired ? b1.len : 0, 0) != MGK_OK)
-          throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[(size_t)g]));
-        fifo.push_back({seq, g, b2, b1});
-        ++seq;
-      } else {
-        if (b2.data) rd2.give_back(b2.data);
-        if (paired && b1.data) rd1->give_back(b1.data);
+        if (!input_done && busy[(size_t)g] < slots && uncollected[(size_t)g] < 2) {
+          Block b2 = rd2.next();
+          Block b1;
+          if (paired) b1 = rd1->next();
+          if (!b2.error.empty()) throw Fatal(b2.error);
+          if (paired && !b1.error.empty()) throw Fatal(b1.error);
+          if (paired && b2.n_records != b1.n_records) throw Fatal("Something wrong in the input files!");  // src/lib.rs:1490-1494
+          if (b2.n_records > 0) {
+            if (be.submit(ctxs[(size_t)g], seq, b2.data, b2.len, paired ? b1.data : nullptr, paired ? b1.len : 0, submit_flags) != MGK_OK)
+              throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[(size_t)g]));
+            ChunkJob* j = new ChunkJob();
+            j->seq = seq;
+            j->ctx = g;
+            j->b2 = b2;
+            j->b1 = b1;
+            fifo.push_back(j);
+            ++busy[(size_t)g];
+            ++uncollected[(size_t)g];
+            ++seq;
+          } else {
+            if (b2.data) rd2.give_back(b2.data);
+            if (paired && b1.data) rd1->give_back(b1.data);
+          }
+          if (b2.last || (paired && b1.last)) {
+            if (paired && b2.last != b1.last) throw Fatal("Something wrong in the input files!");
+            input_done = true;
+          }
+        } else if (!fifo.empty()) {
+          collect_oldest();
+        } else if (held) {
+          release(finished.pop());
+        }
       }
-      if (b2.last || (paired && b1.last)) {
-        if (paired && b2.last != b1.last) throw Fatal("Something wrong in the input files!");
-        break;
+    } catch (const std::exception& e) {
+      pump_error = e.what();
+      failed.store(true);
+    }
+    // drain: chunks still with the workers come back through the committer; chunks never collected are dropped
+    while (held) {
+      ChunkJob* j = finished.pop();
+      try {
+        release(j);
+      } catch (const std::exception& e) {
+        if (pump_error.empty()) pump_error = e.what();
       }
     }
-    while (!fifo.empty()) finish_oldest();
+    to_commit.push(nullptr);
+    committer.join();
+    for (ChunkJob* j : fifo) delete j;
+    if (!pump_error.empty()) throw Fatal(pump_error);
 
     // ReportManager::update across workers (src/lib.rs:819-827) == sum over devices
     std::vector<uint64_t> stats((size_t)total * MGK_N_STATS), mism((size_t)total * (size_t)(2 * m + 2));

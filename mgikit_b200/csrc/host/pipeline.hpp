@@ -31,6 +31,7 @@ struct Backend {
   int (*reduced_counters)(void*, uint64_t*, uint64_t*);
   void* (*host_alloc)(size_t);
   void (*host_free)(void*);
+  uint32_t gzip_flag;   // mgk_submit flag that makes the device return gzip members (0: the backend has none)
 };
 
 struct DemuxOptions {
@@ -42,6 +43,9 @@ struct DemuxOptions {
   int threads = 0;          // -t: host codec threads (0 = all cores)
   int gpus = 1;             // --gpus (extension): chunk k goes to GPU k % gpus
   size_t chunk_bytes = 64u << 20;  // decompressed bytes per read file per chunk
+  int slots = 4;            // chunks per GPU between submit and release (>= 2)
+  int reader_threads = 0;   // --reader-threads: inflate threads per input file (0 = share of -t)
+  bool host_gzip = false;   // --host-gzip (extension): gzip on the host threads even at the default level
 };
 
 // Runs the whole command; throws Fatal on any error the reference would panic on.

@@ -1,0 +1,215 @@
+#!/usr/bin/env python
+"""File-level end to end (bullet 1): `.fq.gz` in -> per-sample `.fastq.gz` + reports out,
+the drop-in CLI next to the reference's own binary ON THE SAME FILES, same box, thread counts stated.
+
+The lane is block-streamed (block b is a pure function of (seed, b), synth.make_block) and written as one gzip
+member per block by a pool of processes -- the multi-member layout of bgzip / pigz -i / concatenated lanes /
+mgikit's own output, which both binaries read (the reference through flate2's MultiGzDecoder).  Parity inside
+the bench: every report file of the full run byte-identical to the reference's, and every FASTQ (decompressed)
+of a prefix lane identical to the reference at -t 1 (its multi-threaded FASTQ order is arbitrary).
+
+  python tools/file_bench.py [pairs]            prints the JSON block bench.py embeds as `e2e_files`
+"""
+from __future__ import annotations
+
+import gzip
+import hashlib
+import json
+import multiprocessing as mp
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BLOCK_PAIRS = 250_000
+
+
+def _gz_member(raw: bytes) -> bytes:
+    c = zlib.compressobj(1, zlib.DEFLATED, 31)
+    return c.compress(raw) + c.flush()
+
+
+def _block(args):
+    lane, b, n, first = args
+    from mgikit_b200 import synth
+    r1, r2 = synth.make_block(lane, b, n, first_read=first)
+    return _gz_member(r1.tobytes()) if r1 is not None else b"", _gz_member(r2.tobytes())
+
+
+def write_lane_blocks(lane, n_pairs, out_dir, block_pairs=BLOCK_PAIRS, single_member=False):
+    """The lane as .fq.gz, one gzip member per block of `block_pairs` (or one member in all, python's gzip
+    writer, when single_member), read numbers continuing across blocks; returns (r1, r2, sheet, seconds)."""
+    from mgikit_b200 import synth
+    os.makedirs(out_dir, exist_ok=True)
+    t0 = time.perf_counter()
+    p1 = os.path.join(out_dir, "V350012345_L01_read_1.fq.gz")
+    p2 = os.path.join(out_dir, "V350012345_L01_read_2.fq.gz")
+    jobs, first = [], 0
+    while first < n_pairs:
+        n = min(block_pairs, n_pairs - first)
+        jobs.append((lane, len(jobs), n, first))
+        first += n
+    if single_member:
+        f1 = gzip.open(p1, "wb", compresslevel=1) if lane.paired else None
+        with gzip.open(p2 if lane.paired else p1, "wb", compresslevel=1) as f2:
+            for j in jobs:
+                r1, r2 = synth.make_block(j[0], j[1], j[2], first_read=j[3])
+                f2.write(r2.tobytes())
+                if f1:
+                    f1.write(r1.tobytes())
+        if f1:
+            f1.close()
+    else:
+        procs = max(1, min(len(jobs), (os.cpu_count() or 2)))
+        with mp.get_context("fork").Pool(procs) as pool, open(p2 if lane.paired else p1, "wb") as f2:
+            f1 = open(p1, "wb") if lane.paired else None
+            for z1, z2 in pool.imap(_block, jobs):
+                f2.write(z2)
+                if f1:
+                    f1.write(z1)
+            if f1:
+                f1.close()
+    sheet = os.path.join(out_dir, "sample_sheet.tsv")
+    with open(sheet, "w") as f:
+        f.write(synth.sample_sheet_text(lane))
+    return p1, (p2 if lane.paired else None), sheet, time.perf_counter() - t0
+
+
+def _scratch(need_bytes):
+    """tmpfs when it has room (the disk of a GPU box is not what is being measured), else the default temp dir."""
+    for base in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            st = os.statvfs(base)
+            if st.f_bavail * st.f_frsize > need_bytes:
+                return base, st.f_bavail * st.f_frsize
+        except OSError:
+            pass
+    st = os.statvfs(tempfile.gettempdir())
+    return tempfile.gettempdir(), st.f_bavail * st.f_frsize
+
+
+def _timed(binary, args, timeout=3600):
+    t0 = time.perf_counter()
+    p = subprocess.run([binary] + args, capture_output=True, text=True, timeout=timeout)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError(f"{os.path.basename(binary)} failed ({p.returncode}): {p.stderr[-500:]}")
+    return dt
+
+
+def _gz_digest(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    return hashlib.sha256(gzip.decompress(raw) if raw else b"").hexdigest()   # all members, like MultiGzDecoder
+
+
+def _digest_dir(d, gz):
+    out = {}
+    names = sorted(n for n in os.listdir(d) if os.path.isfile(os.path.join(d, n)) and n.endswith(".gz") == gz)
+    if gz:
+        with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+            for n, h in zip(names, pool.map(_gz_digest, [os.path.join(d, n) for n in names])):
+                out[n] = h
+    else:
+        for n in names:
+            with open(os.path.join(d, n), "rb") as f:
+                out[n] = hashlib.sha256(f.read()).hexdigest()
+    return out
+
+
+def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figures=True):
+    import lanes
+    cores = os.cpu_count() or 1
+    r1_rec = 336 if lane.paired else 0
+    need = int(n_pairs * (r1_rec + 376) * 0.55 * 3.2) + (2 << 30)    # gz input + two sets of gz output + slack
+    base, free = _scratch(need)
+    if free < need:   # state it, never fail silently: shrink the lane to what the box holds
+        n_pairs = max(prefix_pairs, int(n_pairs * free / need * 0.8))
+    d = tempfile.mkdtemp(prefix="mgk_files_", dir=base)
+    out = {"lane": lane.name, "pairs": n_pairs, "scratch": base, "host_cores": cores,
+           "layout": f"one gzip member per block of {BLOCK_PAIRS} pairs (gzip -1), both reads"}
+    try:
+        r1, r2, sheet, gen_s = write_lane_blocks(lane, n_pairs, os.path.join(d, "in"))
+        out["generate_seconds"] = round(gen_s, 2)
+        out["input_gz_bytes"] = os.path.getsize(r1) + (os.path.getsize(r2) if r2 else 0)
+
+        def args_for(out_dir, threads, extra=()):
+            a = lanes.demux_args(lane, r1, r2, sheet, out_dir, list(extra))
+            a[a.index("-t") + 1] = str(threads)
+            return a
+        # ---- the drop-in CLI, twice (the second run has the page cache the reference run will have too)
+        ours_dir = os.path.join(d, "ours")
+        _timed(product_cli, args_for(ours_dir, cores))
+        t_ours = _timed(product_cli, args_for(ours_dir, cores))
+        out["ours"] = {"pairs_per_s": n_pairs / t_ours, "seconds": t_ours, "threads": cores, "cmd": "mgikit_b200/bin/mgikit demultiplex -t %d" % cores}
+        # ---- the reference binary on the same files
+        ref_dir = os.path.join(d, "ref")
+        t_ref = _timed(ref_bin, args_for(ref_dir, cores))
+        out["reference"] = {"pairs_per_s": n_pairs / t_ref, "seconds": t_ref, "threads": cores,
+                            "cmd": "mgikit demultiplex -t %d --writing-buffer-size 4194304" % cores}
+        out["ratio"] = t_ref / t_ours
+        # ---- parity, full run: every report byte for byte
+        a, b = _digest_dir(ours_dir, gz=False), _digest_dir(ref_dir, gz=False)
+        if a != b:
+            raise AssertionError(f"reports of the full run differ from the reference's: {sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5]}")
+        gz_ours = sorted(n for n in os.listdir(ours_dir) if n.endswith(".gz"))
+        gz_ref = sorted(n for n in os.listdir(ref_dir) if n.endswith(".gz"))
+        if gz_ours != gz_ref:
+            raise AssertionError("the full run wrote a different set of FASTQ files than the reference")
+        out["parity"] = {"reports_full_run": f"{len(a)} report files byte-identical", "fastq_files_full_run": len(gz_ours)}
+        out["output_gz_bytes"] = {"ours": sum(os.path.getsize(os.path.join(ours_dir, n)) for n in gz_ours),
+                                  "reference": sum(os.path.getsize(os.path.join(ref_dir, n)) for n in gz_ref)}
+        shutil.rmtree(ref_dir, ignore_errors=True)
+        shutil.rmtree(ours_dir, ignore_errors=True)
+        if side_figures:   # BASELINE.md §3 side figures + where our own time goes
+            t = _timed(product_cli, args_for(ours_dir, cores, ["--host-gzip"]))
+            out["ours_host_gzip"] = {"pairs_per_s": n_pairs / t, "seconds": t, "what": "gzip members made by zlib on the host threads instead of on the device"}
+            shutil.rmtree(ours_dir, ignore_errors=True)
+            t = _timed(ref_bin, args_for(ref_dir, cores, ["--compression-level", "0", "--report-level", "0"]))
+            out["reference_no_codec_out"] = {"pairs_per_s": n_pairs / t, "seconds": t, "what": "--compression-level 0 --report-level 0"}
+            shutil.rmtree(ref_dir, ignore_errors=True)
+        # ---- parity, prefix lane: every FASTQ (decompressed) and report equal to the reference at -t 1
+        pre = min(prefix_pairs, n_pairs)
+        q1, q2, qsheet, _ = write_lane_blocks(lane, pre, os.path.join(d, "pre"))
+
+        def pre_args(out_dir, threads):
+            a = lanes.demux_args(lane, q1, q2, qsheet, out_dir)
+            a[a.index("-t") + 1] = str(threads)
+            return a
+        _timed(product_cli, pre_args(ours_dir, cores))
+        t1 = _timed(ref_bin, pre_args(ref_dir, 1))
+        out["reference_t1"] = {"pairs_per_s": pre / t1, "seconds": t1, "pairs": pre, "threads": 1}
+        for gz in (False, True):
+            a, b = _digest_dir(ours_dir, gz), _digest_dir(ref_dir, gz)
+            if a != b:
+                raise AssertionError(f"prefix lane: {'FASTQ' if gz else 'report'} files differ from the reference at -t 1: "
+                                     f"{sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5]}")
+            out["parity"]["fastq_prefix" if gz else "reports_prefix"] = f"{len(a)} files identical on a {pre}-pair prefix vs the reference at -t 1"
+        shutil.rmtree(ref_dir, ignore_errors=True)
+        shutil.rmtree(ours_dir, ignore_errors=True)
+        if side_figures:   # one member per file (what a plain `gzip` writes): the input decode is one thread per file
+            s1, s2, ssheet, _ = write_lane_blocks(lane, pre, os.path.join(d, "single"), single_member=True)
+            a = lanes.demux_args(lane, s1, s2, ssheet, ours_dir)
+            a[a.index("-t") + 1] = str(cores)
+            _timed(product_cli, a)
+            t = _timed(product_cli, a)
+            out["ours_single_member_input"] = {"pairs_per_s": pre / t, "seconds": t, "pairs": pre,
+                                               "what": "the same lane as ONE gzip member per file: inflate runs on one thread per input file"}
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    from mgikit_b200 import synth
+    from mgikit_b200.capi import CLI_BIN
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+    ref = os.path.join(ROOT, "oracle", "_ref", "mgikit")
+    print(json.dumps(run(synth.CONFIG2, n, CLI_BIN, ref)))
