@@ -106,6 +106,12 @@ typedef struct {
                                 library's own device copies are padded.                              */
 #define MGK_DEVICE_INPUT_SLACK 32
 #define MGK_OUT_DEVICE  2u   /* leave out_r2/out_r1 in HBM (result pointers are device pointers) */
+#define MGK_OUT_GZIP    4u   /* out_r2/out_r1 hold, per bin, the segment as a run of gzip members made on
+                                the device (BGZF-framed, 32 KiB of text each) instead of the text itself:
+                                what compress_buffer() would hand to write_data() (src/sample_data.rs:
+                                472-503).  seg_off/seg_len and out_*_bytes then describe the compressed
+                                runs; gunzip of bin b's run == the text segment.  The .gz bytes are not
+                                the reference's (libdeflate level 1); its tests compare decompressed text. */
 
 typedef struct mgk_ctx mgk_ctx;
 
@@ -190,6 +196,8 @@ void mgk_host_free(void* p);
  * most recently collected chunk: [0] record scan, [1] match+lengths,
  * [2] bin scan, [3] scatter(+QC), [4] whole chunk incl. copies.               */
 int mgk_last_timings(const mgk_ctx* ctx, float ms[5]);
+/* Device time (ms) of the gzip kernels of the most recently collected chunk (0 without MGK_OUT_GZIP). */
+int mgk_last_gzip_ms(const mgk_ctx* ctx, float* ms);
 /* Device time (ms) from the start of the first chunk submitted after the last
  * call (or after create) to the end of the last chunk submitted: one pair of
  * CUDA events on the launching streams, so overlapped chunks are not counted

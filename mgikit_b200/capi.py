@@ -14,6 +14,7 @@ import numpy as np
 MGK_ABI_VERSION = 1
 MGK_IN_DEVICE = 1
 MGK_OUT_DEVICE = 2
+MGK_OUT_GZIP = 4
 MGK_N_STATS = 10
 MGK_NCCL_ID_BYTES = 128
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -55,7 +56,7 @@ class MgkResult(C.Structure):
 # every entry point include/mgikit_gpu.h declares
 ABI_SYMBOLS = ["create", "destroy", "last_error", "submit", "collect", "release", "counters", "reset_counters",
                "allreduce_counters", "reduced_counters", "nccl_unique_id", "nccl_join", "nccl_allreduce_counters", "host_alloc",
-               "host_free", "last_timings", "span_ms", "launch_count", "scan_newlines", "match_barcodes"]
+               "host_free", "last_timings", "last_gzip_ms", "span_ms", "launch_count", "scan_newlines", "match_barcodes"]
 
 
 def load_gpu_library() -> C.CDLL:
@@ -157,8 +158,8 @@ class HotPath:
     def release(self, seq: int):
         self._check(self._f("release")(self.ctx, seq))
 
-    def process(self, r2, r1=None, seq: int = 0) -> Result:
-        self.submit(seq, r2, r1)
+    def process(self, r2, r1=None, seq: int = 0, flags: int = 0) -> Result:
+        self.submit(seq, r2, r1, flags)
         out = self.collect()
         self.release(seq)
         return out
@@ -209,6 +210,13 @@ class HotPath:
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         self._check(fn(self.ctx, ms))
         return list(ms)
+
+    def last_gzip_ms(self) -> float:
+        ms = C.c_float()
+        fn = self._f("last_gzip_ms")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self._check(fn(self.ctx, C.byref(ms)))
+        return float(ms.value)
 
     def span_ms(self) -> float:
         ms = C.c_float()

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "gz_kernels.cuh"
 #include "kernels.cuh"
 #include "params_build.hpp"
 
@@ -47,7 +48,14 @@ struct Slot {
   std::vector<uint64_t> off2, len2v, off1, len1v;
   ChunkDev cd{};
   float ms[5] = {0, 0, 0, 0, 0};
+  float gz_ms = 0;
   bool in_span = false;   // ev[5] was recorded since the span was opened
+  // MGK_OUT_GZIP (allocated at the slot's first such chunk)
+  GzDev gz{};
+  uint8_t* gz_slots = nullptr;
+  uint32_t *gz_base = nullptr, *gz_size = nullptr;
+  unsigned long long *gz_off = nullptr, *gz_seg = nullptr;
+  cudaEvent_t ev_gz = nullptr;
 };
 
 }  // namespace
@@ -76,6 +84,8 @@ struct mgk_ctx {
   std::deque<int> fifo;     // submitted slots, oldest first
   uint64_t launches = 0;
   float last_ms[5] = {0, 0, 0, 0, 0};
+  float last_gz_ms = 0;
+  GzConsts gzk{};
   ncclComm_t comm = nullptr;
   cudaEvent_t span_begin = nullptr;
   bool span_open = false;
@@ -109,6 +119,8 @@ void free_slot(Slot& s) {
   cudaFree(s.nl2); cudaFree(s.nl1); cudaFree(s.ctrl); cudaFree(s.tile_bins); cudaFree(s.group_sums);
   cudaFree(s.unassigned); cudaFree(s.stg2); cudaFree(s.stg1); cudaFree(s.seg); cudaFree(s.meta); cudaFree(s.status);
   cudaFreeHost(s.h_out2); cudaFreeHost(s.h_out1); cudaFreeHost(s.h_status); cudaFreeHost(s.h_seg); cudaFreeHost(s.h_unassigned);
+  cudaFree(s.gz_slots); cudaFree(s.gz_base); cudaFree(s.gz_size); cudaFree(s.gz_off); cudaFree(s.gz_seg);
+  if (s.ev_gz) cudaEventDestroy(s.ev_gz);
   for (auto& e : s.ev) if (e) cudaEventDestroy(e);
   if (s.ev_status) cudaEventDestroy(s.ev_status);
   if (s.stream) cudaStreamDestroy(s.stream);
@@ -359,6 +371,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     ctx->grid_emit = ctx->n_sm;
   }
 
+  ctx->gzk = gz_make_consts();
+  CUC(cudaFuncSetAttribute(k_gz_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GzShared)));
   if (getenv("MGK_PROFILE")) {   // developer aid: per-warp cycle counters of k_emit, dumped at destroy
     CUC(dalloc(&ctx->d_prof, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 6));
     CUC(cudaMemset(ctx->d_prof, 0, (size_t)ctx->n_sm * (EMIT_THREADS / 32) * 6 * 8));
@@ -500,8 +514,31 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   ctx->launches += 5;
   CU(cudaEventRecord(s.ev[5], st));
   s.in_span = true;
+  if (flags & MGK_OUT_GZIP) {   // the segments as runs of gzip members, packed over the text
+    if (!s.gz_slots) {
+      const uint64_t blocks_cap = (ctx->out_cap * (P.paired ? 2u : 1u)) / GZ_BLOCK + 2ull * P.total + 2ull;
+      CU(dalloc(&s.gz_slots, (size_t)blocks_cap * GZ_SLOT));
+      CU(dalloc(&s.gz_base, (size_t)2 * P.total + 1));
+      CU(dalloc(&s.gz_size, (size_t)blocks_cap));
+      CU(dalloc(&s.gz_off, (size_t)blocks_cap + 1));
+      CU(dalloc(&s.gz_seg, (size_t)4 * P.total));
+      CU(cudaEventCreate(&s.ev_gz));
+      GzDev& g = s.gz;
+      g.seg = s.seg; g.text2 = s.out2; g.text1 = s.out1; g.slots = s.gz_slots; g.blk_base = s.gz_base; g.blk_size = s.gz_size;
+      g.blk_off = s.gz_off; g.gzseg = s.gz_seg; g.total = (uint32_t)P.total; g.blocks_cap = (uint32_t)blocks_cap;
+      g.cap2 = ctx->out_cap; g.cap1 = ctx->out_cap; g.error = &s.status->error; g.err_capacity = ERR_OUT_CAPACITY;
+    }
+    const uint64_t out_bound = std::min<uint64_t>(ctx->out_cap, r2_len + r1_len + rec_bound * ((uint64_t)P.prefix_len + 2ull * P.BL + 32ull));
+    const uint32_t blocks_bound = (uint32_t)std::min<uint64_t>(s.gz.blocks_cap, out_bound / GZ_BLOCK + 2ull * P.total + 2ull);
+    k_gz_plan<<<1, 1024, 0, st>>>(s.gz);
+    k_gz_blocks<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 3u), GZ_THREADS, sizeof(GzShared), st>>>(s.gz, ctx->gzk);
+    k_gz_scan<<<1, 1024, 0, st>>>(s.gz);
+    k_gz_pack<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 8u), 256, 0, st>>>(s.gz);
+    ctx->launches += 4;
+    CU(cudaEventRecord(s.ev_gz, st));
+  }
   CU(cudaMemcpyAsync(s.h_status, s.status, sizeof(Status), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(s.h_seg, s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.h_seg, (flags & MGK_OUT_GZIP) ? s.gz_seg : s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(s.ev_status, st));
   CU(cudaGetLastError());
   s.state = 1;
@@ -523,6 +560,9 @@ extern "C" int mgk_collect(mgk_ctx* ctx, mgk_result* res) {
   for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&s.ms[i], s.ev[i + 1], s.ev[i + 2]);
   cudaEventElapsedTime(&s.ms[4], s.ev[0], s.ev[5]);
   memcpy(ctx->last_ms, s.ms, sizeof s.ms);
+  s.gz_ms = 0.f;
+  if (s.flags & MGK_OUT_GZIP) cudaEventElapsedTime(&s.gz_ms, s.ev[5], s.ev_gz);
+  ctx->last_gz_ms = s.gz_ms;
   if (hs.error & ERR_PANIC)
     return fail(ctx, MGK_ERR_FORMAT, "chunk %llu: a read hits a sample-sheet combination on which the reference panics (stale template dictionary)",
                 (unsigned long long)s.seq);
@@ -735,6 +775,11 @@ extern "C" void mgk_host_free(void* p) {
 extern "C" int mgk_last_timings(const mgk_ctx* ctx, float ms[5]) {
   if (!ctx || !ms) return MGK_ERR_ARG;
   memcpy(ms, ctx->last_ms, sizeof ctx->last_ms);
+  return MGK_OK;
+}
+extern "C" int mgk_last_gzip_ms(const mgk_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return MGK_ERR_ARG;
+  *ms = ctx->last_gz_ms;
   return MGK_OK;
 }
 extern "C" int mgk_span_ms(mgk_ctx* ctx, float* ms) {

@@ -18,6 +18,6 @@ int b_reduced(void* c, uint64_t* a, uint64_t* b) { return mgk_reduced_counters((
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cuda-sm_100a", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, b_reduced, mgk_host_alloc, mgk_host_free, 0u};
+                              b_release, b_counters, b_allreduce, b_reduced, mgk_host_alloc, mgk_host_free, MGK_OUT_GZIP};
   return mgikit::cli_main(argc, argv, be);
 }
