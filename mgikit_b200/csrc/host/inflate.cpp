@@ -11,11 +11,14 @@ namespace mgikit {
 namespace {
 
 // decode-table entry
-//   bits 0-4   code bits to consume (subtable pointer: index bits of the subtable)
-//   bits 8-11  extra bits that follow the code (lengths, distances)
-//   bit 12 literal, 13 end of block, 14 subtable pointer, 15 not a code (incomplete set)
-//   bits 16-31 literal byte / length base / distance base / offset of the subtable
-constexpr uint32_t E_LIT = 1u << 12, E_EOB = 1u << 13, E_SUB = 1u << 14, E_BAD = 1u << 15;
+//   bits 0-3   code bits to consume (all the codes of a literal run; subtable pointer: unused)
+//   literal run (bit 7 set):   bits 4-5 number of literals (1-3), bits 8-31 the literal bytes, first one lowest
+//   anything else (bit 7 clear): bit 4 end of block, bit 5 subtable pointer, bit 6 not a code (incomplete set),
+//                              bits 8-11 extra bits that follow the code (subtable pointer: index bits of the subtable),
+//                              bits 16-31 length base / distance base / offset of the subtable
+// The primary literal/length table resolves up to three literals per lookup when their codes fit its index together:
+// FASTQ out of `gzip -1` is almost only literals, and the serial chain lookup -> shift -> lookup is what bounds it.
+constexpr uint32_t E_LIT = 1u << 7, E_EOB = 1u << 4, E_SUB = 1u << 5, E_BAD = 1u << 6;
 constexpr uint32_t E_SPECIAL = E_EOB | E_SUB | E_BAD;
 
 const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -30,6 +33,8 @@ inline uint64_t load64(const uint8_t* p) {
   return v;
 }
 
+inline void store32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+
 inline unsigned reverse_bits(unsigned code, unsigned len) {
   unsigned r = 0;
   for (unsigned i = 0; i < len; ++i) {
@@ -39,9 +44,9 @@ inline unsigned reverse_bits(unsigned code, unsigned len) {
   return r;
 }
 
-// Canonical Huffman code -> decode table.  lens[sym] in 0..15; entry_of(sym) gives the entry without its code
-// length.  Returns false for an over-subscribed set, and for an incomplete one unless it is a single 1-bit code
-// or (allow_empty) no code at all -- the sets zlib accepts (inftrees.c).
+// Canonical Huffman code -> single-symbol decode table.  lens[sym] in 0..15; entry_of(sym) gives the entry without
+// its code length.  Returns false for an over-subscribed set, and for an incomplete one unless it is a single 1-bit
+// code or (allow_empty) no code at all -- the sets zlib accepts (inftrees.c).
 template <typename F>
 bool build_table(const uint8_t* lens, unsigned n, uint32_t* table, unsigned primary_bits, size_t table_cap, bool allow_empty, F entry_of) {
   unsigned count[16] = {0};
@@ -62,18 +67,27 @@ bool build_table(const uint8_t* lens, unsigned n, uint32_t* table, unsigned prim
   }
   if (left > 0 && max_len != 1) return false;
   const unsigned sub_bits = max_len > primary_bits ? max_len - primary_bits : 0;
-  for (size_t i = 0; i < primary; ++i) table[i] = E_BAD | 1u;
-  unsigned next_code[16], code = 0;
+  if (left > 0 || sub_bits)
+    for (size_t i = 0; i < primary; ++i) table[i] = E_BAD | 1u;   // a complete short code fills every slot below
+  // symbols by (length, symbol): canonical order
+  unsigned offs[17], next_code[16], code = 0;
+  uint16_t order[320];
+  offs[1] = 0;
   for (unsigned l = 1; l <= 15; ++l) {
-    code = (code + count[l - 1]) << 1;
+    offs[l + 1] = offs[l] + count[l];
+    code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
     next_code[l] = code;
   }
-  count[0] = 0;
+  {
+    unsigned at[16];
+    for (unsigned l = 1; l <= 15; ++l) at[l] = offs[l];
+    for (unsigned s = 0; s < n; ++s)
+      if (lens[s]) order[at[lens[s]]++] = (uint16_t)s;
+  }
   size_t sub_next = primary;
-  for (unsigned l = 1; l <= max_len; ++l) {   // by length, then by symbol: canonical order
-    if (!count[l]) continue;
-    for (unsigned s = 0; s < n; ++s) {
-      if (lens[s] != l) continue;
+  for (unsigned l = 1; l <= max_len; ++l) {
+    for (unsigned k = offs[l]; k < offs[l + 1]; ++k) {
+      const unsigned s = order[k];
       const unsigned rev = reverse_bits(next_code[l]++, l);
       const uint32_t e = entry_of(s) | l;
       if (l <= primary_bits) {
@@ -82,7 +96,7 @@ bool build_table(const uint8_t* lens, unsigned n, uint32_t* table, unsigned prim
         const size_t slot = rev & (primary - 1);
         if (!(table[slot] & E_SUB)) {
           if (sub_next + ((size_t)1 << sub_bits) > table_cap) return false;
-          table[slot] = E_SUB | sub_bits | ((uint32_t)sub_next << 16);
+          table[slot] = E_SUB | (sub_bits << 8) | ((uint32_t)sub_next << 16);
           for (size_t i = 0; i < ((size_t)1 << sub_bits); ++i) table[sub_next + i] = E_BAD | 1u;
           sub_next += (size_t)1 << sub_bits;
         }
@@ -95,7 +109,7 @@ bool build_table(const uint8_t* lens, unsigned n, uint32_t* table, unsigned prim
 }
 
 inline uint32_t litlen_entry(unsigned s) {
-  if (s < 256) return E_LIT | (s << 16);
+  if (s < 256) return E_LIT | (1u << 4) | (s << 8);
   if (s == 256) return E_EOB;
   if (s > 285) return E_BAD;   // 286, 287 take part in the code but never appear in valid data
   return ((uint32_t)LEN_BASE[s - 257] << 16) | ((uint32_t)LEN_EXTRA[s - 257] << 8);
@@ -103,6 +117,28 @@ inline uint32_t litlen_entry(unsigned s) {
 inline uint32_t dist_entry(unsigned s) {
   if (s > 29) return E_BAD;
   return ((uint32_t)DIST_BASE[s] << 16) | ((uint32_t)DIST_EXTRA[s] << 8);
+}
+
+// Literal runs: where the bits after a literal's code spell one or two more literal codes that still fit the index,
+// the slot takes them all.  `single` is the table as built above (its replication makes the entry at index y valid for
+// a symbol of up to `avail` known bits exactly when the entry's length is <= avail).
+void fuse_literal_runs(const uint32_t* single, uint32_t* table, unsigned bits) {
+  const uint32_t n = 1u << bits;
+  for (uint32_t x = 0; x < n; ++x) {
+    uint32_t e = single[x];
+    if (e & E_LIT) {
+      const unsigned l1 = e & 15u;
+      const uint32_t e2 = single[x >> l1];
+      const unsigned l2 = e2 & 15u;
+      if ((e2 & E_LIT) && l1 + l2 <= bits) {
+        e = E_LIT | (2u << 4) | (l1 + l2) | (e & 0xff00u) | ((e2 & 0xff00u) << 8);
+        const uint32_t e3 = single[x >> (l1 + l2)];
+        const unsigned l3 = e3 & 15u;
+        if ((e3 & E_LIT) && l1 + l2 + l3 <= bits) e = (e & ~0x3fu) | (3u << 4) | (l1 + l2 + l3) | ((e3 & 0xff00u) << 16);
+      }
+    }
+    table[x] = e;
+  }
 }
 
 }  // namespace
@@ -127,6 +163,8 @@ bool Inflater::build_tables(const uint8_t* lens, unsigned n_lit, unsigned n_dist
     err_ = "invalid literal/lengths set";
     return false;
   }
+  memcpy(single_, lit_, sizeof single_);
+  fuse_literal_runs(single_, lit_, LIT_BITS);
   if (!build_table(lens + n_lit, n_dist, dist_, DIST_BITS, sizeof dist_ / sizeof dist_[0], true, dist_entry)) {
     err_ = "invalid distances set";
     return false;
@@ -213,12 +251,12 @@ Inflater::Status Inflater::read_block_header() {
     while (i < n_lit + n_dist) {
       need(7 + 7);
       const uint32_t e = ctab[bb & 127];
-      if ((e & E_BAD) || (e & 31u) > bc) {
+      if ((e & E_BAD) || (e & 15u) > bc) {
         if (bc < 7 && in >= in_end_) return leave(TRUNCATED);
         err_ = "invalid code lengths set";
         return leave(BAD_DATA);
       }
-      take(e & 31u);
+      take(e & 15u);
       const unsigned sym = e >> 16;
       if (sym < 16) {
         lens[i++] = (uint8_t)sym;
@@ -258,7 +296,7 @@ Inflater::Status Inflater::read_block_header() {
 // symbol group), refills are branch-free 8-byte loads, copies may overshoot by up to 15 bytes.  !FAST: byte-wise
 // refills with bounds, exact copies, suspension when fewer than 258 output bytes are left.
 template <bool FAST>
-Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+inline __attribute__((always_inline)) Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
   uint64_t bb = bitbuf_;
   unsigned bc = bitcnt_;
   const uint8_t* in = in_next_;
@@ -271,6 +309,7 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
     st = (s);        \
     goto leave;      \
   } while (0)
+  uint32_t e;
   for (;;) {
     if (FAST) {
       if (in_end_ - in < 16 || out_end - out < 300) MGK_LEAVE(NEED_OUTPUT);   // the caller goes on with the careful loop
@@ -284,38 +323,50 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
         bc += 8;
       }
     }
-    uint32_t e = lit[bb & ((1u << LIT_BITS) - 1)];
-    if (FAST && (e & E_LIT)) {   // up to three literals per refill (3 x 15 bits)
-      bb >>= e & 31u;
-      bc -= e & 31u;
-      *out++ = (uint8_t)(e >> 16);
+    e = lit[bb & ((1u << LIT_BITS) - 1)];
+  have_entry:
+    if (FAST && (e & E_LIT)) {   // up to four lookups of literal runs per refill (4 x LIT_BITS <= 56 bits)
+      bb >>= e & 15u;
+      bc -= e & 15u;
+      store32(out, e >> 8);
+      out += (e >> 4) & 3u;
       e = lit[bb & ((1u << LIT_BITS) - 1)];
       if (e & E_LIT) {
-        bb >>= e & 31u;
-        bc -= e & 31u;
-        *out++ = (uint8_t)(e >> 16);
+        bb >>= e & 15u;
+        bc -= e & 15u;
+        store32(out, e >> 8);
+        out += (e >> 4) & 3u;
         e = lit[bb & ((1u << LIT_BITS) - 1)];
         if (e & E_LIT) {
-          bb >>= e & 31u;
-          bc -= e & 31u;
-          *out++ = (uint8_t)(e >> 16);
-          continue;
+          bb >>= e & 15u;
+          bc -= e & 15u;
+          store32(out, e >> 8);
+          out += (e >> 4) & 3u;
+          e = lit[bb & ((1u << LIT_BITS) - 1)];
+          if (e & E_LIT) {
+            bb >>= e & 15u;
+            bc -= e & 15u;
+            store32(out, e >> 8);
+            out += (e >> 4) & 3u;
+            continue;
+          }
         }
       }
     }
-    if (e & E_SPECIAL) {
-      if (e & E_SUB) e = lit[(e >> 16) + ((bb >> LIT_BITS) & ((1u << (e & 31u)) - 1))];
-      if (e & E_BAD) {
+    if (!(e & E_LIT) && (e & E_SPECIAL)) {   // (a literal run keeps its count where these flags sit)
+      if (e & E_SUB) e = lit[(e >> 16) + ((bb >> LIT_BITS) & ((1u << ((e >> 8) & 15u)) - 1))];
+      if (!(e & E_LIT) && (e & E_BAD)) {
         if (!FAST && bc < 15 && in >= in_end_) MGK_LEAVE(TRUNCATED);
         err_ = "invalid literal/length code";
         MGK_LEAVE(BAD_DATA);
       }
     }
-    if (!FAST && (e & 31u) + ((e >> 8) & 15u) > bc) MGK_LEAVE(TRUNCATED);
-    bb >>= e & 31u;
-    bc -= e & 31u;
+    if (!FAST && (e & 15u) + ((e & E_LIT) ? 0u : ((e >> 8) & 15u)) > bc) MGK_LEAVE(TRUNCATED);
+    bb >>= e & 15u;
+    bc -= e & 15u;
     if (e & E_LIT) {
-      *out++ = (uint8_t)(e >> 16);
+      store32(out, e >> 8);
+      out += (e >> 4) & 3u;
       continue;
     }
     if (e & E_EOB) {
@@ -327,9 +378,11 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
     bb >>= xb;
     bc -= xb;
     if (FAST) {
-      bb |= load64(in) << bc;
-      in += (63 - bc) >> 3;
-      bc |= 56;
+      if (bc < 32) {   // a distance takes up to 15 + 13 bits; a match right after the refill still has them
+        bb |= load64(in) << bc;
+        in += (63 - bc) >> 3;
+        bc |= 56;
+      }
     } else {
       while (bc <= 56 && in < in_end_) {
         bb |= (uint64_t)*in++ << bc;
@@ -338,7 +391,7 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
     }
     uint32_t d = dst[bb & ((1u << DIST_BITS) - 1)];
     if (d & E_SPECIAL) {
-      if (d & E_SUB) d = dst[(d >> 16) + ((bb >> DIST_BITS) & ((1u << (d & 31u)) - 1))];
+      if (d & E_SUB) d = dst[(d >> 16) + ((bb >> DIST_BITS) & ((1u << ((d >> 8) & 15u)) - 1))];
       if (d & E_BAD) {
         if (!FAST && bc < 15 && in >= in_end_) MGK_LEAVE(TRUNCATED);
         err_ = "invalid distance code";
@@ -346,9 +399,9 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
       }
     }
     xb = (d >> 8) & 15u;
-    if (!FAST && (d & 31u) + xb > bc) MGK_LEAVE(TRUNCATED);
-    bb >>= d & 31u;
-    bc -= d & 31u;
+    if (!FAST && (d & 15u) + xb > bc) MGK_LEAVE(TRUNCATED);
+    bb >>= d & 15u;
+    bc -= d & 15u;
     const size_t dist = (d >> 16) + (size_t)(bb & ((1u << xb) - 1));
     bb >>= xb;
     bc -= xb;
@@ -358,6 +411,14 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
     }
     const uint8_t* src = out - dist;
     uint8_t* end = out + len;
+    bool fetched = false;
+    if (FAST && in_end_ - in >= 16 && out_end - end >= 300) {   // the next entry's load runs under the copy
+      bb |= load64(in) << bc;
+      in += (63 - bc) >> 3;
+      bc |= 56;
+      e = lit[bb & ((1u << LIT_BITS) - 1)];
+      fetched = true;
+    }
     if (FAST && dist >= 8) {
       memcpy(out, src, 8);
       memcpy(out + 8, src + 8, 8);
@@ -376,6 +437,7 @@ Inflater::Status Inflater::block_loop(uint8_t* out_begin, uint8_t** out_next, ui
       while (out < end) *out++ = *src++;
     }
     out = end;
+    if (FAST && fetched) goto have_entry;
   }
 leave:
 #undef MGK_LEAVE
@@ -386,7 +448,23 @@ leave:
   return st;
 }
 
+// The hot loop twice: once for any x86-64, once with BMI2 (shrx / bzhi for the variable shifts and masks of the bit
+// buffer), chosen at run time.
+Inflater::Status Inflater::fast_generic(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+  return block_loop<true>(out_begin, out_next, out_end);
+}
+#if defined(__x86_64__)
+__attribute__((target("bmi2"))) Inflater::Status Inflater::fast_bmi2(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+  return block_loop<true>(out_begin, out_next, out_end);
+}
+#endif
+
 Inflater::Status Inflater::run(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end) {
+#if defined(__x86_64__)
+  static const bool have_bmi2 = __builtin_cpu_supports("bmi2");
+#else
+  const bool have_bmi2 = false;
+#endif
   for (;;) {
     switch (state_) {
       case ST_DONE:
@@ -408,7 +486,7 @@ Inflater::Status Inflater::run(uint8_t* out_begin, uint8_t** out_next, uint8_t* 
         break;
       }
       case ST_CODES: {
-        Status s = block_loop<true>(out_begin, out_next, out_end);
+        Status s = have_bmi2 ? fast_bmi2(out_begin, out_next, out_end) : fast_generic(out_begin, out_next, out_end);
         if (s == NEED_OUTPUT) s = block_loop<false>(out_begin, out_next, out_end);   // near an end of input or output
         if (s != DONE) return s;
         break;

@@ -35,6 +35,8 @@ class Inflater {
  private:
   template <bool FAST>
   Status block_loop(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end);
+  Status fast_generic(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end);
+  Status fast_bmi2(uint8_t* out_begin, uint8_t** out_next, uint8_t* out_end);
   Status read_block_header();
   bool build_tables(const uint8_t* lens, unsigned n_lit, unsigned n_dist);
 
@@ -46,9 +48,10 @@ class Inflater {
   size_t stored_left_ = 0;
   const char* err_ = "";
   // decode tables: entry layout in inflate.cpp
-  static constexpr unsigned LIT_BITS = 11, DIST_BITS = 8;
-  uint32_t lit_[(1u << LIT_BITS) + 1024];    // primary + subtables (at most 288 long codes' worth)
-  uint32_t dist_[(1u << DIST_BITS) + 512];
+  static constexpr unsigned LIT_BITS = 12, DIST_BITS = 8;
+  uint32_t lit_[(1u << LIT_BITS) + 1152];    // primary + subtables (8 slots per long-code prefix, at most 144 prefixes)
+  uint32_t single_[1u << LIT_BITS];          // the primary table before literal runs were fused into it
+  uint32_t dist_[(1u << DIST_BITS) + 2048];  // 128 slots per long-code prefix, at most 15 prefixes
 };
 
 uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n);   // gzip CRC-32 (PCLMULQDQ folding when the CPU has it)

@@ -440,6 +440,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     }
   }
 
+  {
+    char msg[96];
+    snprintf(msg, sizeof msg, "hot path contexts ready after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    log_info(msg);
+  }
   int n_threads = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
   if (n_threads < 1) n_threads = 1;
   // the device makes the gzip members itself at the default level; any other level is zlib on the host threads
@@ -466,6 +471,13 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
 
     // ---- committer: appends the chunks' members to the sample files in chunk order (per-sample order == input
     // order for any number of devices) and merges the barcode histograms; then hands the chunk back to the pump
+    {
+      char msg[96];
+      snprintf(msg, sizeof msg, "input readers started after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+      log_info(msg);
+    }
+    ThreadPool pool(n_threads);
+    double commit_seconds = 0, input_wait = 0, device_wait = 0, done_wait = 0;
     std::thread committer([&] {
       std::map<uint64_t, ChunkJob*> waiting;
       uint64_t next_seq = 0;
@@ -479,8 +491,35 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
           ++next_seq;
           if (c->error.empty() && !failed.load()) {
             try {
-              for (auto& part : c->parts)   // write_data(), src/sample_data.rs:492-503: open(append)/write/close
-                append_file(*part.path, part.z.empty() ? part.p : part.z.data(), part.z.empty() ? part.n : part.z.size());
+              // write_data(), src/sample_data.rs:492-503: open(append)/write/close.  The files of one chunk are all
+              // different, so its appends run side by side; the next chunk starts when this one is on disk.
+              const auto tc = std::chrono::steady_clock::now();
+              const size_t n_parts = c->parts.size(), lanes = std::min<size_t>(n_parts, (size_t)std::max(1, n_threads));
+              std::atomic<size_t> next_part{0};
+              std::atomic<int> left{(int)lanes};
+              std::mutex done_mu;
+              std::condition_variable done_cv;
+              std::string write_error;
+              for (size_t l = 0; l < lanes; ++l)
+                pool.submit([&] {
+                  try {
+                    for (size_t i = next_part.fetch_add(1); i < n_parts; i = next_part.fetch_add(1)) {
+                      auto& part = c->parts[i];
+                      append_file(*part.path, part.z.empty() ? part.p : part.z.data(), part.z.empty() ? part.n : part.z.size());
+                    }
+                  } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> lk(done_mu);
+                    if (write_error.empty()) write_error = e.what();
+                  }
+                  std::lock_guard<std::mutex> lk(done_mu);
+                  if (--left == 0) done_cv.notify_all();
+                });
+              {
+                std::unique_lock<std::mutex> lk(done_mu);
+                done_cv.wait(lk, [&] { return left.load() == 0; });
+              }
+              if (!write_error.empty()) throw Fatal(write_error);
+              commit_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tc).count();
               for (auto& kv : c->und) report.undetermined_barcodes[kv.first] += kv.second;
               for (auto& kv : c->amb) report.ambiguous_barcodes[kv.first] += kv.second;
             } catch (const std::exception& e) {
@@ -492,7 +531,6 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
         }
       }
     });
-    ThreadPool pool(n_threads);
 
     auto last_task_done = [&](ChunkJob* j) {
       if (j->pending.fetch_sub(1) == 1) to_commit.push(j);
@@ -595,9 +633,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
         while (finished.try_pop(done)) release(done);
         const int g = (int)(seq % (uint64_t)G);
         if (!input_done && busy[(size_t)g] < slots && uncollected[(size_t)g] < 2) {
+          const auto ti = std::chrono::steady_clock::now();
           Block b2 = rd2.next();
           Block b1;
           if (paired) b1 = rd1->next();
+          input_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - ti).count();
           if (!b2.error.empty()) throw Fatal(b2.error);
           if (paired && !b1.error.empty()) throw Fatal(b1.error);
           if (paired && b2.n_records != b1.n_records) throw Fatal("Something wrong in the input files!");  // src/lib.rs:1490-1494
@@ -622,9 +662,13 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
             input_done = true;
           }
         } else if (!fifo.empty()) {
+          const auto tg = std::chrono::steady_clock::now();
           collect_oldest();
+          device_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
         } else if (held) {
+          const auto tw = std::chrono::steady_clock::now();
           release(finished.pop());
+          done_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
         }
       }
     } catch (const std::exception& e) {
@@ -644,6 +688,12 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     committer.join();
     for (ChunkJob* j : fifo) delete j;
     if (!pump_error.empty()) throw Fatal(pump_error);
+    {
+      char msg[256];
+      snprintf(msg, sizeof msg, "pump waited %.2f s for input, %.2f s for the device, %.2f s for the output side; appends took %.2f s",
+               input_wait, device_wait, done_wait, commit_seconds);
+      log_info(msg);
+    }
 
     // ReportManager::update across workers (src/lib.rs:819-827) == sum over devices
     std::vector<uint64_t> stats((size_t)total * MGK_N_STATS), mism((size_t)total * (size_t)(2 * m + 2));

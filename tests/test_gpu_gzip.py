@@ -40,9 +40,10 @@ def _check(oracle_lib, gpu_lib, spec, chunks, what):
         for k, (r2, r1) in enumerate(chunks):
             want = o.process(r2, r1, seq=k)
             got = g.process(r2, r1, seq=k, flags=MGK_OUT_GZIP)
-            assert (got.validate_error, got.n_records) == (want.validate_error, want.n_records)
-            if want.validate_error:
+            assert got.validate_error == want.validate_error
+            if want.validate_error:   # the reference panics at that record; nothing after the verdict is defined
                 return
+            assert got.n_records == want.n_records
             for which in (2, 1):
                 for b in range(g.total):
                     z, text = got.segment(which, b), want.segment(which, b)
