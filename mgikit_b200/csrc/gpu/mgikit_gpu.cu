@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -235,6 +236,11 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     return fail(ctx, MGK_ERR_ARG, "mgk_create: max_chunk_bytes must be in (0, 2^31) and max_chunk_records > 0");
   if (cfg->allowed_mismatches < 0 || cfg->allowed_mismatches > 100) return fail(ctx, MGK_ERR_ARG, "mgk_create: bad mismatch count");
 
+  const bool trace = getenv("MGK_TRACE") != nullptr;   // developer aid: where the set-up time goes
+  const auto t_create = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (trace) fprintf(stderr, "[mgk trace] create: %s at %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_create).count());
+  };
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(ctx, MGK_ERR_NO_DEVICE, "no CUDA device is visible: the demultiplex hot path has no CPU fallback");
@@ -263,6 +269,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     return MGK_ERR_ARG;                          \
   } while (0)
   CUC(cudaSetDevice(cfg->device));
+  CUC(cudaFree(nullptr));
+  lap("device context");
 
   Params& P = ctx->hp;
   HostTables tb;
@@ -383,6 +391,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   ctx->h_status_init->fmt_record = ~0ull;
   ctx->h_status_init->validate_key = ~0ull;
 
+  lap("tables and kernel attributes");
   const int n_slots = cfg->n_slots < 1 ? 1 : (cfg->n_slots > 8 ? 8 : cfg->n_slots);
   ctx->slots.resize((size_t)n_slots);
   const size_t B2 = (size_t)2 * P.total;
@@ -435,6 +444,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   }
 #undef CUC
 #undef BAD
+  lap("slots (device scratch, pinned result buffers)");
   *out = ctx;
   return MGK_OK;
 }

@@ -80,14 +80,10 @@ struct Block {
 // counts, so only the piece a cut falls into is scanned.
 class BlockReader {
  public:
-  BlockReader(const std::string& path, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be, int decode_threads)
-      : path_(path), cap_(capacity), rpb_(records_per_block), be_(be), decode_threads_(decode_threads) {
-    for (int i = 0; i < n_buffers; ++i) {
-      auto* p = (uint8_t*)be_.host_alloc(cap_);
-      if (!p) throw Fatal("can not allocate chunk buffers");
-      all_.push_back(p);
-      free_.push_back(p);
-    }
+  // `gz` is already decoding (it was started before the device contexts were made); the pinned chunk buffers are
+  // allocated by the assembler thread itself, the first block is on its way while the others are still being pinned
+  BlockReader(std::unique_ptr<GzReader> gz, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be)
+      : gz_(std::move(gz)), cap_(capacity), rpb_(records_per_block), n_buffers_(n_buffers), be_(be) {
     th_ = std::thread([this] { run(); });
   }
   ~BlockReader() {
@@ -123,6 +119,18 @@ class BlockReader {
     cv_.notify_all();
   }
   uint8_t* take() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      if (stop_) return nullptr;
+      if (free_.empty() && (int)all_.size() < n_buffers_) {   // not all pinned yet: one more
+        lk.unlock();
+        auto* p = (uint8_t*)be_.host_alloc(cap_);
+        if (!p) throw Fatal("can not allocate chunk buffers");
+        lk.lock();
+        all_.push_back(p);
+        return p;
+      }
+    }
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [this] { return stop_ || !free_.empty(); });
     if (stop_) return nullptr;
@@ -138,7 +146,7 @@ class BlockReader {
   }
   void run() {
     try {
-      GzReader gz(path_, decode_threads_);
+      GzReader& gz = *gz_;
       GzPiece piece;           // the piece being copied out, from `at` on
       size_t at = 0, piece_nl = 0;
       bool have_piece = false, eof = false;
@@ -227,10 +235,10 @@ class BlockReader {
       fail(e.what());
     }
   }
-  std::string path_;
+  std::unique_ptr<GzReader> gz_;
   size_t cap_, rpb_;
+  int n_buffers_;
   const Backend& be_;
-  int decode_threads_;
   std::vector<uint8_t*> all_;
   std::deque<uint8_t*> free_;
   std::deque<Block> ready_;
@@ -422,6 +430,14 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
   plan.cfg.max_chunk_records = rpb + 16;
   plan.cfg.n_slots = std::max(2, std::min(8, opt.slots));
 
+  int n_threads = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
+  if (n_threads < 1) n_threads = 1;
+  const int decode_threads = std::max(1, opt.reader_threads > 0 ? opt.reader_threads : n_threads / (paired ? 2 : 1));
+  // the inputs start inflating now: device contexts and pinned buffers take a second to set up
+  std::unique_ptr<GzReader> gz2(new GzReader(run.barcode_reads, decode_threads));
+  std::unique_ptr<GzReader> gz1;
+  if (paired) gz1.reset(new GzReader(run.paired_reads, decode_threads));
+
   const int G = std::max(1, opt.gpus);
   std::vector<void*> ctxs((size_t)G, nullptr);
   auto destroy_all = [&] {
@@ -445,12 +461,9 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     snprintf(msg, sizeof msg, "hot path contexts ready after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     log_info(msg);
   }
-  int n_threads = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
-  if (n_threads < 1) n_threads = 1;
   // the device makes the gzip members itself at the default level; any other level is zlib on the host threads
   const bool device_gzip = be.gzip_flag != 0 && opt.compression_level == 1 && !opt.host_gzip;
   const uint32_t submit_flags = device_gzip ? be.gzip_flag : 0u;
-  const int decode_threads = std::max(1, opt.reader_threads > 0 ? opt.reader_threads : n_threads / (paired ? 2 : 1));
   log_info("Hot path: " + std::string(be.name) + " on " + std::to_string(G) + " device(s); chunk = " + std::to_string(rpb) +
            " reads; host threads: " + std::to_string(decode_threads) + " inflate per input file, " + std::to_string(n_threads) +
            (device_gzip ? " for the output (gzip members are made on the device)" : " deflate"));
@@ -460,9 +473,9 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     const int slots = plan.cfg.n_slots;
     const int max_in_flight = G * slots;
     const int n_buffers = max_in_flight + 2;
-    BlockReader rd2(run.barcode_reads, chunk_bytes, rpb, n_buffers, be, decode_threads);
+    BlockReader rd2(std::move(gz2), chunk_bytes, rpb, n_buffers, be);
     std::unique_ptr<BlockReader> rd1;
-    if (paired) rd1.reset(new BlockReader(run.paired_reads, chunk_bytes, rpb, n_buffers, be, decode_threads));
+    if (paired) rd1.reset(new BlockReader(std::move(gz1), chunk_bytes, rpb, n_buffers, be));
 
     const bool single_template = sheet.templates.size() == 1;
     const auto& g0 = sheet.templates[0].geometry;
@@ -711,6 +724,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
   }
   destroy_all();
 
+  {
+    char msg[96];
+    snprintf(msg, sizeof msg, "hot path closed after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    log_info(msg);
+  }
   report.set_sample_total_reads();  // src/lib.rs:1602
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   log_info(std::to_string(report.get_total_reads()) + " reads were processed in " + std::to_string((long)secs) + " secs.");
