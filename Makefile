@@ -24,7 +24,7 @@ all: gpu host oracle
 
 gpu: mgikit_b200/lib/libmgikit_gpu.so
 host: mgikit_b200/bin/mgikit
-oracle: oracle/_ref/liboracle.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit oracle/_ref/libemu.so oracle/_ref/mgikit_emu
+oracle: oracle/_ref/liboracle.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit oracle/_ref/libemu.so oracle/_ref/mgikit_emu oracle/_ref/libhostcodec.so
 
 mgikit_b200/lib/libmgikit_gpu.so: $(GPU_SRC) $(GPU_HDR)
 	@mkdir -p mgikit_b200/lib
@@ -55,6 +55,11 @@ oracle/_ref/libemu.so: $(EMU_DEP)
 oracle/_ref/mgikit_emu: tests/emu/emu_cli.cpp $(EMU_DEP) $(HOST_SRC) $(HOST_HDR)
 	$(CXX) $(CXXFLAGS) -o $@ tests/emu/emu_cli.cpp tests/emu/emu.cpp $(HOST_SRC) -lz
 
+# C hooks over the product's host codec (inflate, member-parallel reader) for the CPU tests
+oracle/_ref/libhostcodec.so: tests/emu/hostcodec.cpp $(H)/inflate.cpp $(H)/inflate.hpp $(H)/gz_reader.cpp $(H)/gz_reader.hpp
+	@mkdir -p oracle/_ref
+	$(CXX) $(CXXFLAGS) -shared -o $@ tests/emu/hostcodec.cpp $(H)/inflate.cpp $(H)/gz_reader.cpp
+
 # The reference cannot be compiled here (no cargo/rustc, no vendored crates);
 # its own prebuilt, version-matched binary is the strongest oracle we can get.
 oracle/_ref/mgikit:
@@ -63,6 +68,6 @@ oracle/_ref/mgikit:
 	 else echo "reference binary not available here (GPU box): skipping"; fi
 
 clean:
-	rm -rf mgikit_b200/lib mgikit_b200/bin oracle/_ref/liboracle.so oracle/_ref/libemu.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit_emu oracle/_ref/*.o
+	rm -rf mgikit_b200/lib mgikit_b200/bin oracle/_ref/liboracle.so oracle/_ref/libemu.so oracle/_ref/mgikit_oracle oracle/_ref/mgikit_emu oracle/_ref/libhostcodec.so oracle/_ref/*.o
 
 .PHONY: all gpu host oracle clean

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE: C entry points over the product's host codec (mgikit_b200/csrc/host/inflate.cpp,
 // gz_reader.cpp) so that pytest can hold it to zlib on fixtures and fuzzed streams.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -47,4 +48,32 @@ int hc_inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t
 }
 
 size_t hc_gzip_header_length(const uint8_t* p, size_t n) { return GzipMember::header_length(p, n); }
+}
+
+// ---- the member-parallel file reader (gz_reader.cpp)
+#include "../../mgikit_b200/csrc/host/gz_reader.hpp"
+#include "../../mgikit_b200/csrc/host/sample_sheet.hpp"
+
+extern "C" {
+// Whole file -> out (at most cap bytes).  0 = ok; 1 = the reader refused the file (message in err); 2 = cap too small.
+int hc_gunzip_file(const char* path, int threads, size_t max_buffered, uint8_t* out, size_t cap, size_t* produced, size_t* newlines,
+                   size_t* members, char* err, size_t err_cap) {
+  *produced = *newlines = *members = 0;
+  try {
+    GzReader rd(path, threads, max_buffered);
+    GzPiece p;
+    while (rd.next(p)) {
+      if (*produced + p.len > cap) return 2;
+      memcpy(out + *produced, p.data, p.len);
+      *produced += p.len;
+      *newlines += p.newlines;
+      rd.recycle(p);
+    }
+    *members = rd.members_decoded();
+    return 0;
+  } catch (const std::exception& e) {
+    snprintf(err, err_cap, "%s", e.what());
+    return 1;
+  }
+}
 }
