@@ -244,15 +244,20 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(ctx, MGK_ERR_NO_DEVICE, "no CUDA device is visible: the demultiplex hot path has no CPU fallback");
+  lap("device count");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(ctx, MGK_ERR_NO_DEVICE, "CUDA device %d does not exist (%d visible)", cfg->device, ndev);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(ctx, MGK_ERR_NO_DEVICE, "can not query device %d", cfg->device);
-  if (prop.major != 10)
-    return fail(ctx, MGK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only (B200)", cfg->device, prop.major, prop.minor);
+  int cc_major = 0, cc_minor = 0, n_sm = 0;   // attributes one by one: cudaGetDeviceProperties queries everything the driver knows
+  if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, cfg->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess)
+    return fail(ctx, MGK_ERR_NO_DEVICE, "can not query device %d", cfg->device);
+  if (cc_major != 10)
+    return fail(ctx, MGK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only (B200)", cfg->device, cc_major, cc_minor);
+  lap("device attributes");
 
   ctx = new mgk_ctx();
   ctx->device = cfg->device;
-  ctx->n_sm = prop.multiProcessorCount;
+  ctx->n_sm = n_sm;
 #define CUC(call)                                                                                         \
   do {                                                                                                    \
     cudaError_t e_ = (call);                                                                              \

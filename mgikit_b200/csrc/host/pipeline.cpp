@@ -82,8 +82,8 @@ class BlockReader {
  public:
   // `gz` is already decoding (it was started before the device contexts were made); the pinned chunk buffers are
   // allocated by the assembler thread itself, the first block is on its way while the others are still being pinned
-  BlockReader(std::unique_ptr<GzReader> gz, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be)
-      : gz_(std::move(gz)), cap_(capacity), rpb_(records_per_block), n_buffers_(n_buffers), be_(be) {
+  BlockReader(std::unique_ptr<GzReader> gz, size_t capacity, size_t records_per_block, int n_buffers, const Backend& be, ThreadPool& pool)
+      : gz_(std::move(gz)), cap_(capacity), rpb_(records_per_block), n_buffers_(n_buffers), be_(be), pool_(pool) {
     th_ = std::thread([this] { run(); });
   }
   ~BlockReader() {
@@ -138,6 +138,33 @@ class BlockReader {
     free_.pop_front();
     return p;
   }
+  // decoded pieces -> pinned chunk buffer: the copies of a block run on the pool (one thread moves ~3 GB/s into
+  // pinned memory, a lane needs more)
+  struct Copy {
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t n;
+  };
+  static constexpr size_t COPY_GRAIN = (size_t)1 << 20;
+  void run_copies(const std::vector<Copy>& copies) {
+    if (copies.size() <= 1) {
+      for (const auto& c : copies) memcpy(c.dst, c.src, c.n);
+      return;
+    }
+    std::atomic<size_t> next{0};
+    const size_t lanes = std::min<size_t>(copies.size(), 8);
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t left = lanes;
+    for (size_t l = 0; l < lanes; ++l)
+      pool_.submit([&] {
+        for (size_t i = next.fetch_add(1); i < copies.size(); i = next.fetch_add(1)) memcpy(copies[i].dst, copies[i].src, copies[i].n);
+        std::lock_guard<std::mutex> lk(mu);
+        if (--left == 0) cv.notify_all();
+      });
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return left == 0; });
+  }
   void fail(const std::string& why) {
     Block b;
     b.last = true;
@@ -153,6 +180,8 @@ class BlockReader {
       std::vector<uint8_t> carry;
       size_t carry_nl = 0;
       const size_t target = 4 * rpb_;
+      std::vector<Copy> copies;
+      std::vector<GzPiece> spent;
       while (!eof || !carry.empty() || have_piece) {
         uint8_t* buf = take();
         if (!buf) break;
@@ -187,16 +216,20 @@ class BlockReader {
             take_nl = 0;
             for (const uint8_t *s = piece.data + at, *e = s + take_n; (s = (const uint8_t*)memchr(s, '\n', (size_t)(e - s))) != nullptr; ++s) ++take_nl;
           }
-          memcpy(buf + have, piece.data + at, take_n);
+          for (size_t o = 0; o < take_n; o += COPY_GRAIN) copies.push_back({buf + have + o, piece.data + at + o, std::min(COPY_GRAIN, take_n - o)});
           have += take_n;
           lines += take_nl;
           at += take_n;
           piece_nl -= take_nl;
           if (at == piece.len) {
-            gz.recycle(piece);
+            spent.push_back(piece);   // given back once its bytes have been copied out
             have_piece = false;
           }
         }
+        run_copies(copies);
+        copies.clear();
+        for (auto& sp : spent) gz.recycle(sp);
+        spent.clear();
         if (eof && have && buf[have - 1] != '\n' && have < cap_) {
           buf[have++] = '\n';
           ++lines;
@@ -239,6 +272,7 @@ class BlockReader {
   size_t cap_, rpb_;
   int n_buffers_;
   const Backend& be_;
+  ThreadPool& pool_;
   std::vector<uint8_t*> all_;
   std::deque<uint8_t*> free_;
   std::deque<Block> ready_;
@@ -473,9 +507,10 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     const int slots = plan.cfg.n_slots;
     const int max_in_flight = G * slots;
     const int n_buffers = max_in_flight + 2;
-    BlockReader rd2(std::move(gz2), chunk_bytes, rpb, n_buffers, be);
+    ThreadPool pool(n_threads);
+    BlockReader rd2(std::move(gz2), chunk_bytes, rpb, n_buffers, be, pool);
     std::unique_ptr<BlockReader> rd1;
-    if (paired) rd1.reset(new BlockReader(std::move(gz1), chunk_bytes, rpb, n_buffers, be));
+    if (paired) rd1.reset(new BlockReader(std::move(gz1), chunk_bytes, rpb, n_buffers, be, pool));
 
     const bool single_template = sheet.templates.size() == 1;
     const auto& g0 = sheet.templates[0].geometry;
@@ -489,7 +524,6 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
       snprintf(msg, sizeof msg, "input readers started after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
       log_info(msg);
     }
-    ThreadPool pool(n_threads);
     double commit_seconds = 0, input_wait = 0, device_wait = 0, done_wait = 0;
     std::thread committer([&] {
       std::map<uint64_t, ChunkJob*> waiting;
