@@ -731,6 +731,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
         if (pump_error.empty()) pump_error = e.what();
       }
     }
+    {
+      char msg[96];
+      snprintf(msg, sizeof msg, "last chunk released after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+      log_info(msg);
+    }
     to_commit.push(nullptr);
     committer.join();
     for (ChunkJob* j : fifo) delete j;
@@ -752,6 +757,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
       throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[0]));
     }
     report.add_counters(stats.data(), mism.data());
+    {
+      char msg[96];
+      snprintf(msg, sizeof msg, "counters read after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+      log_info(msg);
+    }
   } catch (...) {
     destroy_all();
     throw;
