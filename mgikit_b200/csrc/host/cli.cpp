@@ -301,6 +301,7 @@ int cli_main(int argc, char** argv, const Backend& be) {
     opt.slots = (int)parse_usize("slots", val["slots"]);
     opt.reader_threads = (int)parse_usize("reader-threads", val["reader-threads"]);
     opt.host_gzip = flag("host-gzip");
+    opt.leave_teardown_to_exit = be.exits_after_command;
     log_info("Reporting level is: " + std::to_string(opt.report_level));
     run_demultiplex(be, sheet, run, opt);
   } catch (const std::exception& e) {

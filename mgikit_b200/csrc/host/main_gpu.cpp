@@ -22,7 +22,7 @@ int b_reduced(void* c, uint64_t* a, uint64_t* b) { return mgk_reduced_counters((
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cuda-sm_100a", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, b_reduced, mgk_host_alloc, mgk_host_free, MGK_OUT_GZIP};
+                              b_release, b_counters, b_allreduce, b_reduced, mgk_host_alloc, mgk_host_free, MGK_OUT_GZIP, true};
   const int rc = mgikit::cli_main(argc, argv, be);
   // everything is on disk and every file is closed: leave without the driver's exit handlers (unmapping gigabytes of
   // pinned and device memory one allocation at a time takes half a second that a short lane would notice)

@@ -32,6 +32,7 @@ struct Backend {
   void* (*host_alloc)(size_t);
   void (*host_free)(void*);
   uint32_t gzip_flag;   // mgk_submit flag that makes the device return gzip members (0: the backend has none)
+  bool exits_after_command;   // the binary leaves with _exit: contexts and pinned buffers need no orderly teardown
 };
 
 struct DemuxOptions {
@@ -45,6 +46,7 @@ struct DemuxOptions {
   size_t chunk_bytes = 64u << 20;  // decompressed bytes per read file per chunk
   int slots = 4;            // chunks per GPU between submit and release (>= 2)
   int reader_threads = 0;   // --reader-threads: inflate threads per input file (0 = share of -t)
+  bool leave_teardown_to_exit = false;   // the product binary: it calls _exit right after the command
   bool host_gzip = false;   // --host-gzip (extension): gzip on the host threads even at the default level
 };
 

@@ -21,6 +21,6 @@ int b_reduced(void* c, uint64_t* a, uint64_t* b) { return orc_reduced_counters((
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cpu-oracle", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, b_reduced, orc_host_alloc, orc_host_free, 0u};
+                              b_release, b_counters, b_allreduce, b_reduced, orc_host_alloc, orc_host_free, 0u, false};
   return mgikit::cli_main(argc, argv, be);
 }

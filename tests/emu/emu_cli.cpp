@@ -33,6 +33,6 @@ void b_free(void* p) { free(p); }
 
 int main(int argc, char** argv) {
   const mgikit::Backend be = {"cpu-emulation-of-device-logic", b_create, b_destroy, b_err, b_submit, b_collect,
-                              b_release, b_counters, b_allreduce, b_reduced, b_alloc, b_free, 0u};
+                              b_release, b_counters, b_allreduce, b_reduced, b_alloc, b_free, 0u, false};
   return mgikit::cli_main(argc, argv, be);
 }
