@@ -41,7 +41,22 @@ size_t count_newlines(const uint8_t* p, size_t n) {
 }  // namespace
 
 struct GzReader::Buf {
-  std::unique_ptr<uint8_t[]> mem;   // [INFLATE_WINDOW history | piece_ payload | slack]
+  uint8_t* mem = nullptr;   // [INFLATE_WINDOW history | piece_ payload | slack], huge-page backed where the kernel allows
+  size_t bytes = 0;
+  explicit Buf(size_t n) {
+    bytes = (n + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void* p = mmap(nullptr, bytes + ((size_t)2 << 20), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) throw Fatal("out of memory for the gunzip buffers");
+    base_ = p;
+    mem = (uint8_t*)(((uintptr_t)p + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1));
+    madvise(mem, bytes, MADV_HUGEPAGE);   // 2 MiB pages: a thousand times fewer faults on first touch and frees at exit
+  }
+  ~Buf() { munmap(base_, bytes + ((size_t)2 << 20)); }
+  Buf(const Buf&) = delete;
+  Buf& operator=(const Buf&) = delete;
+
+ private:
+  void* base_ = nullptr;
 };
 
 struct GzReader::Task {
@@ -165,9 +180,7 @@ GzReader::Buf* GzReader::take_buffer(Task* t) {
   }
   ++allocated_;
   lk.unlock();
-  Buf* b = new Buf();
-  b->mem.reset(new uint8_t[INFLATE_WINDOW + piece_ + TAIL_SLACK]);
-  return b;
+  return new Buf(INFLATE_WINDOW + piece_ + TAIL_SLACK);
 }
 
 void GzReader::decode(Task* t) {
@@ -189,7 +202,7 @@ void GzReader::decode(Task* t) {
   for (;;) {
     Buf* b = take_buffer(t);
     if (!b) return finish(Task::FAILED, "cancelled");
-    uint8_t* payload = b->mem.get() + INFLATE_WINDOW;
+    uint8_t* payload = b->mem + INFLATE_WINDOW;
     if (hist) memcpy(payload - hist, carry.get(), hist);
     uint8_t* next = payload;
     const Inflater::Status st = inf.run(payload - hist, &next, payload + piece_ + TAIL_SLACK);

@@ -35,7 +35,7 @@ struct GzPiece {
 class GzReader {
  public:
   // n_threads: inflate workers of this file; max_buffered: bytes of decoded text that may wait for the consumer
-  GzReader(const std::string& path, int n_threads, size_t max_buffered = (size_t)4 << 30);
+  GzReader(const std::string& path, int n_threads, size_t max_buffered = (size_t)2 << 30);
   ~GzReader();
   GzReader(const GzReader&) = delete;
   GzReader& operator=(const GzReader&) = delete;
@@ -57,7 +57,7 @@ class GzReader {
   const uint8_t* map_ = nullptr;
   size_t size_ = 0;
   int fd_ = -1;
-  size_t piece_ = (size_t)4 << 20;
+  size_t piece_ = ((size_t)4 << 20) - 32768 - 512;   // with its window and slack a buffer is two huge pages
   size_t max_bufs_, per_task_bufs_;
 
   std::mutex mu_;
