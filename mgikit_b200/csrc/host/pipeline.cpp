@@ -525,7 +525,7 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
       snprintf(msg, sizeof msg, "input readers started after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
       log_info(msg);
     }
-    double commit_seconds = 0, input_wait = 0, device_wait = 0, done_wait = 0;
+    double commit_seconds = 0, input_wait = 0, device_wait = 0, done_wait = 0, submit_seconds = 0;
     std::thread committer([&] {
       std::map<uint64_t, ChunkJob*> waiting;
       uint64_t next_seq = 0;
@@ -690,8 +690,10 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
           if (paired && !b1.error.empty()) throw Fatal(b1.error);
           if (paired && b2.n_records != b1.n_records) throw Fatal("Something wrong in the input files!");  // src/lib.rs:1490-1494
           if (b2.n_records > 0) {
+            const auto ts = std::chrono::steady_clock::now();
             if (be.submit(ctxs[(size_t)g], seq, b2.data, b2.len, paired ? b1.data : nullptr, paired ? b1.len : 0, submit_flags) != MGK_OK)
               throw Fatal(std::string("hot path failed: ") + be.last_error(ctxs[(size_t)g]));
+            submit_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts).count();
             ChunkJob* j = new ChunkJob();
             j->seq = seq;
             j->ctx = g;
@@ -743,8 +745,8 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     if (!pump_error.empty()) throw Fatal(pump_error);
     {
       char msg[256];
-      snprintf(msg, sizeof msg, "pump waited %.2f s for input, %.2f s for the device, %.2f s for the output side; appends took %.2f s",
-               input_wait, device_wait, done_wait, commit_seconds);
+      snprintf(msg, sizeof msg, "pump waited %.2f s for input, %.2f s for the device, %.2f s for the output side, spent %.2f s submitting; appends took %.2f s",
+               input_wait, device_wait, done_wait, submit_seconds, commit_seconds);
       log_info(msg);
     }
 
