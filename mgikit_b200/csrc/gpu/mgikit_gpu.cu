@@ -489,6 +489,11 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   c.len2 = (uint32_t)r2_len;
   c.len1 = (uint32_t)r1_len;
   cudaStream_t st = s.stream;
+  static const bool trace = getenv("MGK_TRACE") != nullptr;
+  const auto t_sub = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (trace) fprintf(stderr, "[mgk trace] submit %llu: %s at %.3f ms\n", (unsigned long long)seq, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sub).count());
+  };
   CU(cudaEventRecord(s.ev[0], st));
   if (!ctx->span_open) {
     CU(cudaEventRecord(ctx->span_begin, st));
@@ -505,6 +510,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   }
   CU(cudaMemcpyAsync(s.status, ctx->h_status_init, sizeof(Status), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(s.ev[1], st));  // [0..1): input copy
+  lap("copies queued");
   {
     const dim3 grid(ctx->scan_grid, P.paired ? 2 : 1);
     k_scan_newlines<<<grid, SCAN_THREADS, SCAN_STAGES * SCAN_TILE, st>>>(c, P.paired ? 2 : 1);
@@ -529,6 +535,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   ctx->launches += 5;
   CU(cudaEventRecord(s.ev[5], st));
   s.in_span = true;
+  lap("kernels queued");
   if (flags & MGK_OUT_GZIP) {   // the segments as runs of gzip members, packed over the text
     if (!s.gz_slots) {
       const uint64_t blocks_cap = (ctx->out_cap * (P.paired ? 2u : 1u)) / GZ_BLOCK + 2ull * P.total + 2ull;
@@ -556,6 +563,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   CU(cudaMemcpyAsync(s.h_seg, (flags & MGK_OUT_GZIP) ? s.gz_seg : s.seg, (size_t)4 * P.total * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(s.ev_status, st));
   CU(cudaGetLastError());
+  lap("all queued");
   s.state = 1;
   ctx->fifo.push_back(si);
   return MGK_OK;
