@@ -673,6 +673,8 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     };
 
     std::string pump_error;
+    const auto t_pump = std::chrono::steady_clock::now();
+    uint64_t n_chunks = 0;
     try {
       uint64_t seq = 0;
       bool input_done = false;
@@ -703,6 +705,7 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
             ++busy[(size_t)g];
             ++uncollected[(size_t)g];
             ++seq;
+            ++n_chunks;
           } else {
             if (b2.data) rd2.give_back(b2.data);
             if (paired && b1.data) rd1->give_back(b1.data);
@@ -745,6 +748,9 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     if (!pump_error.empty()) throw Fatal(pump_error);
     {
       char msg[256];
+      snprintf(msg, sizeof msg, "pump phase: %llu chunks in %.3f s (first submit to last release)", (unsigned long long)n_chunks,
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pump).count());
+      log_info(msg);
       snprintf(msg, sizeof msg, "pump waited %.2f s for input, %.2f s for the device, %.2f s for the output side, spent %.2f s submitting; appends took %.2f s",
                input_wait, device_wait, done_wait, submit_seconds, commit_seconds);
       log_info(msg);

@@ -95,13 +95,30 @@ def _scratch(need_bytes):
     return tempfile.gettempdir(), st.f_bavail * st.f_frsize
 
 
-def _timed(binary, args, timeout=3600):
+def _timed(binary, args, timeout=3600, want_log=False):
     t0 = time.perf_counter()
     p = subprocess.run([binary] + args, capture_output=True, text=True, timeout=timeout)
     dt = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError(f"{os.path.basename(binary)} failed ({p.returncode}): {p.stderr[-500:]}")
-    return dt
+    return (dt, p.stdout) if want_log else dt
+
+
+def _phases(log):
+    """The CLI's own account of a run: set-up (driver + contexts + pinned buffers), the pump phase, where the pump waited."""
+    import re
+    out = {}
+    m = re.search(r"hot path contexts ready after ([0-9.]+) s", log)
+    if m:
+        out["setup_seconds"] = float(m.group(1))
+    m = re.search(r"pump phase: (\d+) chunks in ([0-9.]+) s", log)
+    if m:
+        out["pump_seconds"] = float(m.group(2))
+        out["chunks"] = int(m.group(1))
+    m = re.search(r"pump waited ([0-9.]+) s for input, ([0-9.]+) s for the device, ([0-9.]+) s for the output side, spent ([0-9.]+) s submitting", log)
+    if m:
+        out["pump_waits_seconds"] = {"input": float(m.group(1)), "device": float(m.group(2)), "output": float(m.group(3)), "submit": float(m.group(4))}
+    return out
 
 
 def _gz_digest(path):
@@ -147,8 +164,12 @@ def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figure
         # ---- the drop-in CLI, twice (the second run has the page cache the reference run will have too)
         ours_dir = os.path.join(d, "ours")
         _timed(product_cli, args_for(ours_dir, cores))
-        t_ours = _timed(product_cli, args_for(ours_dir, cores))
+        t_ours, log = _timed(product_cli, args_for(ours_dir, cores), want_log=True)
         out["ours"] = {"pairs_per_s": n_pairs / t_ours, "seconds": t_ours, "threads": cores, "cmd": "mgikit_b200/bin/mgikit demultiplex -t %d" % cores}
+        ph = _phases(log)
+        if "pump_seconds" in ph:   # the run minus process set-up and exit: what a full flow cell would see
+            ph["pump_pairs_per_s"] = n_pairs / ph["pump_seconds"]
+        out["ours"]["phases"] = ph
         # ---- the reference binary on the same files
         ref_dir = os.path.join(d, "ref")
         t_ref = _timed(ref_bin, args_for(ref_dir, cores))
@@ -195,13 +216,17 @@ def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figure
         shutil.rmtree(ref_dir, ignore_errors=True)
         shutil.rmtree(ours_dir, ignore_errors=True)
         if side_figures:   # one member per file (what a plain `gzip` writes): the input decode is one thread per file
-            s1, s2, ssheet, _ = write_lane_blocks(lane, pre, os.path.join(d, "single"), single_member=True)
+            one = min(pre, 500_000)
+            s1, s2, ssheet, _ = write_lane_blocks(lane, one, os.path.join(d, "single"), single_member=True)
             a = lanes.demux_args(lane, s1, s2, ssheet, ours_dir)
             a[a.index("-t") + 1] = str(cores)
             _timed(product_cli, a)
-            t = _timed(product_cli, a)
-            out["ours_single_member_input"] = {"pairs_per_s": pre / t, "seconds": t, "pairs": pre,
+            t, log = _timed(product_cli, a, want_log=True)
+            ph = _phases(log)
+            out["ours_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "phases": ph,
                                                "what": "the same lane as ONE gzip member per file: inflate runs on one thread per input file"}
+            t = _timed(ref_bin, a)
+            out["reference_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "threads": cores}
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
