@@ -5,6 +5,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #if defined(__x86_64__)
@@ -68,7 +71,8 @@ struct GzReader::Task {
   bool cancel = false;            // the chain has passed this offset: a false candidate
 };
 
-GzReader::GzReader(const std::string& path, int n_threads, size_t max_buffered) : path_(path) {
+GzReader::GzReader(const std::string& path, int n_threads, size_t max_buffered, size_t parallel_min, size_t part_bytes)
+    : path_(path), n_threads_(n_threads < 1 ? 1 : n_threads), PARALLEL_MIN_BYTES(parallel_min), PART_BYTES(part_bytes < 65536 ? 65536 : part_bytes) {
   fd_ = open(path.c_str(), O_RDONLY);
   if (fd_ < 0) throw Fatal("Could not open the file");
   struct stat st;
@@ -183,80 +187,317 @@ GzReader::Buf* GzReader::take_buffer(Task* t) {
   return new Buf(INFLATE_WINDOW + piece_ + TAIL_SLACK);
 }
 
-void GzReader::decode(Task* t) {
-  auto finish = [&](Task::State s, const std::string& why) {
-    std::lock_guard<std::mutex> lk(mu_);
-    t->state = s;
+// Where a member's decoding stands: everything in front of `bit` is decoded, checked and queued.
+struct GzReader::Progress {
+  uint64_t bit = 0;                      // position in the deflate stream (a block boundary)
+  uint32_t crc = 0;
+  uint64_t total = 0;                    // bytes decoded so far
+  size_t hist = 0;                       // valid bytes at the end of `window`
+  std::unique_ptr<uint8_t[]> window;     // the last INFLATE_WINDOW bytes decoded (right-aligned)
+  Progress() : window(new uint8_t[INFLATE_WINDOW]) {}
+  void slide(const uint8_t* data, size_t n) {   // the window after n more bytes
+    if (n >= INFLATE_WINDOW) {
+      memcpy(window.get(), data + n - INFLATE_WINDOW, INFLATE_WINDOW);
+      hist = INFLATE_WINDOW;
+    } else {
+      const size_t keep = std::min(hist, INFLATE_WINDOW - n);
+      memmove(window.get() + INFLATE_WINDOW - n - keep, window.get() + INFLATE_WINDOW - keep, keep);
+      memcpy(window.get() + INFLATE_WINDOW - n, data, n);
+      hist = keep + n;
+    }
+  }
+};
+
+void GzReader::fail_task(Task* t, const std::string& why) {
+  std::lock_guard<std::mutex> lk(mu_);
+  t->state = Task::FAILED;
+  t->error = why;
+}
+
+// Trailer of the member whose deflate stream ended `used` bytes after the member's start.
+void GzReader::finish_member(Task* t, size_t used, const Progress& pg) {
+  const uint8_t* in = map_ + t->start;
+  const size_t left = size_ - t->start;
+  std::string why;
+  if (left < used + 8) {
+    why = "unexpected end of file";
+  } else {
+    const uint8_t* tr = in + used;
+    const uint32_t want_crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    const uint32_t want_len = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    if (want_crc != pg.crc) why = "incorrect data check";
+    else if (want_len != (uint32_t)pg.total) why = "incorrect length check";
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!why.empty()) {
+    t->state = Task::FAILED;
     t->error = why;
-  };
+    return;
+  }
+  t->end = t->start + used + 8;
+  t->state = Task::OK;
+}
+
+void GzReader::decode(Task* t) {
   const uint8_t* in = map_ + t->start;
   const size_t left = size_ - t->start;
   const size_t hl = GzipMember::header_length(in, left);
-  if (hl == 0 || hl == (size_t)-1) return finish(Task::FAILED, hl ? "unexpected end of file" : "not a gzip member");
+  if (hl == 0 || hl == (size_t)-1) return fail_task(t, hl ? "unexpected end of file" : "not a gzip member");
+  Progress pg;
+  // a member that runs on for a long way is taken up at several places at once
+  if (n_threads_ > 1 && left - hl >= PARALLEL_MIN_BYTES) {
+    size_t extent_end = size_;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return stop_ || t->cancel || scan_done_ || scan_pos_ >= t->start + hl + PARALLEL_MIN_BYTES; });
+      if (stop_ || t->cancel) {
+        t->state = Task::FAILED;
+        t->error = "cancelled";
+        return;
+      }
+      for (auto& other : tasks_)
+        if (other->start > t->start) {
+          extent_end = other->start;
+          break;
+        }
+    }
+    if (extent_end - (t->start + hl) >= PARALLEL_MIN_BYTES && parallel_mu_.try_lock()) {
+      const bool finished = decode_parallel(t, hl, extent_end - (t->start + hl), pg);
+      parallel_mu_.unlock();
+      if (finished) return;   // queued to its end (or failed for good)
+    }
+  }
+  decode_serial(t, hl, pg);
+}
+
+// One thread, block after block from pg.bit on, through buffers of piece_ bytes with the window carried along.
+void GzReader::decode_serial(Task* t, size_t hl, Progress& pg) {
+  const uint8_t* in = map_ + t->start;
+  const size_t left = size_ - t->start;
   Inflater inf;
-  inf.reset(in + hl, left - hl);
-  uint32_t crc = 0;
-  uint64_t total = 0;
-  std::unique_ptr<uint8_t[]> carry(new uint8_t[INFLATE_WINDOW]);
-  size_t hist = 0;
+  inf.reset_at(in + hl, left - hl, pg.bit);
   for (;;) {
     Buf* b = take_buffer(t);
-    if (!b) return finish(Task::FAILED, "cancelled");
+    if (!b) return fail_task(t, "cancelled");
     uint8_t* payload = b->mem + INFLATE_WINDOW;
-    if (hist) memcpy(payload - hist, carry.get(), hist);
+    if (pg.hist) memcpy(payload - pg.hist, pg.window.get() + INFLATE_WINDOW - pg.hist, pg.hist);
     uint8_t* next = payload;
-    const Inflater::Status st = inf.run(payload - hist, &next, payload + piece_ + TAIL_SLACK);
+    const Inflater::Status st = inf.run(payload - pg.hist, &next, payload + piece_ + TAIL_SLACK);
     const size_t got = (size_t)(next - payload);
     if (st == Inflater::BAD_DATA || st == Inflater::TRUNCATED) {
-      std::lock_guard<std::mutex> lk(mu_);
-      free_.push_back(b);
-      t->state = Task::FAILED;
-      t->error = st == Inflater::TRUNCATED ? "unexpected end of file" : inf.error();
-      return;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        free_.push_back(b);
+      }
+      return fail_task(t, st == Inflater::TRUNCATED ? "unexpected end of file" : inf.error());
     }
-    crc = crc32_fast(crc, payload, got);
-    total += got;
-    if (st == Inflater::NEED_OUTPUT) {   // the last 32 KiB go along into the next buffer
-      const size_t have = hist + got, keep = have < INFLATE_WINDOW ? have : INFLATE_WINDOW;
-      memmove(carry.get(), next - keep, keep);
-      hist = keep;
-    }
+    pg.crc = crc32_fast(pg.crc, payload, got);
+    pg.total += got;
+    if (st == Inflater::NEED_OUTPUT) pg.slide(payload, got);   // the last 32 KiB go along into the next buffer
     GzPiece piece;
     piece.data = payload;
     piece.len = got;
     piece.newlines = count_newlines(payload, got);
     piece.owner = b;
-    if (st == Inflater::DONE) {
-      const size_t used = hl + inf.consumed();
-      std::string why;
-      if (left < used + 8) {
-        why = "unexpected end of file";
-      } else {
-        const uint8_t* tr = in + used;
-        const uint32_t want_crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
-        const uint32_t want_len = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24);
-        if (want_crc != crc) why = "incorrect data check";
-        else if (want_len != (uint32_t)total) why = "incorrect length check";
-      }
-      std::lock_guard<std::mutex> lk(mu_);
-      if (!why.empty()) {
-        free_.push_back(b);
-        t->state = Task::FAILED;
-        t->error = why;
-        return;
-      }
-      if (got) t->ready.push_back(piece);
-      else free_.push_back(b);
-      t->end = t->start + used + 8;
-      t->state = Task::OK;
-      return;
-    }
     {
       std::lock_guard<std::mutex> lk(mu_);
-      t->ready.push_back(piece);
+      if (got) t->ready.push_back(piece);
+      else free_.push_back(b);
     }
     cv_.notify_all();
+    if (st == Inflater::DONE) return finish_member(t, hl + inf.consumed(), pg);
   }
+}
+
+// One member on several threads.  The deflate stream is cut into parts of PART_BYTES; a helper takes a part, finds the
+// first block that starts in it (Inflater::find_block) and decodes from there WITHOUT the 32 KiB in front of it: bytes
+// it cannot know yet are carried as markers (Inflater::run_markers) until it reaches, at a block boundary, the exact
+// bit where a later part was taken up.  This thread walks the parts in order: a part counts only if its predecessor
+// ended exactly on its first bit (a wrong guess of the finder is stepped over and costs nothing but its helper's
+// time); then the window is known, markers become bytes, CRC and length run on, pieces are queued.  Returns true when
+// the member is finished (t->state set); false leaves `pg` at a confirmed block boundary for decode_serial.
+bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) {
+  const uint8_t* deflate = map_ + t->start + hl;
+  const size_t avail = size_ - t->start - hl;
+  const size_t n_parts = (extent + PART_BYTES - 1) / PART_BYTES;
+  const uint64_t NONE = ~0ull;
+  struct Part {
+    uint64_t bit = ~0ull;        // first bit of the block it was taken up at (~0: none found)
+    bool placed = false;         // `bit` is final
+    bool done = false;
+    Inflater::Status st = Inflater::BAD_DATA;
+    uint64_t end_bit = 0;        // where its decoding stopped
+    size_t consumed = 0;         // bytes of the stream up to the end of the final block (st == DONE)
+    SymbolBuffer sym;
+  };
+  std::vector<Part> parts(n_parts);
+  static const bool trace = getenv("MGK_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t next_part = 0, walker_at = 0;
+  bool quit = false;
+  std::vector<std::unique_ptr<SymbolBuffer>> spare;
+  const size_t n_helpers = (size_t)n_threads_;
+  const size_t ahead = 2 * n_helpers + 2;
+
+  auto helper = [&] {
+    for (;;) {
+      size_t i;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return quit || (next_part < n_parts && next_part < walker_at + ahead); });
+        if (quit || next_part >= n_parts) return;
+        i = next_part++;
+      }
+      Part& P = parts[i];
+      const auto tf = std::chrono::steady_clock::now();
+      const uint64_t bit = i == 0 ? 0 : Inflater::find_block(deflate, avail, (uint64_t)i * PART_BYTES * 8u, (uint64_t)(i + 1) * PART_BYTES * 8u);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        P.bit = bit;
+        P.placed = true;
+      }
+      cv.notify_all();
+      if (bit != NONE) {
+        {   // symbol buffers go round (allocating and unmapping tens of megabytes per part from many threads at once
+            // costs more than the decoding: page faults and TLB shoot-downs serialise on the address space)
+          std::lock_guard<std::mutex> lk(mu);
+          if (!spare.empty()) {
+            P.sym.swap(*spare.back());
+            spare.pop_back();
+          }
+        }
+        P.sym.size = 0;
+        P.sym.reserve(PART_BYTES * 3);
+        Inflater inf;
+        inf.reset_at(deflate, avail, bit);
+        Inflater* self = &inf;
+        inf.set_block_stop([&, i, self](uint64_t pos) {
+          // stop on the first bit of any later part that was taken up exactly here
+          const size_t j = std::min<size_t>((size_t)(pos / (PART_BYTES * 8u)), n_parts - 1);
+          std::unique_lock<std::mutex> lk(mu);
+          if (quit) return true;
+          for (size_t k = i + 1; k <= j; ++k)   // a part nobody has looked at yet (this one ran far ahead through parts
+            if (parts[k].placed && parts[k].bit == pos) return true;   // without a block to hold on to) is simply run through
+          return self->symbols_so_far() > ((size_t)1 << 30);   // a helper on a false start must not run away
+        });
+        const auto td = std::chrono::steady_clock::now();
+        P.st = inf.run_markers(P.sym);
+        P.end_bit = inf.bit_position();
+        if (trace)
+          fprintf(stderr, "[gz trace] part %zu: found +%.1f ms at %.3f s, decoded %zu symbols in %.1f ms (status %d)\n", i,
+                  std::chrono::duration<double, std::milli>(td - tf).count(), std::chrono::duration<double>(td - t_begin).count(), P.sym.size,
+                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count(), (int)P.st);
+        if (P.st == Inflater::DONE) P.consumed = inf.consumed();
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        P.done = true;
+      }
+      cv.notify_all();
+    }
+  };
+  std::vector<std::thread> helpers;
+  for (size_t h = 0; h < n_helpers; ++h) helpers.emplace_back(helper);
+  auto stop_helpers = [&] {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      quit = true;
+    }
+    cv.notify_all();
+    for (auto& th : helpers) th.join();
+  };
+
+  bool finished = false, cancelled = false;
+  size_t cur = 0;
+  std::vector<uint8_t> no_window(INFLATE_WINDOW, 0);
+  for (;;) {
+    Part& P = parts[cur];
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      walker_at = cur;
+      cv.notify_all();
+      cv.wait(lk, [&] { return P.done; });
+    }
+    if (trace) fprintf(stderr, "[gz trace] walker has part %zu at %.3f s\n", cur, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    if (P.st != Inflater::STOPPED && P.st != Inflater::DONE) break;   // serial from pg.bit on says what is wrong
+    if (P.st == Inflater::STOPPED && P.sym.size > ((size_t)1 << 30)) break;
+    // markers -> bytes, through the piece buffers
+    bool bad = false;
+    if (pg.hist < INFLATE_WINDOW)   // a marker that points in front of the stream's first byte: "distance too far back"
+      for (size_t q = 0; q < P.sym.size; ++q) {
+        const uint16_t v = P.sym.data[q];
+        if ((v & Inflater::MARKER) && (size_t)(v & (Inflater::MARKER - 1)) < INFLATE_WINDOW - pg.hist) {
+          bad = true;
+          break;
+        }
+      }
+    if (bad) break;
+    size_t at = 0;
+    while (at < P.sym.size) {
+      Buf* b = take_buffer(t);
+      if (!b) {
+        cancelled = true;
+        break;
+      }
+      uint8_t* payload = b->mem + INFLATE_WINDOW;
+      const size_t n = std::min(piece_, P.sym.size - at);
+      Inflater::resolve_markers(P.sym.data + at, n, pg.window.get(), payload);
+      // markers always point into the window of the PART's start: keep that window until the part is through
+      pg.crc = crc32_fast(pg.crc, payload, n);
+      pg.total += n;
+      GzPiece piece;
+      piece.data = payload;
+      piece.len = n;
+      piece.newlines = count_newlines(payload, n);
+      piece.owner = b;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        t->ready.push_back(piece);
+      }
+      cv_.notify_all();
+      at += n;
+    }
+    if (cancelled) break;
+    // the window for the next part: the tail of what this part decoded (resolved again from the symbols: the piece
+    // buffers may already be with the consumer)
+    {
+      const size_t n = P.sym.size, tail = std::min(n, INFLATE_WINDOW);
+      std::vector<uint8_t> last(tail);
+      Inflater::resolve_markers(P.sym.data + n - tail, tail, pg.window.get(), last.data());
+      pg.slide(last.data(), tail);
+    }
+    pg.bit = P.end_bit;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      spare.emplace_back(new SymbolBuffer());
+      spare.back()->swap(P.sym);
+    }
+    if (P.st == Inflater::DONE) {
+      stop_helpers();
+      finish_member(t, hl + P.consumed, pg);
+      return true;
+    }
+    // the part that was taken up where this one stopped
+    size_t nxt = cur + 1;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      while (nxt < n_parts && !(parts[nxt].placed && parts[nxt].bit == pg.bit)) ++nxt;   // (it was placed: its bit stopped this one)
+    }
+    if (nxt >= n_parts) break;   // nobody started there (cannot happen after a STOPPED): go on serially
+    {   // parts in between were run through: the helpers still go over them (and find them taken), nothing to keep
+      std::lock_guard<std::mutex> lk(mu);
+      if (next_part < nxt) next_part = nxt;
+    }
+    cur = nxt;
+  }
+  stop_helpers();
+  if (cancelled) {
+    fail_task(t, "cancelled");
+    return true;
+  }
+  return finished;
 }
 
 bool GzReader::next(GzPiece& p) {

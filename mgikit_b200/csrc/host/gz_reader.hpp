@@ -35,7 +35,10 @@ struct GzPiece {
 class GzReader {
  public:
   // n_threads: inflate workers of this file; max_buffered: bytes of decoded text that may wait for the consumer
-  GzReader(const std::string& path, int n_threads, size_t max_buffered = (size_t)2 << 30);
+  // parallel_min / part_bytes: a member whose compressed stream is at least parallel_min long is decoded in parts of
+  // part_bytes by all the workers at once (gz_reader.cpp: decode_parallel)
+  GzReader(const std::string& path, int n_threads, size_t max_buffered = (size_t)2 << 30, size_t parallel_min = (size_t)48 << 20,
+           size_t part_bytes = (size_t)4 << 20);
   ~GzReader();
   GzReader(const GzReader&) = delete;
   GzReader& operator=(const GzReader&) = delete;
@@ -48,12 +51,21 @@ class GzReader {
  private:
   struct Buf;
   struct Task;
+  struct Progress;
   void scan();
   void work();
   Buf* take_buffer(Task* t);
   void decode(Task* t);
+  void decode_serial(Task* t, size_t hl, Progress& pg);
+  bool decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg);
+  void finish_member(Task* t, size_t used, const Progress& pg);
+  void fail_task(Task* t, const std::string& why);
+  std::mutex parallel_mu_;   // one member at a time is decoded in parts (its helpers are the reader's thread budget)
 
   std::string path_;
+  int n_threads_ = 1;
+  size_t PARALLEL_MIN_BYTES;   // compressed bytes from which a member is decoded in parts
+  size_t PART_BYTES;
   const uint8_t* map_ = nullptr;
   size_t size_ = 0;
   int fd_ = -1;

@@ -1,6 +1,10 @@
 #include "inflate.hpp"
 
+#include <sys/mman.h>
+
+#include <algorithm>
 #include <cstring>
+#include <new>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -152,6 +156,16 @@ void Inflater::reset(const uint8_t* in, size_t n) {
   final_ = false;
   stored_left_ = 0;
   err_ = "";
+}
+
+void Inflater::reset_at(const uint8_t* in, size_t n, uint64_t bit_offset) {
+  reset(in, n);
+  in_next_ = in + (bit_offset >> 3);
+  const unsigned skip = (unsigned)(bit_offset & 7u);
+  if (skip && in_next_ < in_end_) {   // the first byte's leading bits belong to the block before
+    bitbuf_ = (uint64_t)*in_next_++ >> skip;
+    bitcnt_ = 8u - skip;
+  }
 }
 
 bool Inflater::build_tables(const uint8_t* lens, unsigned n_lit, unsigned n_dist) {
@@ -470,6 +484,7 @@ Inflater::Status Inflater::run(uint8_t* out_begin, uint8_t** out_next, uint8_t* 
       case ST_DONE:
         return DONE;
       case ST_HEADER: {
+        if (stop_ && stop_(bit_position())) return STOPPED;
         const Status s = read_block_header();
         if (s != DONE) return s;
         break;
@@ -493,6 +508,205 @@ Inflater::Status Inflater::run(uint8_t* out_begin, uint8_t** out_next, uint8_t* 
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- a stream taken up in its middle
+// Same tables, 16-bit symbols; a match that reaches in front of the first decoded byte yields markers.  Every step
+// is bounds-checked (this is the speculative side: the position may be no block at all).
+Inflater::Status Inflater::run_markers(SymbolBuffer& out) {
+  size_t n = out.size;   // symbols so far
+  auto leave = [&](Status s) {
+    out.size = n;
+    return s;
+  };
+  for (;;) {
+    if (state_ == ST_DONE) return leave(DONE);
+    if (state_ == ST_HEADER) {
+      out_symbols_ = n;
+      if (stop_ && stop_(bit_position())) return leave(STOPPED);
+      const Status s = read_block_header();
+      if (s != DONE) return leave(s);
+      continue;
+    }
+    if (state_ == ST_STORED) {
+      const size_t have = (size_t)(in_end_ - in_next_);
+      if (have < stored_left_) return leave(TRUNCATED);
+      if (out.cap < n + stored_left_) {
+        out.size = n;
+        out.reserve(n + stored_left_ + (out.cap >> 1));
+      }
+      for (size_t i = 0; i < stored_left_; ++i) out.data[n + i] = in_next_[i];
+      n += stored_left_;
+      in_next_ += stored_left_;
+      stored_left_ = 0;
+      state_ = final_ ? ST_DONE : ST_HEADER;
+      continue;
+    }
+    // ST_CODES
+    uint64_t bb = bitbuf_;
+    unsigned bc = bitcnt_;
+    const uint8_t* in = in_next_;
+    Status st = DONE;
+    for (;;) {
+      if (out.cap - n < 320) {
+        out.size = n;
+        out.reserve(out.cap + (out.cap >> 1) + ((size_t)4 << 20));
+      }
+      uint16_t* o = out.data;
+      if (in_end_ - in >= 8) {
+        bb |= load64(in) << bc;
+        in += (63 - bc) >> 3;
+        bc |= 56;
+      } else {
+        while (bc <= 56 && in < in_end_) {
+          bb |= (uint64_t)*in++ << bc;
+          bc += 8;
+        }
+      }
+      uint32_t e = lit_[bb & ((1u << LIT_BITS) - 1)];
+      if (!(e & E_LIT) && (e & E_SPECIAL)) {
+        if (e & E_SUB) e = lit_[(e >> 16) + ((bb >> LIT_BITS) & ((1u << ((e >> 8) & 15u)) - 1))];
+        if (!(e & E_LIT) && (e & E_BAD)) {
+          st = (bc < 15 && in >= in_end_) ? TRUNCATED : BAD_DATA;
+          err_ = "invalid literal/length code";
+          break;
+        }
+      }
+      if ((e & 15u) + ((e & E_LIT) ? 0u : ((e >> 8) & 15u)) > bc) {
+        st = TRUNCATED;
+        break;
+      }
+      bb >>= e & 15u;
+      bc -= e & 15u;
+      if (e & E_LIT) {
+        const unsigned cnt = (e >> 4) & 3u;
+        o[n] = (uint16_t)((e >> 8) & 0xffu);
+        o[n + 1] = (uint16_t)((e >> 16) & 0xffu);
+        o[n + 2] = (uint16_t)(e >> 24);
+        n += cnt;
+        continue;
+      }
+      if (e & E_EOB) {
+        state_ = final_ ? ST_DONE : ST_HEADER;
+        break;
+      }
+      unsigned xb = (e >> 8) & 15u;
+      const unsigned len = (e >> 16) + (unsigned)(bb & ((1u << xb) - 1));
+      bb >>= xb;
+      bc -= xb;
+      if (bc < 32) {
+        if (in_end_ - in >= 8) {
+          bb |= load64(in) << bc;
+          in += (63 - bc) >> 3;
+          bc |= 56;
+        } else {
+          while (bc <= 56 && in < in_end_) {
+            bb |= (uint64_t)*in++ << bc;
+            bc += 8;
+          }
+        }
+      }
+      uint32_t d = dist_[bb & ((1u << DIST_BITS) - 1)];
+      if (d & E_SPECIAL) {
+        if (d & E_SUB) d = dist_[(d >> 16) + ((bb >> DIST_BITS) & ((1u << ((d >> 8) & 15u)) - 1))];
+        if (d & E_BAD) {
+          st = (bc < 15 && in >= in_end_) ? TRUNCATED : BAD_DATA;
+          err_ = "invalid distance code";
+          break;
+        }
+      }
+      xb = (d >> 8) & 15u;
+      if ((d & 15u) + xb > bc) {
+        st = TRUNCATED;
+        break;
+      }
+      bb >>= d & 15u;
+      bc -= d & 15u;
+      const size_t dist = (d >> 16) + (size_t)(bb & ((1u << xb) - 1));
+      bb >>= xb;
+      bc -= xb;
+      if (dist <= n) {
+        const uint16_t* src = o + (n - dist);
+        for (unsigned i = 0; i < len; ++i) o[n + i] = src[i];
+      } else {   // (part of) the match lies in the unknown window: byte w = INFLATE_WINDOW - (distance back from the start)
+        const size_t before = dist - n;   // 1 .. 32768
+        for (unsigned i = 0; i < len; ++i) {
+          const size_t back = before > i ? before - i : 0;
+          o[n + i] = back ? (uint16_t)(MARKER | (INFLATE_WINDOW - back)) : o[i - before];
+        }
+      }
+      n += len;
+    }
+    bitbuf_ = bb;
+    bitcnt_ = bc;
+    in_next_ = in;
+    if (st != DONE) return leave(st);
+  }
+}
+
+SymbolBuffer::~SymbolBuffer() {
+  if (base_) munmap(base_, mapped_);
+}
+
+void SymbolBuffer::reserve(size_t n) {
+  if (n <= cap) return;
+  const size_t huge = (size_t)2 << 20;
+  const size_t bytes = (n * sizeof(uint16_t) + huge - 1) & ~(huge - 1);
+  void* p = mmap(nullptr, bytes + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) throw std::bad_alloc();
+  uint16_t* d = (uint16_t*)(((uintptr_t)p + huge - 1) & ~(uintptr_t)(huge - 1));
+  madvise(d, bytes, MADV_HUGEPAGE);
+  if (size) memcpy(d, data, size * sizeof(uint16_t));
+  if (base_) munmap(base_, mapped_);
+  base_ = p;
+  mapped_ = bytes + huge;
+  data = d;
+  cap = bytes / sizeof(uint16_t);
+}
+
+void Inflater::resolve_markers(const uint16_t* sym, size_t n, const uint8_t* window, uint8_t* out) {
+  for (size_t i = 0; i < n; ++i) {
+    const uint16_t v = sym[i];
+    out[i] = (v & MARKER) ? window[v & (MARKER - 1)] : (uint8_t)v;
+  }
+}
+
+// Block finder: a cheap test of the first 17 bits and of the code-length code at every bit position, the full header
+// (read_block_header: both Huffman codes complete, end-of-block present) for the few that pass.
+uint64_t Inflater::find_block(const uint8_t* in, size_t n, uint64_t from_bit, uint64_t to_bit) {
+  if (n < 16) return ~0ull;
+  const uint64_t last = (uint64_t)(n - 16) * 8u;   // 64-bit loads stay inside the buffer, headers are at most ~2300 bits
+  if (to_bit > last) to_bit = last;
+  Inflater probe;
+  for (uint64_t b = from_bit; b < to_bit; ++b) {
+    const uint64_t w = load64(in + (b >> 3)) >> (b & 7u);
+    if ((w & 7u) != 4u) continue;                      // BFINAL = 0, BTYPE = 10
+    if (((w >> 3) & 31u) > 29u || ((w >> 8) & 31u) > 29u) continue;   // HLIT, HDIST
+    const unsigned n_clen = (unsigned)((w >> 13) & 15u) + 4u;
+    // code-length code: 3 bits each from bit 17 on; complete <=> sum of 2^(7 - len) over the used lengths == 128
+    unsigned kraft = 0, used = 0;
+    uint64_t bits = w >> 17;
+    unsigned have = 64u - 17u - (unsigned)(b & 7u);
+    uint64_t at = b + 17u;
+    for (unsigned i = 0; i < n_clen; ++i) {
+      if (have < 3) {
+        bits = load64(in + (at >> 3)) >> (at & 7u);
+        have = 64u - (unsigned)(at & 7u);
+      }
+      const unsigned l = (unsigned)(bits & 7u);
+      bits >>= 3;
+      have -= 3;
+      at += 3;
+      if (l) {
+        kraft += 128u >> l;
+        ++used;
+      }
+    }
+    if (kraft != 128u && !(used == 1 && kraft == 64u)) continue;
+    probe.reset_at(in, n, b);
+    if (probe.read_block_header() == DONE && probe.state_ == ST_CODES) return b;
+  }
+  return ~0ull;
 }
 
 // ---------------------------------------------------------------- gzip framing

@@ -12,18 +12,66 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <functional>
+#include <utility>
 #include <string>
+#include <vector>
 
 namespace mgikit {
 
 constexpr size_t INFLATE_WINDOW = 32768;   // how far a match may reach back
 
+// Growable array of 16-bit symbols on huge pages, never shrunk, meant to be reused: in a VM a fresh 4 KiB page costs
+// microseconds and the faults of many threads serialise on the address space.
+struct SymbolBuffer {
+  uint16_t* data = nullptr;
+  size_t size = 0, cap = 0;
+  SymbolBuffer() = default;
+  SymbolBuffer(const SymbolBuffer&) = delete;
+  SymbolBuffer& operator=(const SymbolBuffer&) = delete;
+  ~SymbolBuffer();
+  void reserve(size_t n);   // keeps the first `size` symbols
+  void swap(SymbolBuffer& o) {
+    std::swap(data, o.data);
+    std::swap(size, o.size);
+    std::swap(cap, o.cap);
+    std::swap(base_, o.base_);
+    std::swap(mapped_, o.mapped_);
+  }
+
+ private:
+  void* base_ = nullptr;
+  size_t mapped_ = 0;
+};
+
 class Inflater {
  public:
-  enum Status { DONE = 0, NEED_OUTPUT = 1, BAD_DATA = 2, TRUNCATED = 3 };
+  enum Status { DONE = 0, NEED_OUTPUT = 1, BAD_DATA = 2, TRUNCATED = 3, STOPPED = 4 };
 
   // [in, in + n) holds the raw deflate stream (it may be followed by anything); nothing outside is read
   void reset(const uint8_t* in, size_t n);
+  // the same, decoding from the block that starts `bit_offset` bits into the stream
+  void reset_at(const uint8_t* in, size_t n, uint64_t bit_offset);
+  // bits of the stream consumed so far (exact between blocks)
+  uint64_t bit_position() const { return (uint64_t)(in_next_ - in_begin_) * 8u - bitcnt_; }
+  // Called in front of every block header with bit_position(); returning true ends run() / run_markers() with STOPPED
+  // before the header is read (one stream decoded in parallel: a part stops where the next part begins).
+  void set_block_stop(std::function<bool(uint64_t)> stop) { stop_ = std::move(stop); }
+
+  // Decoding WITHOUT the 32 KiB that precede the starting block (a part of a stream taken up in its middle): symbols
+  // are 16 bit wide, 0..255 a byte, MARKER | w the byte w of that unknown window (w = 32768 - distance back from the
+  // start), copied along by every match that reaches into it; resolve_markers() turns them into bytes once the window is
+  // known.  Appends to `out`; ends with DONE (final block), STOPPED (block stop) or an error.
+  static constexpr uint16_t MARKER = 0x8000;
+  Status run_markers(SymbolBuffer& out);
+  size_t symbols_so_far() const { return out_symbols_; }   // for a block stop that bounds the output
+  static void resolve_markers(const uint16_t* sym, size_t n, const uint8_t* window /* INFLATE_WINDOW bytes */, uint8_t* out);
+
+  // First bit position in [from_bit, to_bit) where a non-final dynamic-Huffman block header parses and both of its
+  // codes are complete (what a decoder taking the stream up there needs), or ~0.  Candidates, not certainties: the
+  // caller confirms a position by reaching it at a block boundary from a position it trusts.
+  static uint64_t find_block(const uint8_t* in, size_t n, uint64_t from_bit, uint64_t to_bit);
+
   // Decodes into [*out_next, out_end).  [out_begin, *out_next) must hold what the stream produced before
   // (all of it, or at least its last INFLATE_WINDOW bytes).  NEED_OUTPUT: fewer than 258 bytes are left in
   // the buffer at a symbol boundary; call again with a new buffer.
@@ -47,6 +95,8 @@ class Inflater {
   bool final_ = false;
   size_t stored_left_ = 0;
   const char* err_ = "";
+  std::function<bool(uint64_t)> stop_;
+  size_t out_symbols_ = 0;   // run_markers: symbols decoded when the block stop is asked
   // decode tables: entry layout in inflate.cpp
   static constexpr unsigned LIT_BITS = 12, DIST_BITS = 8;
   uint32_t lit_[(1u << LIT_BITS) + 1152];    // primary + subtables (8 slots per long-code prefix, at most 144 prefixes)

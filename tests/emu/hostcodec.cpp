@@ -56,11 +56,17 @@ size_t hc_gzip_header_length(const uint8_t* p, size_t n) { return GzipMember::he
 
 extern "C" {
 // Whole file -> out (at most cap bytes).  0 = ok; 1 = the reader refused the file (message in err); 2 = cap too small.
+int hc_gunzip_file2(const char* path, int threads, size_t max_buffered, size_t parallel_min, size_t part_bytes, uint8_t* out, size_t cap,
+                    size_t* produced, size_t* newlines, size_t* members, char* err, size_t err_cap);
 int hc_gunzip_file(const char* path, int threads, size_t max_buffered, uint8_t* out, size_t cap, size_t* produced, size_t* newlines,
                    size_t* members, char* err, size_t err_cap) {
+  return hc_gunzip_file2(path, threads, max_buffered, (size_t)48 << 20, (size_t)4 << 20, out, cap, produced, newlines, members, err, err_cap);
+}
+int hc_gunzip_file2(const char* path, int threads, size_t max_buffered, size_t parallel_min, size_t part_bytes, uint8_t* out, size_t cap,
+                    size_t* produced, size_t* newlines, size_t* members, char* err, size_t err_cap) {
   *produced = *newlines = *members = 0;
   try {
-    GzReader rd(path, threads, max_buffered);
+    GzReader rd(path, threads, max_buffered, parallel_min, part_bytes);
     GzPiece p;
     while (rd.next(p)) {
       if (*produced + p.len > cap) return 2;

@@ -28,6 +28,9 @@ def hc():
     lib.hc_crc32.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t]
     lib.hc_inflate_raw.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                    ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+    lib.hc_gunzip_file2.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                                    ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t),
+                                    ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
     lib.hc_gunzip_file.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                    ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t),
                                    ctypes.c_char_p, ctypes.c_size_t]
@@ -170,3 +173,63 @@ def test_gunzip_reference_fixtures(hc):
                 assert rc == 0 and got == want and nl == want.count(b"\n"), (f, err)
                 n += 1
     assert n >= 10
+
+
+def _gunzip_parts(lib, path, threads, cap, parallel_min, part_bytes):
+    out = ctypes.create_string_buffer(cap + 16)
+    p, nl, m = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    err = ctypes.create_string_buffer(512)
+    rc = lib.hc_gunzip_file2(path.encode(), threads, 256 << 20, parallel_min, part_bytes, out, cap, ctypes.byref(p), ctypes.byref(nl),
+                             ctypes.byref(m), err, 512)
+    return rc, out.raw[:p.value], nl.value, m.value, err.value.decode()
+
+
+@pytest.mark.parametrize("level,strategy", [(1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                                            (1, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY)],
+                         ids=["l1", "l6", "l9", "huffman-only", "fixed-blocks", "stored"])
+def test_one_member_decoded_in_parts_equals_zlib(hc, tmp_path, level, strategy):
+    """A long member is taken up at several places at once (block finder + markers for the unknown 32 KiB in front of a
+    part, resolved when the part before it is through): same bytes as one pass.  Fixed and stored blocks give the
+    finder nothing to hold on to: the part before simply runs on."""
+    want = _fastq(40000) + bytes(range(256)) * 300 + _fastq(20000, 3)
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, 8, strategy)
+    blob = c.compress(want) + c.flush()
+    path = str(tmp_path / "long.fq.gz")
+    with open(path, "wb") as f:
+        f.write(blob)
+    for threads, part in ((2, 1 << 20), (5, 200000), (8, 65536)):
+        rc, got, nl, members, err = _gunzip_parts(hc, path, threads, len(want), 1 << 18, part)
+        assert rc == 0, err
+        assert got == want and nl == want.count(b"\n") and members == 1, (threads, part)
+
+
+def test_parts_inside_a_multi_member_file_and_damage(hc, tmp_path):
+    big = _fastq(50000, 1)
+    small = [_fastq(1500, b) for b in range(3)]
+    blob = _member(small[0]) + _member(big, level=6) + _member(small[1]) + _member(small[2])
+    want = small[0] + big + small[1] + small[2]
+    path = str(tmp_path / "mix.fq.gz")
+    with open(path, "wb") as f:
+        f.write(blob)
+    rc, got, _, members, err = _gunzip_parts(hc, path, 6, len(want), 1 << 18, 300000)
+    assert rc == 0 and got == want and members == 4, err
+    # a flipped bit deep inside the long member: an error, never silently different bytes
+    rng = np.random.default_rng(11)
+    for k in range(12):
+        bad = bytearray(blob)
+        i = len(_member(small[0])) + int(rng.integers(2000, len(_member(big, level=6)) - 2000))
+        bad[i] ^= 1 << int(rng.integers(0, 8))
+        with open(path, "wb") as f:
+            f.write(bytes(bad))
+        rc, got, _, _, err = _gunzip_parts(hc, path, 6, len(want) + (1 << 20), 1 << 18, 300000)
+        try:
+            ref = gzip.decompress(bytes(bad))
+        except Exception:
+            ref = None
+        assert (rc == 0) == (ref is not None), (k, rc, err)
+        if ref is not None:
+            assert got == ref
+    with open(path, "wb") as f:
+        f.write(blob[:len(blob) // 2])
+    rc, _, _, _, err = _gunzip_parts(hc, path, 6, len(want), 1 << 18, 300000)
+    assert rc == 1 and "end of file" in err

@@ -216,7 +216,7 @@ def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figure
         shutil.rmtree(ref_dir, ignore_errors=True)
         shutil.rmtree(ours_dir, ignore_errors=True)
         if side_figures:   # one member per file (what a plain `gzip` writes): the input decode is one thread per file
-            one = min(pre, 500_000)
+            one = min(pre, 1_000_000)
             s1, s2, ssheet, _ = write_lane_blocks(lane, one, os.path.join(d, "single"), single_member=True)
             a = lanes.demux_args(lane, s1, s2, ssheet, ours_dir)
             a[a.index("-t") + 1] = str(cores)
