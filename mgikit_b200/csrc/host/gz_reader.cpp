@@ -46,6 +46,7 @@ size_t count_newlines(const uint8_t* p, size_t n) {
 struct GzReader::Buf {
   uint8_t* mem = nullptr;   // [INFLATE_WINDOW history | piece_ payload | slack], huge-page backed where the kernel allows
   size_t bytes = 0;
+  bool pooled = false;      // one of the reader's circulating piece buffers (else: a part's own text, freed when recycled)
   explicit Buf(size_t n) {
     bytes = (n + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
     void* p = mmap(nullptr, bytes + ((size_t)2 << 20), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
@@ -184,7 +185,9 @@ GzReader::Buf* GzReader::take_buffer(Task* t) {
   }
   ++allocated_;
   lk.unlock();
-  return new Buf(INFLATE_WINDOW + piece_ + TAIL_SLACK);
+  Buf* b = new Buf(INFLATE_WINDOW + piece_ + TAIL_SLACK);
+  b->pooled = true;
+  return b;
 }
 
 // Where a member's decoding stands: everything in front of `bit` is decoded, checked and queued.
@@ -312,23 +315,36 @@ void GzReader::decode_serial(Task* t, size_t hl, Progress& pg) {
 // One member on several threads.  The deflate stream is cut into parts of PART_BYTES; a helper takes a part, finds the
 // first block that starts in it (Inflater::find_block) and decodes from there WITHOUT the 32 KiB in front of it: bytes
 // it cannot know yet are carried as markers (Inflater::run_markers) until it reaches, at a block boundary, the exact
-// bit where a later part was taken up.  This thread walks the parts in order: a part counts only if its predecessor
-// ended exactly on its first bit (a wrong guess of the finder is stepped over and costs nothing but its helper's
-// time); then the window is known, markers become bytes, CRC and length run on, pieces are queued.  Returns true when
-// the member is finished (t->state set); false leaves `pg` at a confirmed block boundary for decode_serial.
+// bit where a later part was taken up.  A part counts once its predecessor has ended exactly on its first bit (a wrong
+// guess of the finder is never reached and costs nothing but its helper's time): the predecessor then hands it the
+// window -- only its own last 32 KiB have to be bytes for that -- and the helper turns its markers into bytes, CRC and
+// newline count included, while the parts behind it do the same.  This thread walks the chain in order, joins the
+// CRCs (crc32_combine) and queues the text.  Returns true when the member is finished (t->state set); false leaves
+// `pg` at a confirmed block boundary for decode_serial.
 bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) {
   const uint8_t* deflate = map_ + t->start + hl;
   const size_t avail = size_ - t->start - hl;
   const size_t n_parts = (extent + PART_BYTES - 1) / PART_BYTES;
   const uint64_t NONE = ~0ull;
+  const size_t NO_PART = (size_t)-1;
   struct Part {
     uint64_t bit = ~0ull;        // first bit of the block it was taken up at (~0: none found)
     bool placed = false;         // `bit` is final
-    bool done = false;
+    bool decoded = false;
     Inflater::Status st = Inflater::BAD_DATA;
     uint64_t end_bit = 0;        // where its decoding stopped
+    size_t next = (size_t)-1;    // the part that was taken up there
     size_t consumed = 0;         // bytes of the stream up to the end of the final block (st == DONE)
     SymbolBuffer sym;
+    // set by the predecessor (part 0: by the walker)
+    bool confirmed = false;
+    std::unique_ptr<uint8_t[]> window;   // the INFLATE_WINDOW bytes in front of it, right-aligned
+    size_t window_valid = 0;
+    // set by its helper once the window is there
+    bool resolved = false, bad_marker = false;
+    Buf* text = nullptr;         // the part's bytes (a buffer of its own, outside the pool)
+    size_t text_len = 0, newlines = 0;
+    uint32_t crc = 0;
   };
   std::vector<Part> parts(n_parts);
   static const bool trace = getenv("MGK_TRACE") != nullptr;
@@ -352,48 +368,101 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
       }
       Part& P = parts[i];
       const auto tf = std::chrono::steady_clock::now();
-      const uint64_t bit = i == 0 ? 0 : Inflater::find_block(deflate, avail, (uint64_t)i * PART_BYTES * 8u, (uint64_t)(i + 1) * PART_BYTES * 8u);
+      const uint64_t bit = i == 0 ? pg.bit : Inflater::find_block(deflate, avail, (uint64_t)i * PART_BYTES * 8u, (uint64_t)(i + 1) * PART_BYTES * 8u);
       {
         std::lock_guard<std::mutex> lk(mu);
         P.bit = bit;
         P.placed = true;
       }
       cv.notify_all();
-      if (bit != NONE) {
-        {   // symbol buffers go round (allocating and unmapping tens of megabytes per part from many threads at once
-            // costs more than the decoding: page faults and TLB shoot-downs serialise on the address space)
-          std::lock_guard<std::mutex> lk(mu);
-          if (!spare.empty()) {
-            P.sym.swap(*spare.back());
-            spare.pop_back();
-          }
+      if (bit == NONE) continue;
+      {   // symbol buffers go round (allocating and unmapping tens of megabytes per part from many threads at once
+          // costs more than the decoding: page faults and TLB shoot-downs serialise on the address space)
+        std::lock_guard<std::mutex> lk(mu);
+        if (!spare.empty()) {
+          P.sym.swap(*spare.back());
+          spare.pop_back();
         }
-        P.sym.size = 0;
-        P.sym.reserve(PART_BYTES * 3);
-        Inflater inf;
-        inf.reset_at(deflate, avail, bit);
-        Inflater* self = &inf;
-        inf.set_block_stop([&, i, self](uint64_t pos) {
-          // stop on the first bit of any later part that was taken up exactly here
-          const size_t j = std::min<size_t>((size_t)(pos / (PART_BYTES * 8u)), n_parts - 1);
-          std::unique_lock<std::mutex> lk(mu);
-          if (quit) return true;
-          for (size_t k = i + 1; k <= j; ++k)   // a part nobody has looked at yet (this one ran far ahead through parts
-            if (parts[k].placed && parts[k].bit == pos) return true;   // without a block to hold on to) is simply run through
-          return self->symbols_so_far() > ((size_t)1 << 30);   // a helper on a false start must not run away
-        });
-        const auto td = std::chrono::steady_clock::now();
-        P.st = inf.run_markers(P.sym);
+      }
+      P.sym.size = 0;
+      P.sym.reserve(PART_BYTES * 3);
+      Inflater inf;
+      inf.reset_at(deflate, avail, bit);
+      Inflater* self = &inf;
+      size_t landed = NO_PART;
+      inf.set_block_stop([&, i, self](uint64_t pos) {
+        // stop on the first bit of any later part that was taken up exactly here
+        const size_t j = std::min<size_t>((size_t)(pos / (PART_BYTES * 8u)), n_parts - 1);
+        std::unique_lock<std::mutex> lk(mu);
+        if (quit) return true;
+        for (size_t k = i + 1; k <= j; ++k)   // a part nobody has looked at yet (this one ran far ahead through parts
+          if (parts[k].placed && parts[k].bit == pos) {   // without a block to hold on to) is simply run through
+            landed = k;
+            return true;
+          }
+        return self->symbols_so_far() > ((size_t)1 << 30);   // a helper on a false start must not run away
+      });
+      const auto td = std::chrono::steady_clock::now();
+      const Inflater::Status st = inf.run_markers(P.sym);
+      if (trace)
+        fprintf(stderr, "[gz trace] part %zu: found +%.1f ms at %.3f s, decoded %zu symbols in %.1f ms (status %d)\n", i,
+                std::chrono::duration<double, std::milli>(td - tf).count(), std::chrono::duration<double>(td - t_begin).count(), P.sym.size,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count(), (int)st);
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        P.st = st;
         P.end_bit = inf.bit_position();
-        if (trace)
-          fprintf(stderr, "[gz trace] part %zu: found +%.1f ms at %.3f s, decoded %zu symbols in %.1f ms (status %d)\n", i,
-                  std::chrono::duration<double, std::milli>(td - tf).count(), std::chrono::duration<double>(td - t_begin).count(), P.sym.size,
-                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count(), (int)P.st);
-        if (P.st == Inflater::DONE) P.consumed = inf.consumed();
+        P.next = landed;
+        if (st == Inflater::DONE) P.consumed = inf.consumed();
+        P.decoded = true;
+        cv.notify_all();
+        // the window in front of this part: from the part that ends on its first bit
+        cv.wait(lk, [&] { return quit || P.confirmed || walker_at > i; });
+        if (quit) return;
+        if (!P.confirmed) {   // the chain went past it: a false start of the finder
+          spare.emplace_back(new SymbolBuffer());
+          spare.back()->swap(P.sym);
+          continue;
+        }
+      }
+      const bool usable = (st == Inflater::STOPPED && landed != NO_PART) || st == Inflater::DONE;
+      if (usable) {
+        // its own last 32 KiB first: that is all the next part waits for
+        const size_t n = P.sym.size, tail = std::min(n, INFLATE_WINDOW);
+        if (landed != NO_PART) {
+          Part& N = parts[landed];
+          std::unique_ptr<uint8_t[]> w(new uint8_t[INFLATE_WINDOW]);
+          size_t valid = std::min(INFLATE_WINDOW, P.window_valid + n);
+          if (tail < INFLATE_WINDOW) memcpy(w.get(), P.window.get() + tail, INFLATE_WINDOW - tail);   // what stays of the old window
+          Inflater::resolve_markers(P.sym.data + n - tail, tail, P.window.get(), w.get() + INFLATE_WINDOW - tail);
+          std::lock_guard<std::mutex> lk(mu);
+          N.window = std::move(w);
+          N.window_valid = valid;
+          N.confirmed = true;
+          cv.notify_all();
+        }
+        // then all of it, into a buffer of its own
+        if (P.window_valid < INFLATE_WINDOW)   // a marker in front of the stream's first byte: "distance too far back"
+          for (size_t q = 0; q < n; ++q) {
+            const uint16_t v = P.sym.data[q];
+            if ((v & Inflater::MARKER) && (size_t)(v & (Inflater::MARKER - 1)) < INFLATE_WINDOW - P.window_valid) {
+              P.bad_marker = true;
+              break;
+            }
+          }
+        if (!P.bad_marker) {
+          P.text = new Buf(n + 64);
+          Inflater::resolve_markers(P.sym.data, n, P.window.get(), P.text->mem);
+          P.text_len = n;
+          P.crc = crc32_fast(0, P.text->mem, n);
+          P.newlines = count_newlines(P.text->mem, n);
+        }
       }
       {
         std::lock_guard<std::mutex> lk(mu);
-        P.done = true;
+        spare.emplace_back(new SymbolBuffer());
+        spare.back()->swap(P.sym);
+        P.resolved = true;
       }
       cv.notify_all();
     }
@@ -407,97 +476,75 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
     }
     cv.notify_all();
     for (auto& th : helpers) th.join();
+    for (auto& P : parts)
+      if (P.text) delete P.text;
   };
+  {   // part 0 starts where the member stands, with what is known of the window
+    std::lock_guard<std::mutex> lk(mu);
+    parts[0].window.reset(new uint8_t[INFLATE_WINDOW]);
+    memcpy(parts[0].window.get(), pg.window.get(), INFLATE_WINDOW);
+    parts[0].window_valid = pg.hist;
+    parts[0].confirmed = true;
+  }
 
-  bool finished = false, cancelled = false;
+  bool cancelled = false;
   size_t cur = 0;
-  std::vector<uint8_t> no_window(INFLATE_WINDOW, 0);
   for (;;) {
     Part& P = parts[cur];
     {
       std::unique_lock<std::mutex> lk(mu);
       walker_at = cur;
       cv.notify_all();
-      cv.wait(lk, [&] { return P.done; });
+      cv.wait(lk, [&] { return P.resolved; });
     }
     if (trace) fprintf(stderr, "[gz trace] walker has part %zu at %.3f s\n", cur, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
-    if (P.st != Inflater::STOPPED && P.st != Inflater::DONE) break;   // serial from pg.bit on says what is wrong
-    if (P.st == Inflater::STOPPED && P.sym.size > ((size_t)1 << 30)) break;
-    // markers -> bytes, through the piece buffers
-    bool bad = false;
-    if (pg.hist < INFLATE_WINDOW)   // a marker that points in front of the stream's first byte: "distance too far back"
-      for (size_t q = 0; q < P.sym.size; ++q) {
-        const uint16_t v = P.sym.data[q];
-        if ((v & Inflater::MARKER) && (size_t)(v & (Inflater::MARKER - 1)) < INFLATE_WINDOW - pg.hist) {
-          bad = true;
-          break;
-        }
-      }
-    if (bad) break;
-    size_t at = 0;
-    while (at < P.sym.size) {
-      Buf* b = take_buffer(t);
-      if (!b) {
-        cancelled = true;
-        break;
-      }
-      uint8_t* payload = b->mem + INFLATE_WINDOW;
-      const size_t n = std::min(piece_, P.sym.size - at);
-      Inflater::resolve_markers(P.sym.data + at, n, pg.window.get(), payload);
-      // markers always point into the window of the PART's start: keep that window until the part is through
-      pg.crc = crc32_fast(pg.crc, payload, n);
-      pg.total += n;
-      GzPiece piece;
-      piece.data = payload;
-      piece.len = n;
-      piece.newlines = count_newlines(payload, n);
-      piece.owner = b;
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        t->ready.push_back(piece);
-      }
-      cv_.notify_all();
-      at += n;
+    const bool usable = ((P.st == Inflater::STOPPED && P.next != NO_PART) || P.st == Inflater::DONE) && !P.bad_marker;
+    if (!usable) {   // serial from this part's first bit on says what is wrong with the stream
+      memcpy(pg.window.get(), P.window.get(), INFLATE_WINDOW);
+      pg.hist = P.window_valid;
+      pg.bit = P.bit;
+      break;
+    }
+    {   // the consumer's budget holds for this member too: wait while it is behind
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return stop_ || t->cancel || t->start == chain_pos_ || t->ready.size() < per_task_bufs_; });
+      if (stop_ || t->cancel) cancelled = true;
     }
     if (cancelled) break;
-    // the window for the next part: the tail of what this part decoded (resolved again from the symbols: the piece
-    // buffers may already be with the consumer)
-    {
-      const size_t n = P.sym.size, tail = std::min(n, INFLATE_WINDOW);
-      std::vector<uint8_t> last(tail);
-      Inflater::resolve_markers(P.sym.data + n - tail, tail, pg.window.get(), last.data());
-      pg.slide(last.data(), tail);
-    }
+    pg.crc = crc32_combine_fast(pg.crc, P.crc, P.text_len);
+    pg.total += P.text_len;
     pg.bit = P.end_bit;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      spare.emplace_back(new SymbolBuffer());
-      spare.back()->swap(P.sym);
+    if (P.text_len) {
+      GzPiece piece;
+      piece.data = P.text->mem;
+      piece.len = P.text_len;
+      piece.newlines = P.newlines;
+      piece.owner = P.text;
+      P.text = nullptr;
+      std::lock_guard<std::mutex> lk(mu_);
+      t->ready.push_back(piece);
+    } else if (P.text) {
+      delete P.text;
+      P.text = nullptr;
     }
+    cv_.notify_all();
     if (P.st == Inflater::DONE) {
       stop_helpers();
       finish_member(t, hl + P.consumed, pg);
       return true;
     }
-    // the part that was taken up where this one stopped
-    size_t nxt = cur + 1;
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      while (nxt < n_parts && !(parts[nxt].placed && parts[nxt].bit == pg.bit)) ++nxt;   // (it was placed: its bit stopped this one)
-    }
-    if (nxt >= n_parts) break;   // nobody started there (cannot happen after a STOPPED): go on serially
-    {   // parts in between were run through: the helpers still go over them (and find them taken), nothing to keep
+    {   // parts in between were run through: nobody needs to look at them any more
       std::lock_guard<std::mutex> lk(mu);
-      if (next_part < nxt) next_part = nxt;
+      if (next_part < P.next) next_part = P.next;
     }
-    cur = nxt;
+    cur = P.next;
   }
   stop_helpers();
   if (cancelled) {
     fail_task(t, "cancelled");
     return true;
   }
-  return finished;
+  return false;
 }
 
 bool GzReader::next(GzPiece& p) {
@@ -515,7 +562,10 @@ bool GzReader::next(GzPiece& p) {
           cv_.notify_all();
           cv_.wait(lk, [t] { return t->state != Task::RUNNING; });
         }
-        for (auto& q : t->ready) free_.push_back((Buf*)q.owner);
+        for (auto& q : t->ready) {
+          if (((Buf*)q.owner)->pooled) free_.push_back((Buf*)q.owner);
+          else delete (Buf*)q.owner;
+        }
         tasks_.pop_front();
         ++dropped;
       }
@@ -552,9 +602,12 @@ bool GzReader::next(GzPiece& p) {
 
 void GzReader::recycle(GzPiece& p) {
   if (!p.owner) return;
-  {
+  Buf* b = (Buf*)p.owner;
+  if (b->pooled) {
     std::lock_guard<std::mutex> lk(mu_);
-    free_.push_back((Buf*)p.owner);
+    free_.push_back(b);
+  } else {
+    delete b;
   }
   p.owner = nullptr;
   cv_.notify_all();

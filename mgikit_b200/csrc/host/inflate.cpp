@@ -817,6 +817,37 @@ __attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul(uint32_t c, const 
 
 }  // namespace
 
+namespace {
+uint32_t multmodp(uint32_t a, uint32_t b) {   // a * b mod P, reflected (zlib crc32.c)
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1u) ? (b >> 1) ^ 0xedb88320u : b >> 1;
+  }
+  return p;
+}
+}  // namespace
+
+uint32_t crc32_combine_fast(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+  static uint32_t x2n[32];
+  static const bool init = [] {
+    uint32_t p = 1u << 30;   // x^1
+    x2n[0] = p;
+    for (int n = 1; n < 32; ++n) x2n[n] = p = multmodp(p, p);
+    return true;
+  }();
+  (void)init;
+  uint32_t p = 1u << 31;     // x^0
+  unsigned k = 3;            // x^(len_b * 2^3)
+  for (uint64_t n = len_b; n; n >>= 1, ++k)
+    if (n & 1) p = multmodp(x2n[k & 31], p);
+  return multmodp(p, crc_a) ^ crc_b;
+}
+
 uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n) {
   uint32_t c = ~crc;
 #if defined(__x86_64__)

@@ -104,7 +104,9 @@ class Inflater {
   uint32_t dist_[(1u << DIST_BITS) + 2048];  // 128 slots per long-code prefix, at most 15 prefixes
 };
 
-uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n);   // gzip CRC-32 (PCLMULQDQ folding when the CPU has it)
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n);
+// CRC-32 of A||B from the CRC-32s of A and B and the length of B (zlib's crc32_combine)
+uint32_t crc32_combine_fast(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);   // gzip CRC-32 (PCLMULQDQ folding when the CPU has it)
 
 // One gzip member: header parsing, the deflate stream, CRC-32 + ISIZE check.
 struct GzipMember {

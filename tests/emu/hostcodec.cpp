@@ -11,6 +11,7 @@ using namespace mgikit;
 extern "C" {
 
 uint32_t hc_crc32(uint32_t crc, const uint8_t* p, size_t n) { return crc32_fast(crc, p, n); }
+uint32_t hc_crc32_combine(uint32_t a, uint32_t b, uint64_t len_b) { return crc32_combine_fast(a, b, len_b); }
 
 // Raw deflate stream -> out, through output buffers of `piece` bytes (0: one buffer), the way the reader streams a
 // member.  Returns the Inflater status; *produced / *consumed as far as decoding got.

@@ -61,6 +61,16 @@ def test_crc32_matches_zlib(hc):
         assert hc.hc_crc32(12345, b, n) == zlib.crc32(b, 12345)
 
 
+def test_crc32_combine_matches_zlib(hc):
+    hc.hc_crc32_combine.restype = ctypes.c_uint32
+    hc.hc_crc32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+    rng = np.random.default_rng(7)
+    for la, lb in [(0, 0), (5, 0), (0, 7), (100, 1), (1, 100000), (123457, 765432), (1 << 20, (1 << 21) + 3)]:
+        a = rng.integers(0, 256, la, dtype=np.uint8).tobytes()
+        b = rng.integers(0, 256, lb, dtype=np.uint8).tobytes()
+        assert hc.hc_crc32_combine(zlib.crc32(a), zlib.crc32(b), lb) == zlib.crc32(a + b), (la, lb)
+
+
 def test_inflate_equals_zlib_on_every_kind_of_stream(hc):
     rng = np.random.default_rng(2)
     datas = [b"", b"a", b"abc" * 1000, bytes(100000), _fastq(4000), rng.integers(0, 256, size=150000, dtype=np.uint8).tobytes(),
