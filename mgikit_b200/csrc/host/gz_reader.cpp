@@ -351,30 +351,41 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
   const auto t_begin = std::chrono::steady_clock::now();
   std::mutex mu;
   std::condition_variable cv;
-  size_t next_part = 0, walker_at = 0;
+  size_t next_find = 0, next_part = 0, walker_at = 0;   // parts placed / decoding started up to here; the walker's part
   bool quit = false;
   std::vector<std::unique_ptr<SymbolBuffer>> spare;
   const size_t n_helpers = (size_t)n_threads_;
   const size_t ahead = 2 * n_helpers + 2;
 
+  // Two kinds of work for a helper, the cheap one first: placing parts (the finder, well under a millisecond each) runs
+  // twice as far ahead as decoding, so that a decoder always finds the parts behind its own placed when it gets there.
   auto helper = [&] {
     for (;;) {
       size_t i;
+      bool find;
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return quit || (next_part < n_parts && next_part < walker_at + ahead); });
-        if (quit || next_part >= n_parts) return;
-        i = next_part++;
+        cv.wait(lk, [&] {
+          return quit || (next_find < n_parts && next_find < walker_at + 2 * ahead) ||
+                 (next_part < next_find && next_part < walker_at + ahead && parts[next_part].placed);
+        });
+        if (quit) return;
+        find = next_find < n_parts && next_find < walker_at + 2 * ahead;
+        i = find ? next_find++ : next_part++;
       }
       Part& P = parts[i];
       const auto tf = std::chrono::steady_clock::now();
-      const uint64_t bit = i == 0 ? pg.bit : Inflater::find_block(deflate, avail, (uint64_t)i * PART_BYTES * 8u, (uint64_t)(i + 1) * PART_BYTES * 8u);
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        P.bit = bit;
-        P.placed = true;
+      if (find) {
+        const uint64_t b = i == 0 ? pg.bit : Inflater::find_block(deflate, avail, (uint64_t)i * PART_BYTES * 8u, (uint64_t)(i + 1) * PART_BYTES * 8u);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          P.bit = b;
+          P.placed = true;
+        }
+        cv.notify_all();
+        continue;
       }
-      cv.notify_all();
+      const uint64_t bit = P.bit;
       if (bit == NONE) continue;
       {   // symbol buffers go round (allocating and unmapping tens of megabytes per part from many threads at once
           // costs more than the decoding: page faults and TLB shoot-downs serialise on the address space)
@@ -395,11 +406,16 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
         const size_t j = std::min<size_t>((size_t)(pos / (PART_BYTES * 8u)), n_parts - 1);
         std::unique_lock<std::mutex> lk(mu);
         if (quit) return true;
-        for (size_t k = i + 1; k <= j; ++k)   // a part nobody has looked at yet (this one ran far ahead through parts
-          if (parts[k].placed && parts[k].bit == pos) {   // without a block to hold on to) is simply run through
+        for (size_t k = i + 1; k <= j; ++k) {
+          if (k >= next_find) break;   // nobody has looked at that part yet (this one ran far ahead through parts
+                                       // without a block to hold on to): it is simply run through
+          cv.wait(lk, [&] { return quit || parts[k].placed; });
+          if (quit) return true;
+          if (parts[k].bit == pos) {
             landed = k;
             return true;
           }
+        }
         return self->symbols_so_far() > ((size_t)1 << 30);   // a helper on a false start must not run away
       });
       const auto td = std::chrono::steady_clock::now();
@@ -536,6 +552,7 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
     {   // parts in between were run through: nobody needs to look at them any more
       std::lock_guard<std::mutex> lk(mu);
       if (next_part < P.next) next_part = P.next;
+      if (next_find < P.next) next_find = P.next;
     }
     cur = P.next;
   }
