@@ -24,9 +24,13 @@ try:
     p = subprocess.run([CLI_BIN] + a, capture_output=True, text=True, env=dict(os.environ, MGK_TRACE="1"))
     print("wall %.2f" % (time.perf_counter() - t))
     lines = [l for l in p.stderr.split("\n") if "gz trace" in l or "create" in l]
-    print("\n".join(lines[:30]))
-    print("...")
-    print("\n".join(lines[-12:]))
+    import re
+    slow = [l for l in lines if "decoded" in l and float(re.search(r"in ([0-9.]+) ms", l).group(1)) > 100]
+    print("parts slower than 100 ms:", len(slow))
+    print("\n".join(slow[:10]))
+    walk = [l for l in lines if "walker" in l]
+    print("\n".join(walk[::max(1, len(walk) // 30)]))
+    print("\n".join(lines[-6:]))
     print("\n".join(line[30:] for line in p.stdout.split("\n") if "pump" in line or "ready after" in line))
 finally:
     shutil.rmtree(d, ignore_errors=True)
