@@ -155,6 +155,7 @@ void GzReader::work() {
     cv_.wait(lk, [this] { return stop_ || next_claim_ < tasks_.size(); });
     if (stop_) return;
     Task* t = tasks_[next_claim_++].get();
+    if (t->state != Task::PENDING) continue;
     if (t->start < chain_pos_ || t->cancel) {   // the chain is already past it
       t->state = Task::FAILED;
       continue;
@@ -264,8 +265,10 @@ void GzReader::decode(Task* t) {
           break;
         }
     }
+    // (the next listed start decides whether this member is long; the parts themselves run to the end of the file:
+    // a listed start may be no member, and a member that does end there ends its parts with its final block)
     if (extent_end - (t->start + hl) >= PARALLEL_MIN_BYTES && parallel_mu_.try_lock()) {
-      const bool finished = decode_parallel(t, hl, extent_end - (t->start + hl), pg);
+      const bool finished = decode_parallel(t, hl, left - hl, pg);
       parallel_mu_.unlock();
       if (finished) return;   // queued to its end (or failed for good)
     }
@@ -587,6 +590,17 @@ bool GzReader::next(GzPiece& p) {
         ++dropped;
       }
       next_claim_ = std::max(next_claim_, dropped) - dropped;
+      if ((tasks_.empty() || tasks_.front()->start != chain_pos_) && chain_pos_ < size_) {
+        // the scanner lists likely member starts only; what the chain arrives at is a member if its header says so
+        const size_t hl = GzipMember::header_length(map_ + chain_pos_, size_ - chain_pos_);
+        if (hl != 0 && hl != (size_t)-1) {
+          std::unique_ptr<Task> nt(new Task());
+          nt->start = chain_pos_;
+          tasks_.push_front(std::move(nt));
+          next_claim_ = 0;   // (tasks already taken are skipped by their state)
+          cv_.notify_all();
+        }
+      }
       if (tasks_.empty() || tasks_.front()->start != chain_pos_) {
         if (chain_pos_ == 0) throw Fatal("corrupt gzip input: " + path_ + " (not a gzip file)");
         for (size_t i = chain_pos_; i < size_; ++i)   // zero padding after the last member is tolerated

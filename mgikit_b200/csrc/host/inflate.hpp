@@ -113,9 +113,10 @@ struct GzipMember {
   // Parses the header at [p, p + n); returns its length, 0 if this is not a gzip (deflate) member header,
   // or (size_t)-1 if it is cut off.
   static size_t header_length(const uint8_t* p, size_t n);
-  // magic + method + reserved flag bits: cheap test of a candidate member start
+  // magic + method + reserved flag bits + an XFL value RFC 1952 defines: cheap test of a candidate member start (the
+  // reader does not depend on it: a member the chain arrives at is taken on header_length() alone)
   static bool plausible(const uint8_t* p, size_t n) {
-    return n >= 18 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 0xe0) == 0;
+    return n >= 18 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 0xe0) == 0 && (p[8] == 0 || p[8] == 2 || p[8] == 4);
   }
 };
 

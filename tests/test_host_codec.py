@@ -243,3 +243,19 @@ def test_parts_inside_a_multi_member_file_and_damage(hc, tmp_path):
         f.write(blob[:len(blob) // 2])
     rc, _, _, _, err = _gunzip_parts(hc, path, 6, len(want), 1 << 18, 300000)
     assert rc == 1 and "end of file" in err
+
+
+def test_members_the_scanner_does_not_list_are_still_taken(hc, tmp_path):
+    """The scanner lists likely starts only (XFL in {0, 2, 4}); a member with another XFL byte is reached by the chain and
+    accepted on its header alone."""
+    parts = [_fastq(2500, b) for b in range(4)]
+    blob = b""
+    for i, p in enumerate(parts):
+        m = bytearray(_member(p))
+        m[8] = 7 if i % 2 else 0
+        blob += bytes(m)
+    path = str(tmp_path / "xfl.fq.gz")
+    with open(path, "wb") as f:
+        f.write(blob)
+    rc, got, _, members, err = _gunzip_file(hc, path, 3, sum(map(len, parts)))
+    assert rc == 0 and got == b"".join(parts) and members == 4, err
