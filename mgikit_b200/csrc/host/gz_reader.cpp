@@ -2,7 +2,9 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -149,7 +151,16 @@ void GzReader::scan() {
   cv_.notify_all();
 }
 
+namespace {
+// Inflating is bulk work that starts before the device contexts exist: it yields to the thread that sets those up
+// (driver initialisation is CPU-bound and takes two to three times longer on a machine whose cores are all busy).
+void lower_thread_priority() {
+  setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);
+}
+}  // namespace
+
 void GzReader::work() {
+  lower_thread_priority();
   std::unique_lock<std::mutex> lk(mu_);
   for (;;) {
     cv_.wait(lk, [this] { return stop_ || next_claim_ < tasks_.size(); });
@@ -363,6 +374,7 @@ bool GzReader::decode_parallel(Task* t, size_t hl, size_t extent, Progress& pg) 
   // Two kinds of work for a helper, the cheap one first: placing parts (the finder, well under a millisecond each) runs
   // twice as far ahead as decoding, so that a decoder always finds the parts behind its own placed when it gets there.
   auto helper = [&] {
+    lower_thread_priority();
     for (;;) {
       size_t i;
       bool find;
