@@ -276,6 +276,12 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   CUC(cudaSetDevice(cfg->device));
   CUC(cudaFree(nullptr));
   lap("device context");
+  if (const char* g = getenv("MGK_L2_FETCH")) {   // developer aid: L2 fetch granularity hint (32 / 64 / 128 bytes)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "[mgk] L2 fetch granularity: asked %s, device says %zu\n", g, got);
+  }
 
   Params& P = ctx->hp;
   HostTables tb;
