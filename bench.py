@@ -241,7 +241,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from mgikit_b200.capi import CLI_BIN, MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
+    from mgikit_b200.capi import CLI_BIN, MGK_IN_DEVICE, MGK_OUT_DEVICE, MGK_OUT_GZIP, load_gpu_library
     from util import device_copy, make_hotpath
 
     if not torch.cuda.is_available():
@@ -352,11 +352,11 @@ def main():
                      (h1.data_ptr() + cuts[j] * r1_rec, (cuts[j + 1] - cuts[j]) * r1_rec)) for j in range(n_sub)]
         per_step_pieces = cps * n_sub
 
-        def run_e2e(steps):
+        def run_e2e(steps, flags=0):
             d2h = 0
             pieces = steps * per_step_pieces
             for k in range(pieces):
-                hp.submit(k, sub_args[k % n_sub][0], sub_args[k % n_sub][1], 0)
+                hp.submit(k, sub_args[k % n_sub][0], sub_args[k % n_sub][1], flags)
                 if k >= 1:
                     res = hp.collect(device_out=True)      # results are in pinned host memory; no python copy
                     d2h += res.out_r2_bytes + res.out_r1_bytes + 4 * res.unassigned.size + 4 * 8 * hp.total
@@ -373,10 +373,21 @@ def main():
         d2h = run_e2e(a.steps)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # the same with MGK_OUT_GZIP: the segments leave the device as gzip members (what the reference's workers make
+        # of them before they reach a file), so the D2H side carries about half the bytes
+        gz_steps = max(1, min(a.steps, 4))
+        run_e2e(1, MGK_OUT_GZIP)
+        barrier()
+        t0 = time.perf_counter()
+        d2h_gz = run_e2e(gz_steps, MGK_OUT_GZIP)
+        barrier()
+        dt_gz = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": n * cps * a.steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes * cps),
                "d2h_bytes_per_step": int(d2h), "seconds": dt,
                "timing": "host clock between barrier+synchronize, max over ranks; pinned buffers, "
-                         f"{per_step_pieces} pieces of {cuts[1]} pairs per step, 2 in flight"}
+                         f"{per_step_pieces} pieces of {cuts[1]} pairs per step, 2 in flight",
+               "gzip_out": {"value": n * cps * gz_steps * world / dt_gz, "unit": UNIT, "d2h_bytes_per_step": int(d2h_gz), "steps": gz_steps,
+                            "what": "same call with MGK_OUT_GZIP: per-sample segments come back as gzip members made on the device"}}
 
         # copy-only leg: the same pinned input buffers and piece sizes, one cudaMemcpyAsync per piece and direction
         # (H2D of the text on one stream, D2H of as many bytes as the path returns on another), no kernels: what the
