@@ -29,7 +29,6 @@ constexpr uint32_t GZ_ROW_WORDS = GZ_RUN / 4 + 1;        // rows of the staged t
 constexpr uint32_t GZ_HDR = 18, GZ_TRL = 8;
 constexpr uint32_t GZ_SLOT = GZ_BLOCK + 64;              // worst case (stored): 18 + 5 + 32768 + 8 bytes
 constexpr uint32_t GZ_OUT_WORDS = GZ_SLOT / 4;
-constexpr uint32_t GZ_TABLE_BITS = 3 + 14 + 19 * 3 + 257 * 4 + 2 * 4;   // block header: type, counts, code-length code, the lengths
 constexpr uint32_t GZ_POLY = 0xedb88320u;
 
 struct GzConsts {
@@ -116,21 +115,161 @@ __global__ void __launch_bounds__(1024) k_gz_plan(GzDev g) {
 }
 
 // ---------------------------------------------------------------- blocks
+constexpr uint32_t GZ_MAX_TOK = 16;        // matches per thread run (at least GZ_MIN_MATCH bytes each)
+constexpr uint32_t GZ_MIN_MATCH = 8;       // shorter repeats do not pay for their distance bits
+constexpr uint32_t GZ_HASH_BITS = 12;
+constexpr uint32_t GZ_NLIT = 286, GZ_NDIST = 30;
+
 struct GzShared {
-  uint32_t text[GZ_THREADS * GZ_ROW_WORDS];   // the block, right-aligned: text byte i at position (GZ_BLOCK - n) + i
-  uint32_t out[GZ_OUT_WORDS];                 // the member being built (before that: histograms and Huffman scratch)
-  uint32_t code[257];                         // reversed code | length << 16
+  uint32_t text[GZ_THREADS * GZ_ROW_WORDS + 4];   // the block, right-aligned: text byte i at position (GZ_BLOCK - n) + i
+  // the member being built; before that: first-occurrence table [4096] | literal/length histograms [8][286] | distance
+  // histograms [8][30], and (over the dead table) symbol counts, sort order and the Huffman scratch
+  uint32_t out[GZ_OUT_WORDS];
+  uint32_t tok[GZ_THREADS][GZ_MAX_TOK];           // a run's matches: position in the run | length << 7 | distance << 16
+  uint32_t ntok[GZ_THREADS];
+  uint32_t code[GZ_NLIT];                         // reversed code | length << 16
+  uint32_t dcode[GZ_NDIST];
   uint32_t crc_tab[256];
   uint32_t warp_bits[8], warp_crc[8];
-  uint32_t q, stored, total_bits;
+  uint32_t q, stored, total_bits, hlit, hdist;
 };
+constexpr uint32_t GZ_O_TABLE = 0, GZ_O_HLIT = 1u << GZ_HASH_BITS, GZ_O_HDIST = GZ_O_HLIT + 8u * GZ_NLIT;
+static_assert(GZ_O_HDIST + 8u * GZ_NDIST <= GZ_OUT_WORDS, "scratch fits the image area");
 
+// word g of the block's text (rows of 32 words, skewed by one)
+__device__ __forceinline__ uint32_t gz_word(const GzShared& S, uint32_t g) { return S.text[g + (g >> 5)]; }
 __device__ __forceinline__ uint32_t gz_text_byte(const GzShared& S, uint32_t pos) {   // pos in right-aligned coordinates
-  const uint32_t row = pos / GZ_RUN, col = pos % GZ_RUN;
-  return (S.text[row * GZ_ROW_WORDS + (col >> 2)] >> (8u * (col & 3u))) & 0xffu;
+  return (gz_word(S, pos >> 2) >> (8u * (pos & 3u))) & 0xffu;
+}
+// the 8 bytes at pos (pos + 8 <= GZ_BLOCK)
+__device__ __forceinline__ void gz_load8(const GzShared& S, uint32_t pos, uint32_t& lo, uint32_t& hi) {
+  const uint32_t g = pos >> 2, sh = (pos & 3u) * 8u;
+  const uint32_t a = gz_word(S, g), b = gz_word(S, g + 1u);
+  if (sh) {
+    const uint32_t c = gz_word(S, g + 2u);
+    lo = __funnelshift_r(a, b, sh);
+    hi = __funnelshift_r(b, c, sh);
+  } else {
+    lo = a;
+    hi = b;
+  }
+}
+__device__ __forceinline__ uint32_t gz_hash(uint32_t lo, uint32_t hi) {
+  return ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u)) >> (32u - GZ_HASH_BITS);
+}
+// deflate's length / distance alphabets (RFC 1951 3.2.5)
+__device__ __forceinline__ void gz_len_symbol(uint32_t len, uint32_t& sym, uint32_t& eb, uint32_t& ev) {
+  if (len == 258u) {
+    sym = 285u;
+    eb = ev = 0u;
+    return;
+  }
+  const uint32_t l = len - 3u;
+  if (l < 8u) {
+    sym = 257u + l;
+    eb = ev = 0u;
+    return;
+  }
+  const uint32_t k = 31u - (uint32_t)__clz((int)l);
+  eb = k - 2u;
+  sym = 261u + 4u * eb + ((l >> eb) & 3u);
+  ev = l & ((1u << eb) - 1u);
+}
+__device__ __forceinline__ void gz_dist_symbol(uint32_t dist, uint32_t& sym, uint32_t& eb, uint32_t& ev) {
+  const uint32_t d = dist - 1u;
+  if (d < 4u) {
+    sym = d;
+    eb = ev = 0u;
+    return;
+  }
+  const uint32_t k = 31u - (uint32_t)__clz((int)d);
+  eb = k - 1u;
+  sym = 2u * k + ((d >> eb) & 1u);
+  ev = d & ((1u << eb) - 1u);
+}
+__device__ __forceinline__ uint32_t gz_len_extra(uint32_t sym) { return (sym < 265u || sym == 285u) ? 0u : (sym - 261u) >> 2; }
+__device__ __forceinline__ uint32_t gz_dist_extra(uint32_t sym) { return sym < 4u ? 0u : (sym >> 1) - 1u; }
+
+// One thread: Huffman code lengths (<= 15) and canonical, bit-reversed codes for the symbols with cnt > 0.
+// sorted[0 .. m) = the used symbols by (count, symbol) ascending.  Returns sum of count * length.
+__device__ uint32_t gz_build_code(const uint32_t* cnt, uint32_t n_sym, const uint32_t* sorted, uint32_t m, uint32_t* scratch, uint32_t* code) {
+  uint32_t bl_count[17];
+  for (int i = 0; i < 17; ++i) bl_count[i] = 0;
+  int overflow = 0;
+  if (m == 1) {
+    bl_count[1] = 1;
+  } else {
+    // two-queue Huffman over the leaves (ascending): nodes 0..m-1 leaves, m..2m-2 internal
+    uint32_t* iw = scratch;                 // [m - 1] weights of the internal nodes, in creation order (ascending)
+    uint32_t* parent = scratch + 290u;      // [2m - 1]
+    uint32_t* depth = parent + 580u;        // [2m - 1]
+    uint32_t li = 0, ii = 0, ni = 0;
+    for (uint32_t step = 0; step + 1 < m; ++step) {
+      uint32_t pick[2], wsum = 0;
+      for (int t = 0; t < 2; ++t) {
+        const bool leaf = li < m && (ii >= ni || cnt[sorted[li]] <= iw[ii]);
+        if (leaf) {
+          pick[t] = li;
+          wsum += cnt[sorted[li]];
+          ++li;
+        } else {
+          pick[t] = m + ii;
+          wsum += iw[ii];
+          ++ii;
+        }
+      }
+      iw[ni] = wsum;
+      parent[pick[0]] = parent[pick[1]] = m + ni;
+      ++ni;
+    }
+    depth[2u * m - 2u] = 0;
+    for (int node = (int)(2u * m - 3u); node >= 0; --node) {
+      uint32_t d = depth[parent[node]] + 1u;
+      depth[node] = d;
+      if ((uint32_t)node < m) {
+        if (d > 15u) {
+          d = 15u;
+          ++overflow;
+        }
+        ++bl_count[d];
+      }
+    }
+  }
+  while (overflow > 0) {   // zlib's gen_bitlen: move a leaf down one level, two overflowing leaves up
+    uint32_t bits = 14;
+    while (bl_count[bits] == 0) --bits;
+    --bl_count[bits];
+    bl_count[bits + 1] += 2;
+    --bl_count[15];
+    overflow -= 2;
+  }
+  uint32_t total = 0;
+  {   // the rarest symbols take the longest codes
+    uint32_t i = 0;
+    for (uint32_t bits = 15; bits >= 1; --bits)
+      for (uint32_t c = 0; c < bl_count[bits]; ++c) {
+        const uint32_t s = sorted[i++];
+        code[s] = bits << 16;
+        total += bits * cnt[s];
+      }
+  }
+  // canonical codes, bit-reversed (deflate packs Huffman codes starting with their most significant bit)
+  uint32_t next_code[16], c0 = 0;
+  bl_count[0] = 0;
+  for (uint32_t bits = 1; bits <= 15; ++bits) {
+    c0 = (c0 + bl_count[bits - 1]) << 1;
+    next_code[bits] = c0;
+  }
+  for (uint32_t s = 0; s < n_sym; ++s) {
+    const uint32_t len = code[s] >> 16;
+    if (!len) continue;
+    const uint32_t c = next_code[len]++;
+    code[s] = (__brev(c) >> (32u - len)) | (len << 16);
+  }
+  return total;
 }
 
-__global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K) {
+__global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K) {
   extern __shared__ __align__(16) unsigned char gz_smem[];
   GzShared& S = *reinterpret_cast<GzShared*>(gz_smem);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -173,28 +312,24 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
       }
       S.text[(j >> 5) * GZ_ROW_WORDS + (j & 31u)] = w;
     }
-    for (uint32_t i = tid; i < 8u * 257u; i += GZ_THREADS) S.out[i] = 0;   // histograms, one per warp
+    for (uint32_t i = tid; i < GZ_O_HLIT; i += GZ_THREADS) S.out[i] = 0xffffffffu;                               // first-occurrence table
+    for (uint32_t i = GZ_O_HLIT + tid; i < GZ_O_HDIST + 8u * GZ_NDIST; i += GZ_THREADS) S.out[i] = 0;            // histograms, one per warp
+    if (tid < 4) S.text[GZ_THREADS * GZ_ROW_WORDS + tid] = 0;
     __syncthreads();
-    // ---- histogram + CRC of this thread's run: positions [tid * GZ_RUN, +GZ_RUN) that are >= pad
-    const uint32_t p0 = tid * GZ_RUN;
+    const uint32_t p0 = tid * GZ_RUN, run_lo = max(p0, pad), run_hi = p0 + GZ_RUN;   // run_lo >= run_hi: nothing of the text here
+    // ---- CRC of this thread's run; first occurrence of every 8-byte string that starts in it
     uint32_t crc = 0;
     {
-      uint32_t* hist = S.out + warp * 257u;
       uint32_t c = 0xffffffffu;
-      bool any = false;
-      for (uint32_t w = 0; w < GZ_RUN / 4; ++w) {
-        const uint32_t word = S.text[tid * GZ_ROW_WORDS + w];
-#pragma unroll
-        for (uint32_t bi = 0; bi < 4; ++bi) {
-          if (p0 + 4u * w + bi >= pad) {
-            const uint32_t v = (word >> (8u * bi)) & 0xffu;
-            atomicAdd(&hist[v], 1u);
-            c = S.crc_tab[(c ^ v) & 0xffu] ^ (c >> 8);
-            any = true;
-          }
+      for (uint32_t p = run_lo; p < run_hi; ++p) {
+        c = S.crc_tab[(c ^ gz_text_byte(S, p)) & 0xffu] ^ (c >> 8);
+        if (p + 8u <= GZ_BLOCK) {
+          uint32_t lo, hi;
+          gz_load8(S, p, lo, hi);
+          atomicMin(&S.out[GZ_O_TABLE + gz_hash(lo, hi)], p);
         }
       }
-      crc = any ? ~c : 0u;
+      crc = run_lo < run_hi ? ~c : 0u;
     }
     // CRC of the block: tree over the threads (a left part is moved over its right part by a multiplication)
 #pragma unroll
@@ -204,106 +339,109 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
     }
     if (lane == 31) S.warp_crc[warp] = crc;
     __syncthreads();
-    // ---- symbol counts -> S.code[] temporarily (count), then the Huffman code
-    uint32_t* cnt = S.out + 8u * 257u;            // [257]
-    uint32_t* sorted = cnt + 257u;                // [257] symbols by count, ascending
-    uint32_t* scratch = sorted + 257u;            // thread 0's arrays
+    // ---- greedy parse of the run: a repeat of at least GZ_MIN_MATCH bytes of anything earlier in the block (its first
+    // occurrence: the table does not depend on timing, so the member's bytes are the same on every run), ending
+    // inside the run; histograms of what it emits
     {
-      uint32_t c = 0;
-      for (uint32_t w = 0; w < 8; ++w) c += S.out[w * 257u + tid];
-      cnt[tid] = c;
-      if (tid == 0) cnt[256] = 1;   // end of block
+      uint32_t* hl = S.out + GZ_O_HLIT + warp * GZ_NLIT;
+      uint32_t* hd = S.out + GZ_O_HDIST + warp * GZ_NDIST;
+      uint32_t nt = 0, p = run_lo;
+      while (p < run_hi) {
+        uint32_t len = 0, c = 0;
+        if (p + GZ_MIN_MATCH <= run_hi && nt < GZ_MAX_TOK) {
+          uint32_t lo, hi;
+          gz_load8(S, p, lo, hi);
+          c = S.out[GZ_O_TABLE + gz_hash(lo, hi)];
+          if (c < p) {
+            uint32_t clo, chi;
+            gz_load8(S, c, clo, chi);
+            if (clo == lo && chi == hi) {
+              len = 8;
+              while (p + len < run_hi && len < 258u && gz_text_byte(S, c + len) == gz_text_byte(S, p + len)) ++len;
+            }
+          }
+        }
+        if (len) {
+          S.tok[tid][nt++] = (p - p0) | (len << 7) | ((p - c) << 16);
+          uint32_t sym, eb, ev;
+          gz_len_symbol(len, sym, eb, ev);
+          atomicAdd(&hl[sym], 1u);
+          gz_dist_symbol(p - c, sym, eb, ev);
+          atomicAdd(&hd[sym], 1u);
+          p += len;
+        } else {
+          atomicAdd(&hl[gz_text_byte(S, p)], 1u);
+          ++p;
+        }
+      }
+      S.ntok[tid] = nt;
     }
     __syncthreads();
-    for (uint32_t s = tid; s < 257u; s += GZ_THREADS) {   // rank sort of the used symbols
-      const uint32_t c = cnt[s];
+    // ---- symbol counts (over the dead table), then the two Huffman codes
+    uint32_t* cnt = S.out;                        // [286] literal/length, [30] distance behind them
+    uint32_t* cntd = cnt + GZ_NLIT;
+    uint32_t* sorted = cntd + GZ_NDIST + 2u;      // [286] | [30]
+    uint32_t* sortedd = sorted + GZ_NLIT;
+    uint32_t* scratch = sortedd + GZ_NDIST + 2u;  // thread 0's arrays (1450 words)
+    for (uint32_t s = tid; s < GZ_NLIT + GZ_NDIST; s += GZ_THREADS) {
+      uint32_t c = 0;
+      if (s < GZ_NLIT) {
+        for (uint32_t w = 0; w < 8; ++w) c += S.out[GZ_O_HLIT + w * GZ_NLIT + s];
+        if (s == 256u) c = 1;   // end of block
+      } else {
+        for (uint32_t w = 0; w < 8; ++w) c += S.out[GZ_O_HDIST + w * GZ_NDIST + (s - GZ_NLIT)];
+      }
+      // (the counts overwrite the table area only: the histograms sit behind it)
+      cnt[s < GZ_NLIT ? s : GZ_NLIT + (s - GZ_NLIT)] = c;
+    }
+    __syncthreads();
+    for (uint32_t s = tid; s < GZ_NLIT + GZ_NDIST; s += GZ_THREADS) {   // rank sort of the used symbols of either alphabet
+      const bool lit = s < GZ_NLIT;
+      const uint32_t* cc = lit ? cnt : cntd;
+      const uint32_t me = lit ? s : s - GZ_NLIT, nn = lit ? GZ_NLIT : GZ_NDIST;
+      const uint32_t c = cc[me];
       if (c) {
         uint32_t rank = 0;
-        for (uint32_t u = 0; u < 257u; ++u) {
-          const uint32_t cu = cnt[u];
-          rank += (cu != 0u) & ((cu < c) | ((cu == c) & (u < s)));
+        for (uint32_t u = 0; u < nn; ++u) {
+          const uint32_t cu = cc[u];
+          rank += (cu != 0u) & ((cu < c) | ((cu == c) & (u < me)));
         }
-        sorted[rank] = s;
+        (lit ? sorted : sortedd)[rank] = me;
       }
-      S.code[s] = 0;
+      (lit ? S.code : S.dcode)[me] = 0;
     }
-    const uint32_t m = (uint32_t)__syncthreads_count(cnt[tid] != 0u) + 1u;   // + end of block (symbol 256 is nobody's tid)
+    __syncthreads();
     if (tid == 0) {
-      // two-queue Huffman over the leaves sorted[0 .. m) (ascending): nodes 0..m-1 leaves, m..2m-2 internal
-      uint32_t* iw = scratch;                 // [m - 1] weights of the internal nodes, in creation order (ascending)
-      uint32_t* parent = scratch + 260u;      // [2m - 1]
-      uint32_t* depth = parent + 520u;        // [2m - 1]
-      uint32_t li = 0, ii = 0, ni = 0;
-      for (uint32_t step = 0; step + 1 < m; ++step) {
-        uint32_t pick[2], wsum = 0;
-        for (int t = 0; t < 2; ++t) {
-          const bool leaf = li < m && (ii >= ni || cnt[sorted[li]] <= iw[ii]);
-          if (leaf) {
-            pick[t] = li;
-            wsum += cnt[sorted[li]];
-            ++li;
-          } else {
-            pick[t] = m + ii;
-            wsum += iw[ii];
-            ++ii;
-          }
+      uint32_t m = 0, md = 0, hlit = 257, hdist = 1;
+      for (uint32_t s = 0; s < GZ_NLIT; ++s)
+        if (cnt[s]) {
+          ++m;
+          if (s >= 257u) hlit = s + 1u;
         }
-        iw[ni] = wsum;
-        parent[pick[0]] = parent[pick[1]] = m + ni;
-        ++ni;
-      }
-      uint32_t bl_count[17];
-      for (int i = 0; i < 17; ++i) bl_count[i] = 0;
-      int overflow = 0;
-      if (m == 1) {
-        bl_count[1] = 1;
-      } else {
-        depth[2u * m - 2u] = 0;
-        for (int node = (int)(2u * m - 3u); node >= 0; --node) {
-          uint32_t d = depth[parent[node]] + 1u;
-          depth[node] = d;
-          if ((uint32_t)node < m) {
-            if (d > 15u) {
-              d = 15u;
-              ++overflow;
-            }
-            ++bl_count[d];
-          }
+      for (uint32_t s = 0; s < GZ_NDIST; ++s)
+        if (cntd[s]) {
+          ++md;
+          hdist = s + 1u;
         }
+      uint32_t bits = gz_build_code(cnt, GZ_NLIT, sorted, m, scratch, S.code);
+      if (md >= 2u) {
+        bits += gz_build_code(cntd, GZ_NDIST, sortedd, md, scratch, S.dcode);
+      } else {   // none or one distance in use: two one-bit codes make the set complete for every inflater
+        const uint32_t used = md ? sortedd[0] : 0u, other = used ? 0u : 1u;
+        S.dcode[used] = 0u | (1u << 16);
+        S.dcode[other] = 1u | (1u << 16);
+        if (used > other) {   // canonical order: the lower symbol takes code 0
+          S.dcode[other] = 0u | (1u << 16);
+          S.dcode[used] = 1u | (1u << 16);
+        }
+        hdist = max(hdist, 2u);
+        bits += md ? cntd[used] : 0u;
       }
-      while (overflow > 0) {   // zlib's gen_bitlen: move a leaf down one level, two overflowing leaves up
-        uint32_t bits = 14;
-        while (bl_count[bits] == 0) --bits;
-        --bl_count[bits];
-        bl_count[bits + 1] += 2;
-        --bl_count[15];
-        overflow -= 2;
-      }
-      // the rarest symbols take the longest codes
-      uint32_t lens_total = 0;
-      {
-        uint32_t i = 0;
-        for (uint32_t bits = 15; bits >= 1; --bits)
-          for (uint32_t c = 0; c < bl_count[bits]; ++c) {
-            const uint32_t s = sorted[i++];
-            S.code[s] = bits << 16;
-            lens_total += bits * cnt[s];
-          }
-      }
-      // canonical codes, bit-reversed (deflate packs Huffman codes starting with their most significant bit)
-      uint32_t next_code[16], code = 0;
-      bl_count[0] = 0;
-      for (uint32_t bits = 1; bits <= 15; ++bits) {
-        code = (code + bl_count[bits - 1]) << 1;
-        next_code[bits] = code;
-      }
-      for (uint32_t s = 0; s < 257u; ++s) {
-        const uint32_t len = S.code[s] >> 16;
-        if (!len) continue;
-        const uint32_t c = next_code[len]++;
-        S.code[s] = (__brev(c) >> (32u - len)) | (len << 16);
-      }
-      S.total_bits = GZ_TABLE_BITS + lens_total;
+      for (uint32_t s = 265u; s < 285u; ++s) bits += cnt[s] * gz_len_extra(s);
+      for (uint32_t s = 4u; s < GZ_NDIST; ++s) bits += cntd[s] * gz_dist_extra(s);
+      S.hlit = hlit;
+      S.hdist = hdist;
+      S.total_bits = 3u + 14u + 19u * 3u + 4u * (hlit + hdist) + bits;
       S.stored = (S.total_bits + 7u) / 8u >= n + 5u;
       // the whole block's CRC: the warps' parts, left to right
       uint32_t c = S.warp_crc[0];
@@ -311,7 +449,8 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
       S.warp_crc[0] = c;
     }
     __syncthreads();
-    const uint32_t total_bits = S.total_bits, stored = S.stored;
+    const uint32_t total_bits = S.total_bits, stored = S.stored, hlit = S.hlit, hdist = S.hdist;
+    const uint32_t table_bits = 3u + 14u + 19u * 3u + 4u * (hlit + hdist);
     const uint32_t deflate_bytes = stored ? n + 5u : (total_bits + 7u) / 8u;
     const uint32_t member = GZ_HDR + deflate_bytes + GZ_TRL;
     for (uint32_t i = tid; i < GZ_OUT_WORDS; i += GZ_THREADS) S.out[i] = 0;
@@ -319,12 +458,24 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
     uint8_t* ob = reinterpret_cast<uint8_t*>(S.out);
     if (!stored) {
       // ---- bits of every thread's run, block-wide exclusive scan
+      const uint32_t nt = S.ntok[tid];
       uint32_t my_bits = 0;
-      for (uint32_t w = 0; w < GZ_RUN / 4; ++w) {
-        const uint32_t word = S.text[tid * GZ_ROW_WORDS + w];
-#pragma unroll
-        for (uint32_t bi = 0; bi < 4; ++bi)
-          if (p0 + 4u * w + bi >= pad) my_bits += S.code[(word >> (8u * bi)) & 0xffu] >> 16;
+      {
+        uint32_t kt = 0, p = run_lo;
+        while (p < run_hi) {
+          if (kt < nt && (S.tok[tid][kt] & 127u) == p - p0) {
+            const uint32_t t = S.tok[tid][kt++], len = (t >> 7) & 511u, dist = t >> 16;
+            uint32_t sym, eb, ev;
+            gz_len_symbol(len, sym, eb, ev);
+            my_bits += (S.code[sym] >> 16) + eb;
+            gz_dist_symbol(dist, sym, eb, ev);
+            my_bits += (S.dcode[sym] >> 16) + eb;
+            p += len;
+          } else {
+            my_bits += S.code[gz_text_byte(S, p)] >> 16;
+            ++p;
+          }
+        }
       }
       uint32_t incl = my_bits;
 #pragma unroll
@@ -336,7 +487,7 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
       __syncthreads();
       uint32_t before = 0;
       for (uint32_t w = 0; w < warp; ++w) before += S.warp_bits[w];
-      uint32_t at = 8u * GZ_HDR + GZ_TABLE_BITS + before + incl - my_bits;   // bit position of this thread's first code
+      const uint32_t at = 8u * GZ_HDR + table_bits + before + incl - my_bits;   // bit position of this thread's first code
       // ---- OR the codes into the image (zeroed): a 64-bit accumulator, whole words out
       uint32_t wi = at >> 5, nb = at & 31u;
       unsigned long long acc = 0;
@@ -349,7 +500,7 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
           nb -= 32u;
         }
       };
-      if (tid == 0) {   // block header in front of the first code: BFINAL=1, BTYPE=10, HLIT=0 (257), HDIST=1 (2), HCLEN=15 (19)
+      if (tid == 0) {   // block header in front of the first code: BFINAL=1, BTYPE=10, HLIT, HDIST, HCLEN=15 (19)
         uint32_t hw = 8u * GZ_HDR >> 5, hb = (8u * GZ_HDR) & 31u;
         unsigned long long hacc = 0;
         auto hput = [&](uint32_t bits, uint32_t len) {
@@ -362,26 +513,36 @@ __global__ void __launch_bounds__(GZ_THREADS, 3) k_gz_blocks(GzDev g, GzConsts K
           }
         };
         hput(1u | (2u << 1), 3);
-        hput(0u, 5);
-        hput(1u, 5);
+        hput(hlit - 257u, 5);
+        hput(hdist - 1u, 5);
         hput(15u, 4);
         // code-length code: the lengths 0..15 as 4-bit codes, the repeat symbols 16-18 unused (order 16,17,18,0,8,...)
         for (int i = 0; i < 19; ++i) hput(i < 3 ? 0u : 4u, 3);
-        for (uint32_t s = 0; s < 257u; ++s) hput(__brev(S.code[s] >> 16) >> 28, 4);   // canonical 4-bit code of value v is v, sent MSB first
-        hput(__brev(1u) >> 28, 4);   // two distance codes of one bit each (never used; a complete set for every inflater)
-        hput(__brev(1u) >> 28, 4);
+        for (uint32_t s = 0; s < hlit; ++s) hput(__brev(S.code[s] >> 16) >> 28, 4);   // canonical 4-bit code of value v is v, sent MSB first
+        for (uint32_t s = 0; s < hdist; ++s) hput(__brev(S.dcode[s] >> 16) >> 28, 4);
         if (hb) atomicOr(&S.out[hw], (uint32_t)hacc);
       }
-      for (uint32_t w = 0; w < GZ_RUN / 4; ++w) {
-        const uint32_t word = S.text[tid * GZ_ROW_WORDS + w];
-#pragma unroll
-        for (uint32_t bi = 0; bi < 4; ++bi)
-          if (p0 + 4u * w + bi >= pad) {
-            const uint32_t e = S.code[(word >> (8u * bi)) & 0xffu];
+      {
+        uint32_t kt = 0, p = run_lo;
+        while (p < run_hi) {
+          if (kt < nt && (S.tok[tid][kt] & 127u) == p - p0) {
+            const uint32_t t = S.tok[tid][kt++], len = (t >> 7) & 511u, dist = t >> 16;
+            uint32_t sym, eb, ev;
+            gz_len_symbol(len, sym, eb, ev);
+            uint32_t e = S.code[sym];
+            put((e & 0xffffu) | (ev << (e >> 16)), (e >> 16) + eb);
+            gz_dist_symbol(dist, sym, eb, ev);
+            e = S.dcode[sym];
+            put((e & 0xffffu) | (ev << (e >> 16)), (e >> 16) + eb);
+            p += len;
+          } else {
+            const uint32_t e = S.code[gz_text_byte(S, p)];
             put(e & 0xffffu, e >> 16);
+            ++p;
           }
+        }
       }
-      if (tid == GZ_THREADS - 1) put(S.code[256] & 0xffffu, S.code[256] >> 16);   // end of block after the last literal
+      if (tid == GZ_THREADS - 1) put(S.code[256] & 0xffffu, S.code[256] >> 16);   // end of block after the last symbol
       if (nb) atomicOr(&S.out[wi], (uint32_t)acc);
       __syncthreads();
     } else {

@@ -559,7 +559,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
     const uint64_t out_bound = std::min<uint64_t>(ctx->out_cap, r2_len + r1_len + rec_bound * ((uint64_t)P.prefix_len + 2ull * P.BL + 32ull));
     const uint32_t blocks_bound = (uint32_t)std::min<uint64_t>(s.gz.blocks_cap, out_bound / GZ_BLOCK + 2ull * P.total + 2ull);
     k_gz_plan<<<1, 1024, 0, st>>>(s.gz);
-    k_gz_blocks<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 3u), GZ_THREADS, sizeof(GzShared), st>>>(s.gz, ctx->gzk);
+    k_gz_blocks<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 2u), GZ_THREADS, sizeof(GzShared), st>>>(s.gz, ctx->gzk);
     k_gz_scan<<<1, 1024, 0, st>>>(s.gz);
     k_gz_pack<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 8u), 256, 0, st>>>(s.gz);
     ctx->launches += 4;
