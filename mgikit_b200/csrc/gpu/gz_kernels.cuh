@@ -317,19 +317,30 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
     if (tid < 4) S.text[GZ_THREADS * GZ_ROW_WORDS + tid] = 0;
     __syncthreads();
     const uint32_t p0 = tid * GZ_RUN, run_lo = max(p0, pad), run_hi = p0 + GZ_RUN;   // run_lo >= run_hi: nothing of the text here
-    // ---- CRC of this thread's run; first occurrence of every 8-byte string that starts in it
+    // ---- CRC of this thread's run; first occurrence of every 8-byte string that starts in it.  The run's words pass
+    // through three registers (the 8 bytes at a position span at most three words)
     uint32_t crc = 0;
-    {
+    if (run_lo < run_hi) {
       uint32_t c = 0xffffffffu;
-      for (uint32_t p = run_lo; p < run_hi; ++p) {
-        c = S.crc_tab[(c ^ gz_text_byte(S, p)) & 0xffu] ^ (c >> 8);
-        if (p + 8u <= GZ_BLOCK) {
-          uint32_t lo, hi;
-          gz_load8(S, p, lo, hi);
-          atomicMin(&S.out[GZ_O_TABLE + gz_hash(lo, hi)], p);
+      const uint32_t g0 = tid * (GZ_RUN / 4u);
+      uint32_t a = gz_word(S, g0), b = gz_word(S, g0 + 1u), d = gz_word(S, g0 + 2u);
+      for (uint32_t i = 0; i < GZ_RUN / 4u; ++i) {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint32_t p = p0 + 4u * i + k;
+          if (p >= run_lo) {
+            c = S.crc_tab[(c ^ (a >> (8u * k))) & 0xffu] ^ (c >> 8);
+            if (p + 8u <= GZ_BLOCK) {
+              const uint32_t lo = k ? __funnelshift_r(a, b, 8u * k) : a, hi = k ? __funnelshift_r(b, d, 8u * k) : b;
+              atomicMin(&S.out[GZ_O_TABLE + gz_hash(lo, hi)], p);
+            }
+          }
         }
+        a = b;
+        b = d;
+        d = gz_word(S, min(g0 + i + 3u, GZ_BLOCK / 4u));   // (the word behind the block is zero padding)
       }
-      crc = run_lo < run_hi ? ~c : 0u;
+      crc = ~c;
     }
     // CRC of the block: tree over the threads (a left part is moved over its right part by a multiplication)
 #pragma unroll
@@ -346,11 +357,23 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       uint32_t* hl = S.out + GZ_O_HLIT + warp * GZ_NLIT;
       uint32_t* hd = S.out + GZ_O_HDIST + warp * GZ_NDIST;
       uint32_t nt = 0, p = run_lo;
+      uint32_t cg = 0xfffffff0u, a = 0, b = 0, d = 0;   // words cg, cg + 1, cg + 2 of the text
       while (p < run_hi) {
+        const uint32_t g = p >> 2, k8 = (p & 3u) * 8u;
+        if (g != cg) {
+          if (g == cg + 1u) {
+            a = b;
+            b = d;
+          } else {
+            a = gz_word(S, g);
+            b = gz_word(S, g + 1u);
+          }
+          d = gz_word(S, min(g + 2u, GZ_BLOCK / 4u));
+          cg = g;
+        }
         uint32_t len = 0, c = 0;
         if (p + GZ_MIN_MATCH <= run_hi && nt < GZ_MAX_TOK) {
-          uint32_t lo, hi;
-          gz_load8(S, p, lo, hi);
+          const uint32_t lo = k8 ? __funnelshift_r(a, b, k8) : a, hi = k8 ? __funnelshift_r(b, d, k8) : b;
           c = S.out[GZ_O_TABLE + gz_hash(lo, hi)];
           if (c < p) {
             uint32_t clo, chi;
@@ -370,7 +393,7 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
           atomicAdd(&hd[sym], 1u);
           p += len;
         } else {
-          atomicAdd(&hl[gz_text_byte(S, p)], 1u);
+          atomicAdd(&hl[(a >> k8) & 0xffu], 1u);
           ++p;
         }
       }
@@ -395,20 +418,32 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       cnt[s < GZ_NLIT ? s : GZ_NLIT + (s - GZ_NLIT)] = c;
     }
     __syncthreads();
-    for (uint32_t s = tid; s < GZ_NLIT + GZ_NDIST; s += GZ_THREADS) {   // rank sort of the used symbols of either alphabet
+    // the used symbols of either alphabet, listed (any order), then ranked among themselves by (count, symbol)
+    uint32_t* used = scratch + 1500u;             // [286] | [30]
+    uint32_t* usedd = used + GZ_NLIT;
+    if (tid == 0) S.hlit = S.hdist = 0;           // (list lengths for now)
+    __syncthreads();
+    for (uint32_t s = tid; s < GZ_NLIT + GZ_NDIST; s += GZ_THREADS) {
       const bool lit = s < GZ_NLIT;
-      const uint32_t* cc = lit ? cnt : cntd;
-      const uint32_t me = lit ? s : s - GZ_NLIT, nn = lit ? GZ_NLIT : GZ_NDIST;
-      const uint32_t c = cc[me];
-      if (c) {
+      const uint32_t me = lit ? s : s - GZ_NLIT;
+      if ((lit ? cnt : cntd)[me]) (lit ? used : usedd)[atomicAdd(lit ? &S.hlit : &S.hdist, 1u)] = me;
+      (lit ? S.code : S.dcode)[me] = 0;
+    }
+    __syncthreads();
+    {
+      const uint32_t m = S.hlit, md = S.hdist;
+      for (uint32_t i = tid; i < m + md; i += GZ_THREADS) {
+        const bool lit = i < m;
+        const uint32_t* cc = lit ? cnt : cntd;
+        const uint32_t* uu = lit ? used : usedd;
+        const uint32_t nn = lit ? m : md, me = uu[lit ? i : i - m], c = cc[me];
         uint32_t rank = 0;
         for (uint32_t u = 0; u < nn; ++u) {
-          const uint32_t cu = cc[u];
-          rank += (cu != 0u) & ((cu < c) | ((cu == c) & (u < me)));
+          const uint32_t o = uu[u], cu = cc[o];
+          rank += (cu < c) | ((cu == c) & (o < me));
         }
         (lit ? sorted : sortedd)[rank] = me;
       }
-      (lit ? S.code : S.dcode)[me] = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -460,6 +495,7 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       // ---- bits of every thread's run, block-wide exclusive scan
       const uint32_t nt = S.ntok[tid];
       uint32_t my_bits = 0;
+      uint32_t cgw = 0xffffffffu, cw = 0;   // the text word the walk is in
       {
         uint32_t kt = 0, p = run_lo;
         while (p < run_hi) {
@@ -472,7 +508,11 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
             my_bits += (S.dcode[sym] >> 16) + eb;
             p += len;
           } else {
-            my_bits += S.code[gz_text_byte(S, p)] >> 16;
+            if ((p >> 2) != cgw) {
+              cgw = p >> 2;
+              cw = gz_word(S, cgw);
+            }
+            my_bits += S.code[(cw >> ((p & 3u) * 8u)) & 0xffu] >> 16;
             ++p;
           }
         }
@@ -536,7 +576,11 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
             put((e & 0xffffu) | (ev << (e >> 16)), (e >> 16) + eb);
             p += len;
           } else {
-            const uint32_t e = S.code[gz_text_byte(S, p)];
+            if ((p >> 2) != cgw) {
+              cgw = p >> 2;
+              cw = gz_word(S, cgw);
+            }
+            const uint32_t e = S.code[(cw >> ((p & 3u) * 8u)) & 0xffu];
             put(e & 0xffffu, e >> 16);
             ++p;
           }
