@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) k_gz_plan(GzDev g) {
 
 // ---------------------------------------------------------------- blocks
 constexpr uint32_t GZ_MAX_TOK = 16;        // matches per thread run (at least GZ_MIN_MATCH bytes each)
-constexpr uint32_t GZ_MIN_MATCH = 8;       // shorter repeats do not pay for their distance bits
+constexpr uint32_t GZ_MIN_MATCH = 12;      // shorter repeats do not pay for their distance bits (and random bases repeat 8-mers all the time)
 constexpr uint32_t GZ_HASH_BITS = 12;
 constexpr uint32_t GZ_NLIT = 286, GZ_NDIST = 30;
 
@@ -141,22 +141,12 @@ __device__ __forceinline__ uint32_t gz_word(const GzShared& S, uint32_t g) { ret
 __device__ __forceinline__ uint32_t gz_text_byte(const GzShared& S, uint32_t pos) {   // pos in right-aligned coordinates
   return (gz_word(S, pos >> 2) >> (8u * (pos & 3u))) & 0xffu;
 }
-// the 8 bytes at pos (pos + 8 <= GZ_BLOCK)
-__device__ __forceinline__ void gz_load8(const GzShared& S, uint32_t pos, uint32_t& lo, uint32_t& hi) {
-  const uint32_t g = pos >> 2, sh = (pos & 3u) * 8u;
-  const uint32_t a = gz_word(S, g), b = gz_word(S, g + 1u);
-  if (sh) {
-    const uint32_t c = gz_word(S, g + 2u);
-    lo = __funnelshift_r(a, b, sh);
-    hi = __funnelshift_r(b, c, sh);
-  } else {
-    lo = a;
-    hi = b;
-  }
+// slot and tag of a 12-byte string: the table keeps, per slot, position << 16 | tag of the FIRST string that hashes there
+__device__ __forceinline__ uint32_t gz_hash(uint32_t w0, uint32_t w1, uint32_t w2) {
+  return (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du);
 }
-__device__ __forceinline__ uint32_t gz_hash(uint32_t lo, uint32_t hi) {
-  return ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u)) >> (32u - GZ_HASH_BITS);
-}
+__device__ __forceinline__ uint32_t gz_slot(uint32_t h) { return h >> (32u - GZ_HASH_BITS); }
+__device__ __forceinline__ uint32_t gz_tag(uint32_t h) { return (h >> 3) & 0xffffu; }
 // deflate's length / distance alphabets (RFC 1951 3.2.5)
 __device__ __forceinline__ void gz_len_symbol(uint32_t len, uint32_t& sym, uint32_t& eb, uint32_t& ev) {
   if (len == 258u) {
@@ -323,22 +313,23 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
     if (run_lo < run_hi) {
       uint32_t c = 0xffffffffu;
       const uint32_t g0 = tid * (GZ_RUN / 4u);
-      uint32_t a = gz_word(S, g0), b = gz_word(S, g0 + 1u), d = gz_word(S, g0 + 2u);
+      uint32_t a = gz_word(S, g0), b = gz_word(S, g0 + 1u), d = gz_word(S, g0 + 2u), e = gz_word(S, min(g0 + 3u, GZ_BLOCK / 4u));
       for (uint32_t i = 0; i < GZ_RUN / 4u; ++i) {
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) {
           const uint32_t p = p0 + 4u * i + k;
           if (p >= run_lo) {
             c = S.crc_tab[(c ^ (a >> (8u * k))) & 0xffu] ^ (c >> 8);
-            if (p + 8u <= GZ_BLOCK) {
-              const uint32_t lo = k ? __funnelshift_r(a, b, 8u * k) : a, hi = k ? __funnelshift_r(b, d, 8u * k) : b;
-              atomicMin(&S.out[GZ_O_TABLE + gz_hash(lo, hi)], p);
+            if (p + GZ_MIN_MATCH <= GZ_BLOCK) {
+              const uint32_t h = k ? gz_hash(__funnelshift_r(a, b, 8u * k), __funnelshift_r(b, d, 8u * k), __funnelshift_r(d, e, 8u * k)) : gz_hash(a, b, d);
+              atomicMin(&S.out[GZ_O_TABLE + gz_slot(h)], (p << 16) | gz_tag(h));
             }
           }
         }
         a = b;
         b = d;
-        d = gz_word(S, min(g0 + i + 3u, GZ_BLOCK / 4u));   // (the word behind the block is zero padding)
+        d = e;
+        e = gz_word(S, min(g0 + i + 4u, GZ_BLOCK / 4u));   // (the words behind the block are zero padding)
       }
       crc = ~c;
     }
@@ -357,30 +348,33 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       uint32_t* hl = S.out + GZ_O_HLIT + warp * GZ_NLIT;
       uint32_t* hd = S.out + GZ_O_HDIST + warp * GZ_NDIST;
       uint32_t nt = 0, p = run_lo;
-      uint32_t cg = 0xfffffff0u, a = 0, b = 0, d = 0;   // words cg, cg + 1, cg + 2 of the text
+      uint32_t cg = 0xfffffff0u, a = 0, b = 0, d = 0, e = 0;   // words cg .. cg + 3 of the text
       while (p < run_hi) {
         const uint32_t g = p >> 2, k8 = (p & 3u) * 8u;
         if (g != cg) {
           if (g == cg + 1u) {
             a = b;
             b = d;
+            d = e;
           } else {
             a = gz_word(S, g);
             b = gz_word(S, g + 1u);
+            d = gz_word(S, min(g + 2u, GZ_BLOCK / 4u));
           }
-          d = gz_word(S, min(g + 2u, GZ_BLOCK / 4u));
+          e = gz_word(S, min(g + 3u, GZ_BLOCK / 4u));
           cg = g;
         }
         uint32_t len = 0, c = 0;
         if (p + GZ_MIN_MATCH <= run_hi && nt < GZ_MAX_TOK) {
-          const uint32_t lo = k8 ? __funnelshift_r(a, b, k8) : a, hi = k8 ? __funnelshift_r(b, d, k8) : b;
-          c = S.out[GZ_O_TABLE + gz_hash(lo, hi)];
-          if (c < p) {
-            uint32_t clo, chi;
-            gz_load8(S, c, clo, chi);
-            if (clo == lo && chi == hi) {
-              len = 8;
+          const uint32_t h = k8 ? gz_hash(__funnelshift_r(a, b, k8), __funnelshift_r(b, d, k8), __funnelshift_r(d, e, k8)) : gz_hash(a, b, d);
+          const uint32_t entry = S.out[GZ_O_TABLE + gz_slot(h)];
+          c = entry >> 16;
+          if (c < p && (entry & 0xffffu) == gz_tag(h)) {   // very likely the same 12 bytes: compare, then extend
+            while (len < GZ_MIN_MATCH && gz_text_byte(S, c + len) == gz_text_byte(S, p + len)) ++len;
+            if (len == GZ_MIN_MATCH) {
               while (p + len < run_hi && len < 258u && gz_text_byte(S, c + len) == gz_text_byte(S, p + len)) ++len;
+            } else {
+              len = 0;
             }
           }
         }
