@@ -141,6 +141,12 @@ __device__ __forceinline__ uint32_t gz_word(const GzShared& S, uint32_t g) { ret
 __device__ __forceinline__ uint32_t gz_text_byte(const GzShared& S, uint32_t pos) {   // pos in right-aligned coordinates
   return (gz_word(S, pos >> 2) >> (8u * (pos & 3u))) & 0xffu;
 }
+// the 4 bytes at pos (any alignment; words behind the block are zero padding)
+__device__ __forceinline__ uint32_t gz_load4(const GzShared& S, uint32_t pos) {
+  const uint32_t g = pos >> 2, sh = (pos & 3u) * 8u;
+  const uint32_t a = gz_word(S, min(g, GZ_BLOCK / 4u));
+  return sh ? __funnelshift_r(a, gz_word(S, min(g + 1u, GZ_BLOCK / 4u)), sh) : a;
+}
 // slot and tag of a 12-byte string: the table keeps, per slot, position << 16 | tag of the FIRST string that hashes there
 __device__ __forceinline__ uint32_t gz_hash(uint32_t w0, uint32_t w1, uint32_t w2) {
   return (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du);
@@ -370,12 +376,17 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
           const uint32_t entry = S.out[GZ_O_TABLE + gz_slot(h)];
           c = entry >> 16;
           if (c < p && (entry & 0xffffu) == gz_tag(h)) {   // very likely the same 12 bytes: compare, then extend
-            while (len < GZ_MIN_MATCH && gz_text_byte(S, c + len) == gz_text_byte(S, p + len)) ++len;
-            if (len == GZ_MIN_MATCH) {
-              while (p + len < run_hi && len < 258u && gz_text_byte(S, c + len) == gz_text_byte(S, p + len)) ++len;
-            } else {
-              len = 0;
+            const uint32_t max_len = min(258u, run_hi - p);
+            while (len < max_len) {   // four bytes at a time
+              const uint32_t x = gz_load4(S, c + len) ^ gz_load4(S, p + len);
+              if (x) {
+                len += (uint32_t)(__ffs((int)x) - 1) >> 3;
+                break;
+              }
+              len += 4u;
             }
+            len = min(len, max_len);
+            if (len < GZ_MIN_MATCH) len = 0;
           }
         }
         if (len) {
