@@ -4,12 +4,14 @@
 // compare decompressed text, tests/integration_test.rs:44-53 -- the decompressed bytes are).
 //
 // One member per GZ_BLOCK = 32 KiB of text, BGZF-framed (extra field "BC", so bgzip-aware tools can index the
-// files), holding ONE dynamic-Huffman deflate block of literals only: FASTQ text out of this path is three
-// order-0 populations (bases, qualities, header characters); a per-block Huffman code takes what a level-1 LZ takes
-// on it, and all of it parallelises: histogram -> code lengths (two-queue Huffman, lengths capped at 15 like
-// zlib's gen_bitlen) -> bit offsets by a block-wide scan -> every thread ORs the codes of its 128 bytes into the
-// shared-memory image of the member.  CRC-32 per thread, combined with carry-less multiplications by x^(8*128*2^j).
-// A block that would not shrink is stored.
+// files), holding ONE dynamic-Huffman deflate block.  Per 256-thread CTA: the text is staged in shared memory, every
+// thread owns a run of 128 bytes; a first-occurrence table over the 12-byte strings of the block (position | tag per
+// slot, filled with atomicMin: the result does not depend on timing, so the member's bytes are the same on every
+// run) gives each run its repeats of 12 bytes or more (the rewritten headers of consecutive records of a sample, runs
+// of equal qualities; random bases repeat shorter strings all the time and are cheaper as literals); histograms ->
+// two Huffman codes (two-queue construction, lengths capped at 15 like zlib's gen_bitlen) -> bit offsets by a
+// block-wide scan -> every thread ORs the codes of its run into the shared-memory image of the member.  CRC-32 per
+// thread, combined with carry-less multiplications by x^(8*128*2^j).  A block that would not shrink is stored.
 //
 //   k_gz_plan    blocks per (read, bin) run, their prefix
 //   k_gz_blocks  persistent, one 32 KiB block per CTA at a time -> a member in its worst-case sized slot
@@ -503,9 +505,11 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       uint32_t cgw = 0xffffffffu, cw = 0;   // the text word the walk is in
       {
         uint32_t kt = 0, p = run_lo;
+        uint32_t t = nt ? S.tok[tid][0] : 0xffffffffu;   // the next match (its position in the low 7 bits), kept in a register
         while (p < run_hi) {
-          if (kt < nt && (S.tok[tid][kt] & 127u) == p - p0) {
-            const uint32_t t = S.tok[tid][kt++], len = (t >> 7) & 511u, dist = t >> 16;
+          if (kt < nt && (t & 127u) == p - p0) {
+            const uint32_t len = (t >> 7) & 511u, dist = t >> 16;
+            t = ++kt < nt ? S.tok[tid][kt] : 0xffffffffu;
             uint32_t sym, eb, ev;
             gz_len_symbol(len, sym, eb, ev);
             my_bits += (S.code[sym] >> 16) + eb;
@@ -569,9 +573,11 @@ __global__ void __launch_bounds__(GZ_THREADS, 2) k_gz_blocks(GzDev g, GzConsts K
       }
       {
         uint32_t kt = 0, p = run_lo;
+        uint32_t t = nt ? S.tok[tid][0] : 0xffffffffu;
         while (p < run_hi) {
-          if (kt < nt && (S.tok[tid][kt] & 127u) == p - p0) {
-            const uint32_t t = S.tok[tid][kt++], len = (t >> 7) & 511u, dist = t >> 16;
+          if (kt < nt && (t & 127u) == p - p0) {
+            const uint32_t len = (t >> 7) & 511u, dist = t >> 16;
+            t = ++kt < nt ? S.tok[tid][kt] : 0xffffffffu;
             uint32_t sym, eb, ev;
             gz_len_symbol(len, sym, eb, ev);
             uint32_t e = S.code[sym];
