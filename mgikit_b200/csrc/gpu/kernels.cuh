@@ -710,11 +710,10 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
       const uint32_t mis = (uint32_t)(a & 3u);
       if (hl >= L + 13u && hl - 3u + mis <= L + 32u) {   // the fields end inside the window (else record_plan reads them)
         const uint32_t* w = reinterpret_cast<const uint32_t*>(a - mis);
-        const uint32_t need = hl - 3u - L + mis;   // window bytes in front of the '/' (touch no sector the fields are not in)
         uint32_t nz = 0;   // bit j: byte j of the window is not '0'
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t v = (4u * (uint32_t)k < need ? __ldg(w + k) : 0x30303030u) ^ 0x30303030u;
+          const uint32_t v = __ldg(w + k) ^ 0x30303030u;
           const uint32_t t = ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v;   // bit 7 of a byte set <=> the byte is not zero
           nz |= (((t & 0x80808080u) >> 7) * 0x10204080u >> 28) << (4 * k);   // the four flags of the word, byte order
         }
