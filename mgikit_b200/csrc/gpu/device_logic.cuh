@@ -356,15 +356,7 @@ MGK_HD uint32_t barcode_text_len(const Params& P, int bar_t) {
 }
 MGK_HD uint32_t umi_text_len(const Params& P, int umi_t) { return umi_t < 0 ? 0u : 1u + (uint32_t)P.tpl[umi_t].g[7]; }
 
-// The three digit fields of an MGI header as found ahead of time (k_match_plan fetches the header's tail in one go,
-// together with the barcode, instead of walking it byte by byte behind the match): valid == 0 -> record_plan reads them.
-struct HdrDigits {
-  uint32_t z, f1, f2;
-  int valid;
-};
-
-MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G, int sample, int bar_t, int umi_t,
-                           const HdrDigits* pre = nullptr) {
+MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G, int sample, int bar_t, int umi_t) {
   RecPlan pl;
   pl.z = pl.f1 = pl.f2 = 0;
   const uint32_t BL = (uint32_t)P.BL, L = (uint32_t)P.L;
@@ -388,22 +380,15 @@ MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G,
   if (P.out_mode == MGK_OUT_ILLUMINA) {
     const uint8_t* H = r2 + G.h2;
     const uint32_t sep = hl - 3u;
-    if (pre && pre->valid) {
-      pl.z = pre->z;
-      pl.f1 = pre->f1;
-      pl.f2 = pre->f2;
-    } else {
-      uint32_t z = sep;
-      for (uint32_t i = L + 10u; i < sep; ++i)
-        if (ldg_u8(H + i) != '0') {
-          z = i;
-          break;
-        }
-      pl.z = z;
-      pl.f1 = ldg_u8(H + L + 3) != '0' ? L + 3u : (ldg_u8(H + L + 4) != '0' ? L + 4u : L + 5u);
-      pl.f2 = ldg_u8(H + L + 7) != '0' ? L + 7u : (ldg_u8(H + L + 8) != '0' ? L + 8u : L + 9u);
-    }
-    const uint32_t z = pl.z;
+    uint32_t z = sep;
+    for (uint32_t i = L + 10u; i < sep; ++i)
+      if (ldg_u8(H + i) != '0') {
+        z = i;
+        break;
+      }
+    pl.z = z;
+    pl.f1 = ldg_u8(H + L + 3) != '0' ? L + 3u : (ldg_u8(H + L + 4) != '0' ? L + 4u : L + 5u);
+    pl.f2 = ldg_u8(H + L + 7) != '0' ? L + 7u : (ldg_u8(H + L + 8) != '0' ? L + 8u : L + 9u);
     hdr2 = (uint32_t)P.prefix_len + 2u + (sep - z) + 1u + (L + 6u - pl.f1) + 1u + (L + 10u - pl.f2) + utl + 7u + btl;
     hdr1 = hdr2;
   } else if (P.out_mode == MGK_OUT_MGI_FULL_HEADER) {

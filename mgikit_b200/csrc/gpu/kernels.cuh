@@ -699,38 +699,10 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
         bar = c.r2 + bar_off;
       }
     }
-    // the header's digit fields (leading zeros decide the length of the rewritten header): the 32 bytes from the lane
-    // letter on are fetched NOW, in flight together with the barcode, not walked byte by byte behind the match
-    HdrDigits hd;
-    hd.valid = 0;
-    hd.z = hd.f1 = hd.f2 = 0;
-    if (active && P.out_mode == MGK_OUT_ILLUMINA) {
-      const uint32_t hl = G.s2 - G.h2, L = (uint32_t)P.L;
-      const uintptr_t a = (uintptr_t)(c.r2 + G.h2 + L);
-      const uint32_t mis = (uint32_t)(a & 3u);
-      if (hl >= L + 13u && hl - 3u + mis <= L + 32u) {   // the fields end inside the window (else record_plan reads them)
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(a - mis);
-        uint32_t nz = 0;   // bit j: byte j of the window is not '0'
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t v = __ldg(w + k) ^ 0x30303030u;
-          const uint32_t t = ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v;   // bit 7 of a byte set <=> the byte is not zero
-          nz |= (((t & 0x80808080u) >> 7) * 0x10204080u >> 28) << (4 * k);   // the four flags of the word, byte order
-        }
-        const uint32_t sep = hl - 3u;
-        auto bit = [&](uint32_t i) { return (nz >> (i - L + mis)) & 1u; };   // header byte i is not '0'
-        const uint32_t lo = 10u + mis, hi = sep - L + mis;                    // window bits of [L + 10, sep)
-        const uint32_t field = hi > lo ? (nz >> lo) & (hi - lo >= 32u ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) : 0u;
-        hd.z = field ? L + 10u + (uint32_t)(__ffs((int)field) - 1) : sep;
-        hd.f1 = bit(L + 3u) ? L + 3u : (bit(L + 4u) ? L + 4u : L + 5u);
-        hd.f2 = bit(L + 7u) ? L + 7u : (bit(L + 8u) ? L + 8u : L + 9u);
-        hd.valid = 1;
-      }
-    }
     const MatchOut mo = cta_match(P, s_codes, bar, ms);   // CTA-wide: every thread calls it
     if (active) {
       if (mo.panicked) atomicOr(&c.status->error, ERR_PANIC);
-      const RecPlan pl = record_plan(P, c.r2, G, mo.sample, mo.bar_t, mo.umi_t, &hd);
+      const RecPlan pl = record_plan(P, c.r2, G, mo.sample, mo.bar_t, mo.umi_t);
       if (pl.fmt_error) {
         atomicMin(&c.status->fmt_record, (unsigned long long)rec);
         mt.flags = 1;
