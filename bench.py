@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="chunks in flight in the resident leg (= slots of the context)")
     return ap.parse_args()
 
 
@@ -148,18 +149,21 @@ def cpu_run(lane, n_pairs, steps, warmup):
 
 
 # ------------------------------------------------------------------ resident runs (any lane)
-def resident_run(hp, dev_args, n_chunks, flags):
-    """n_chunks submissions of the resident block, two in flight; returns (per-kernel ms rows, last result)."""
-    rows, res = [], None
+def resident_run(hp, dev_args, n_chunks, flags, depth=2):
+    """n_chunks submissions of the resident block, `depth` in flight; returns (per-kernel ms rows, last result)."""
+    rows, res, done = [], None, 0
     for k in range(n_chunks):
         hp.submit(k, dev_args[0], dev_args[1], flags)
-        if k >= 1:
+        if k - done + 1 >= depth:
             res = hp.collect(device_out=True)
             rows.append(hp.last_timings())
-            hp.release(k - 1)
-    res = hp.collect(device_out=True)
-    rows.append(hp.last_timings())
-    hp.release(n_chunks - 1)
+            hp.release(done)
+            done += 1
+    while done < n_chunks:
+        res = hp.collect(device_out=True)
+        rows.append(hp.last_timings())
+        hp.release(done)
+        done += 1
     return rows, res
 
 
@@ -275,7 +279,7 @@ def main():
     n = a.pairs
     r1, r2 = synth.make_block(lane, rank, n)          # every rank its own block of the lane (weak scaling)
     in_bytes = r1.size + r2.size
-    spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size, r2.size) + 4096, max_chunk_records=n + 64, n_slots=2, device=local)
+    spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size, r2.size) + 4096, max_chunk_records=n + 64, n_slots=max(2, a.in_flight), device=local)
     lib = load_gpu_library()
     hp = make_hotpath(lib, "mgk_", spec)
     if world > 1:   # NCCL communicator of the library itself, id shared through torch.distributed
@@ -312,7 +316,7 @@ def main():
 
     # ---- resident (kernel path) timing
     hp.reset_counters()
-    resident_run(hp, dev_args, max(a.warmup, 3) * min(cps, 4), RES)
+    resident_run(hp, dev_args, max(a.warmup, 3) * min(cps, 4), RES, a.in_flight)
     serial_kernel = serial_run(hp, dev_args, max(4, min(a.steps, 10)), RES)[1:]
     hp.span_ms()
     hp.span_ms()
@@ -323,7 +327,7 @@ def main():
         sampler.start()
     launches0 = hp.launch_count()
     t0 = time.perf_counter()
-    per_kernel, last = resident_run(hp, dev_args, a.steps * cps, RES)
+    per_kernel, last = resident_run(hp, dev_args, a.steps * cps, RES, a.in_flight)
     span = hp.span_ms()
     barrier()
     wall = time.perf_counter() - t0
