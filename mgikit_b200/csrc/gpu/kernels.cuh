@@ -903,8 +903,6 @@ __host__ __device__ inline uint32_t hdr_slot(uint32_t k, uint32_t i) {
 
 struct EmitLayout {       // byte offsets inside the dynamic shared memory, all 16-byte aligned
   uint32_t consts;        // prefix + literals (+ slack)
-  uint32_t wide;          // many samples: QC sums go straight to the global tables and the bin of a sample is read from
-                          // global memory, so that a stage still holds a tile of EMIT_NMAX records (stats / writing unused)
   uint32_t stats;         // [total][QC_SLOTS] u32
   uint32_t writing;       // [total] writing_samples (bin of a matched sample)
   uint32_t hdr;           // header staging slots, hdr_slot()
@@ -961,14 +959,12 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   {  // constants, QC accumulators, bin of every sample
     const uint32_t nconst = (uint32_t)P.prefix_len + LIT_BYTES;
     for (uint32_t i = tid; i < nconst; i += EMIT_THREADS) smem[lay.consts + i] = P.consts[i];
-    if (!lay.wide) {
-      uint32_t* st = reinterpret_cast<uint32_t*>(smem + lay.stats);
-      for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) st[i] = 0;
-      int32_t* wr = reinterpret_cast<int32_t*>(smem + lay.writing);
-      for (int i = tid; i < total; i += EMIT_THREADS) wr[i] = P.writing[i];
-    }
+    uint32_t* st = reinterpret_cast<uint32_t*>(smem + lay.stats);
+    for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) st[i] = 0;
+    int32_t* wr = reinterpret_cast<int32_t*>(smem + lay.writing);
+    for (int i = tid; i < total; i += EMIT_THREADS) wr[i] = P.writing[i];
   }
-  const int32_t* s_writing = lay.wide ? P.writing : reinterpret_cast<const int32_t*>(smem + lay.writing);
+  const int32_t* s_writing = reinterpret_cast<const int32_t*>(smem + lay.writing);
   const uint32_t n_rec = device_n_records(c, P);
   if (s_abort) return;  // nothing safe to write (one read: another CTA may be raising ERR_REC_TOO_LONG right now)
   if (n_rec == 0) return;
@@ -1051,7 +1047,6 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   uint32_t* s_stats = reinterpret_cast<uint32_t*>(smem + lay.stats);
   const uint32_t smem_s = smem_u32(smem), desc_s = smem_s + lay.desc;   // shared-window addresses
   auto flush_stats = [&]() {   // all threads; s_stats quiescent
-    if (lay.wide) return;
     for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) {
       const uint32_t v = s_stats[i];
       if (v) {
@@ -1255,10 +1250,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
               const QcSix q = qc_pair(P, smem, G, role == 2 ? 1 : 2);
 #pragma unroll
               for (int j = 0; j < QC_SLOTS; ++j)
-                if (q.v[j]) {
-                  if (lay.wide) atomicAdd(c.stats + (size_t)mt.sample * MGK_N_STATS + qc_stat_column(j, paired), (unsigned long long)q.v[j]);
-                  else atomicAdd(&s_stats[mt.sample * QC_SLOTS + j], q.v[j]);
-                }
+                if (q.v[j]) atomicAdd(&s_stats[mt.sample * QC_SLOTS + j], q.v[j]);
             }
             if (P.validate && role == val_role) {
               const int v = validate_pair(P, smem, G);

@@ -361,14 +361,10 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     uint32_t at = 0;
     L.consts = at;
     at += up((uint32_t)P.prefix_len + LIT_BYTES + 48u, 16u);
-    // with many samples the per-CTA QC accumulators and the sample->bin table would take the room a stage needs for
-    // a tile of EMIT_NMAX records (a plan tile then falls into three staged tiles instead of two): they stay in
-    // global memory instead (atomics on the running tables, the table through L1)
-    L.wide = (uint32_t)P.total * (QC_SLOTS + 1u) * 4u > 6144u ? 1u : 0u;
     L.stats = at;
-    if (!L.wide) at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
+    at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
     L.writing = at;
-    if (!L.wide) at += up((uint32_t)P.total * 4u, 16u);
+    at += up((uint32_t)P.total * 4u, 16u);
     at += 32u;                                   // slack in front of the header staging areas (gather16 reads around them)
     L.hdr = at;
     at += (P.out_mode == MGK_OUT_MGI_FULL_HEADER && P.paired ? 2u : 1u) * HDR_KIND_BYTES + 32u;   // the paired read has its own header only with --mgi-full-header
