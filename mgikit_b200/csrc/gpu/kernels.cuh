@@ -69,7 +69,7 @@ struct ChunkDev {
   uint32_t* counts;            // [2] newline totals
   RecMeta* meta;
   uint32_t* tile_bins;         // [tiles][bins_stride]: bytes, then absolute offsets (rows 16-byte aligned)
-  uint32_t bins_stride, pad0;
+  uint32_t bins_stride, emit_cap;   // emit_cap: bytes of text one shared-memory stage of k_emit holds
   uint32_t* group_sums;        // [groups][2*total]
   unsigned long long* seg;     // [4][total]: off2, len2, off1, len1
   uint8_t* out2;
@@ -88,6 +88,19 @@ __device__ __forceinline__ uint32_t device_n_records(const ChunkDev& c, const Pa
   const uint32_t a = c.counts[0] >> 2;
   const uint32_t n = P.paired ? min(a, c.counts[1] >> 2) : a;
   return min(n, c.max_records);
+}
+
+// Records per plan tile (the unit of the multisplit: one row of tile_bins, one CTA pass of k_match_plan).  256 when
+// half of it -- what k_emit stages at a time -- fits a shared-memory stage at the chunk's mean record size; with many
+// samples or long records less fits, and the plan tile shrinks to twice what does (two staged tiles per plan tile
+// instead of three uneven ones).  Every kernel derives it from the same device-resident numbers.
+__device__ __forceinline__ uint32_t device_tile_records(const ChunkDev& c, const Params& P, uint32_t n_rec) {
+  if (n_rec == 0 || c.emit_cap == 0) return (uint32_t)TILE_RECORDS;
+  const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (P.paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
+  const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
+  const uint32_t fit = (c.emit_cap - 256u) / mean;
+  if (fit >= (uint32_t)TILE_RECORDS / 2u || fit < (uint32_t)TILE_RECORDS / 4u) return (uint32_t)TILE_RECORDS;
+  return 2u * fit;
 }
 
 template <typename T>
@@ -671,14 +684,15 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
     if (min(raw2, raw1) > c.max_records) atomicOr(&c.status->error, ERR_REC_CAPACITY);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t tr = device_tile_records(c, P, n_rec);
+  const uint32_t n_tiles = (n_rec + tr - 1) / tr;
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
     for (int i = threadIdx.x; i < B2; i += blockDim.x) bin_acc[i] = 0;
     __syncthreads();
-    const uint32_t rec = tile * TILE_RECORDS + threadIdx.x;
-    const bool active = rec < n_rec;
+    const uint32_t rec = tile * tr + threadIdx.x;
+    const bool active = threadIdx.x < tr && rec < n_rec;
     int bin = 0;
     uint32_t l2 = 0, l1 = 0;
     RecMeta mt;
@@ -787,7 +801,8 @@ __global__ void k_scan_groups(const Params* __restrict__ Pg, ChunkDev c) {
   if (c.status->error & ERR_NL_CAPACITY) return;   // no plan was made (k_match_plan)
   const int B2 = 2 * Pg->total;
   const uint32_t n_rec = device_n_records(c, *Pg);
-  const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t tr = device_tile_records(c, *Pg, n_rec);
+  const uint32_t n_tiles = (n_rec + tr - 1) / tr;
   const uint32_t n_groups = (n_tiles + GROUP_TILES - 1) / GROUP_TILES;
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t g = id / B2, b = id % B2;
@@ -804,7 +819,8 @@ __global__ void __launch_bounds__(1024) k_scan_bins(const Params* __restrict__ P
   if (c.status->error & ERR_NL_CAPACITY) return;
   const int total = Pg->total, B2 = 2 * total;
   const uint32_t n_rec = device_n_records(c, *Pg);
-  const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t tr = device_tile_records(c, *Pg, n_rec);
+  const uint32_t n_tiles = (n_rec + tr - 1) / tr;
   const uint32_t n_groups = (n_tiles + GROUP_TILES - 1) / GROUP_TILES;
   unsigned long long* seg = c.seg;  // [off2 | len2 | off1 | len1] x total
   for (int b = threadIdx.x; b < B2; b += blockDim.x) {
@@ -848,7 +864,8 @@ __global__ void k_scan_tiles(const Params* __restrict__ Pg, ChunkDev c) {
   if (c.status->error & ERR_NL_CAPACITY) return;   // no plan was made (k_match_plan)
   const int total = Pg->total, B2 = 2 * total;
   const uint32_t n_rec = device_n_records(c, *Pg);
-  const uint32_t n_tiles = (n_rec + TILE_RECORDS - 1) / TILE_RECORDS;
+  const uint32_t tr = device_tile_records(c, *Pg, n_rec);
+  const uint32_t n_tiles = (n_rec + tr - 1) / tr;
   const uint32_t n_groups = (n_tiles + GROUP_TILES - 1) / GROUP_TILES;
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t g = id / B2, b = id % B2;
@@ -973,12 +990,13 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   // records per tile from the chunk's mean pair size (identical in every CTA; oversized tiles are shrunk below), and
   // the unit of ownership: EMIT_NMAX records when a whole tile of them fits a stage, else a plan tile cut into equal
   // parts (many samples or long records leave less room: three tiles of 86 are better than a tile of 117 and a sliver)
+  const uint32_t plan_tile = device_tile_records(c, P, n_rec);
   uint32_t n_tile, unit;
   {
     const unsigned long long bytes = (unsigned long long)c.nl2[4u * n_rec - 1u] + (paired ? c.nl1[4u * n_rec - 1u] : 0u) + 2ull;
     const uint32_t mean = (uint32_t)(bytes / n_rec) + 1u;
     n_tile = max(1u, min((lay.cap - 256u) / mean, (uint32_t)EMIT_NMAX));
-    unit = n_tile < (uint32_t)EMIT_NMAX ? (uint32_t)TILE_RECORDS : (uint32_t)EMIT_NMAX;
+    unit = n_tile < plan_tile / 2u ? plan_tile : plan_tile / 2u;   // half a plan tile when it fits (device_tile_records sees to that)
     const uint32_t parts = (unit + n_tile - 1u) / n_tile;
     n_tile = (unit + parts - 1u) / parts;
   }
@@ -1035,7 +1053,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
     bulk_g2s(st, c.nl2 + ((long long)4 * r0 - 4), nl_bytes, &s_bar[s]);
     if (paired) bulk_g2s(st + lay.nl1, c.nl1 + ((long long)4 * r0 - 4), nl_bytes, &s_bar[s]);
     bulk_g2s(st + lay.meta, c.meta + r0, meta_bytes, &s_bar[s]);
-    bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / TILE_RECORDS) * bins_stride, bins_bytes, &s_bar[s]);
+    bulk_g2s(st + lay.bins, c.tile_bins + (size_t)(r0 / plan_tile) * bins_stride, bins_bytes, &s_bar[s]);
     fresh = lim == pt_end;
     next_rec = fresh ? (r0 / unit + gridDim.x) * unit : lim;
     start2 = e2;

@@ -339,7 +339,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   ctx->scan_grid = (uint32_t)ctx->n_sm * 3u / (P.paired ? 2u : 1u);   // 3 CTAs per SM over both streams, one wave
   ctx->scan_cap = (uint32_t)((4 * (ctx->cap_records * 4 + 4)) / ((uint64_t)ctx->scan_grid * SCAN_WARPS) + SCAN_WTILE + 64) & ~3u;   // per range (one per warp)
   CUC(cudaFuncSetAttribute(k_scan_newlines, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_STAGES * SCAN_TILE));
-  ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS - 1) / TILE_RECORDS) + 1;
+  ctx->tiles_max = (uint32_t)((ctx->cap_records + TILE_RECORDS / 2 - 1) / (TILE_RECORDS / 2)) + 1;   // plan tiles hold 128..256 records (device_tile_records)
   ctx->groups_max = (ctx->tiles_max + GROUP_TILES - 1) / GROUP_TILES;
   ctx->match_smem = (size_t)P.n_codes * 8 + (size_t)2 * P.total * 4 + 16;
   ctx->mism_smem = (size_t)P.total * P.mism_w <= 8192 ? 1 : 0;   // per-CTA mismatch counters in shared memory
@@ -441,6 +441,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     ChunkDev& c = s.cd;
     c.nl2 = s.nl2 + 4; c.nl1 = s.nl1 ? s.nl1 + 4 : nullptr;
     c.bins_stride = ctx->bins_stride;
+    c.emit_cap = ctx->lay.cap;
     c.nl_cap = (uint32_t)(ctx->cap_records * 4 + 4);
     c.max_records = (uint32_t)ctx->cap_records;
     c.stg2 = s.stg2; c.stg1 = s.stg1;
@@ -527,7 +528,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
   // the grids below are sized from the byte length (a record is >= 8 bytes); the kernels
   // themselves read the record count the scan left on the device
   const uint64_t rec_bound = std::min<uint64_t>(ctx->cap_records, r2_len / 8 + 1);
-  const uint32_t tiles_bound = (uint32_t)((rec_bound + TILE_RECORDS - 1) / TILE_RECORDS);
+  const uint32_t tiles_bound = (uint32_t)((rec_bound + TILE_RECORDS / 2 - 1) / (TILE_RECORDS / 2));
   const uint32_t groups_bound = (tiles_bound + GROUP_TILES - 1) / GROUP_TILES;
   const uint32_t B2 = 2u * (uint32_t)P.total;
   k_match_plan<<<std::min<uint32_t>(tiles_bound, (uint32_t)ctx->grid_match), TILE_RECORDS, ctx->match_smem, st>>>(ctx->d_params, c, ctx->mism_smem);
