@@ -547,6 +547,101 @@ Inflater::Status Inflater::run_markers(SymbolBuffer& out) {
     unsigned bc = bitcnt_;
     const uint8_t* in = in_next_;
     Status st = DONE;
+    // the bulk of a block: no input bounds to watch (16 bytes ahead cover both refills of a symbol group), literal runs
+    // stored as one 64-bit word, matches copied four symbols at a time
+    for (;;) {
+      if (out.cap - n < 640) {
+        out.size = n;
+        out.reserve(out.cap + (out.cap >> 1) + ((size_t)4 << 20));
+      }
+      if (in_end_ - in < 16) break;
+      uint16_t* o = out.data;
+      bb |= load64(in) << bc;
+      in += (63 - bc) >> 3;
+      bc |= 56;
+      uint32_t e = lit_[bb & ((1u << LIT_BITS) - 1)];
+      unsigned runs = 0;
+      while ((e & E_LIT) && runs < 3) {   // up to three lookups of literal runs per refill, then a length still fits
+        bb >>= e & 15u;
+        bc -= e & 15u;
+        const uint64_t v = (uint64_t)((e >> 8) & 0xffu) | ((uint64_t)((e >> 16) & 0xffu) << 16) | ((uint64_t)(e >> 24) << 32);
+        memcpy(o + n, &v, 8);
+        n += (e >> 4) & 3u;
+        e = lit_[bb & ((1u << LIT_BITS) - 1)];
+        ++runs;
+      }
+      if (e & E_LIT) continue;   // (fourth run: after the next refill)
+      if (e & E_SPECIAL) {
+        if (e & E_SUB) e = lit_[(e >> 16) + ((bb >> LIT_BITS) & ((1u << ((e >> 8) & 15u)) - 1))];
+        if (e & E_LIT) {
+          bb >>= e & 15u;
+          bc -= e & 15u;
+          o[n++] = (uint16_t)((e >> 8) & 0xffu);
+          continue;
+        }
+        if (e & E_BAD) {
+          st = BAD_DATA;
+          err_ = "invalid literal/length code";
+          break;
+        }
+        if (e & E_EOB) {
+          bb >>= e & 15u;
+          bc -= e & 15u;
+          state_ = final_ ? ST_DONE : ST_HEADER;
+          break;
+        }
+      }
+      bb >>= e & 15u;
+      bc -= e & 15u;
+      unsigned xb = (e >> 8) & 15u;
+      const unsigned len = (e >> 16) + (unsigned)(bb & ((1u << xb) - 1));
+      bb >>= xb;
+      bc -= xb;
+      if (bc < 32) {
+        bb |= load64(in) << bc;
+        in += (63 - bc) >> 3;
+        bc |= 56;
+      }
+      uint32_t d = dist_[bb & ((1u << DIST_BITS) - 1)];
+      if (d & E_SPECIAL) {
+        if (d & E_SUB) d = dist_[(d >> 16) + ((bb >> DIST_BITS) & ((1u << ((d >> 8) & 15u)) - 1))];
+        if (d & E_BAD) {
+          st = BAD_DATA;
+          err_ = "invalid distance code";
+          break;
+        }
+      }
+      xb = (d >> 8) & 15u;
+      bb >>= d & 15u;
+      bc -= d & 15u;
+      const size_t dist = (d >> 16) + (size_t)(bb & ((1u << xb) - 1));
+      bb >>= xb;
+      bc -= xb;
+      if (dist <= n) {
+        const uint16_t* src = o + (n - dist);
+        uint16_t* dst = o + n;
+        if (dist >= 4) {
+          for (unsigned i = 0; i < len; i += 4) memcpy(dst + i, src + i, 8);
+        } else {
+          for (unsigned i = 0; i < len; ++i) dst[i] = src[i];
+        }
+      } else {   // (part of) the match lies in the unknown window
+        const size_t before = dist - n;
+        for (unsigned i = 0; i < len; ++i) {
+          const size_t back = before > i ? before - i : 0;
+          o[n + i] = back ? (uint16_t)(MARKER | (INFLATE_WINDOW - back)) : o[i - before];
+        }
+      }
+      n += len;
+    }
+    if (st != DONE || state_ != ST_CODES) {
+      bitbuf_ = bb;
+      bitcnt_ = bc;
+      in_next_ = in;
+      if (st != DONE) return leave(st);
+      continue;
+    }
+    // the last bytes of the input: every step checked
     for (;;) {
       if (out.cap - n < 320) {
         out.size = n;
