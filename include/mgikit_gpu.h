@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGK_ABI_VERSION 1
+#define MGK_ABI_VERSION 2
 #define MGK_MAX_TEMPLATES 16
 #define MGK_MAX_INDEX_LEN 32      /* bases per i7 / i5 (2-bit packed into 64 bit) */
 #define MGK_MAX_BARCODE_LEN 255
@@ -94,6 +94,16 @@ typedef struct {
   uint64_t max_chunk_bytes;        /* capacity per read file per chunk (< 2^31) */
   uint64_t max_chunk_records;      /* capacity in records per chunk */
   int32_t n_slots;                 /* chunks that may be in flight (>=1; 2 = double buffering) */
+  /* `mgikit reformat` (src/lib.rs:2266-2464): the same call with demultiplex == false (src/lib.rs:1090-1147,
+   * :1240-1293).  Every read belongs to sample 0 (n_samples = 1, n_templates = 0, allowed_mismatches = 5 as
+   * at :2431); the barcode is the one already in the header (" n:N:0:BARCODE", or none: MGI raw "/n").     */
+  int32_t reformat;                /* 0: demultiplex */
+  int32_t reformat_umi_length;     /* bases at the end of the barcode read's sequence that move into the header
+                                      (:1117-1124); it is the barcode_length of the trim and of the r3 QC
+                                      sums (:878-882) */
+  const char* reformat_barcode;    /* --barcode ("" / NULL: none): mismatches are counted against the header's
+                                      barcode (:1103-1113, more than 4 count as 4); headers without one get
+                                      " n:N:0:" + this (:1256-1264) */
 } mgk_config;
 
 /* mgk_submit flags */

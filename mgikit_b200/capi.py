@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-MGK_ABI_VERSION = 1
+MGK_ABI_VERSION = 2
 MGK_IN_DEVICE = 1
 MGK_OUT_DEVICE = 2
 MGK_OUT_GZIP = 4
@@ -41,7 +41,9 @@ class MgkConfig(C.Structure):
                 ("l_position", C.c_int32), ("illumina_prefix", C.c_char_p), ("n_samples", C.c_int32),
                 ("writing_sample", C.POINTER(C.c_int32)), ("n_templates", C.c_int32),
                 ("templates", C.POINTER(MgkTemplate)), ("max_chunk_bytes", C.c_uint64),
-                ("max_chunk_records", C.c_uint64), ("n_slots", C.c_int32)]
+                ("max_chunk_records", C.c_uint64), ("n_slots", C.c_int32),
+                # `mgikit reformat`: one sample, the barcode is the one in the header
+                ("reformat", C.c_int32), ("reformat_umi_length", C.c_int32), ("reformat_barcode", C.c_char_p)]
 
 
 class MgkResult(C.Structure):

@@ -65,6 +65,9 @@ struct TemplateDev {
 struct Params {
   int32_t paired, read2_has_sequence, out_mode, keep_barcode, comprehensive, validate, report_level, mgi_data;
   int32_t m, M, L, S, total, BL, mism_w, n_tpl, prefix_len, n_codes;
+  // `reformat` (src/lib.rs:1090-1147): one sample, no matching; BL is the UMI length; the sample's barcode (rf_bc_len
+  // bytes, 0: none) follows the literals in `consts`
+  int32_t reformat, rf_bc_len;
   TemplateDev tpl[MGK_MAX_TEMPLATES];
   // xl7_off[d*16+t] >= 0: table translating index ids of template d into template t
   // (only consulted when the reference's dictionary iterator lags, src/lib.rs:375-376)
@@ -94,6 +97,7 @@ constexpr int LIT_TAIL = 2;    // ":N:0:"
 constexpr int LIT_PLUS = 7;    // "+"
 constexpr int LIT_NL = 8;      // "\n"
 constexpr int LIT_BYTES = 16;
+constexpr int RF_MAX_TAIL = 255;   // reformat: bytes of the input header from its first ' ' on that one record may carry over
 
 // ---------------------------------------------------------------- 2-bit packing
 // A,C,G,T -> 0,1,3,2 ((b>>1)&3).  N packs as 0 and sets its position in nmask
@@ -347,7 +351,36 @@ struct RecPlan {
   // illumina header pieces (src/sample_data.rs:584-626)
   uint32_t z;           // first non-'0' of the read-number field, == sep if none
   uint32_t f1, f2;      // offsets of the first kept digit of the two 3-digit fields
+  // reformat only: bytes of the input header that follow its fields (from the first ' ' on; none for MGI raw headers),
+  // whether the header is raw ("/n", no ' '), mismatches of the header's barcode against the sample's
+  uint32_t rf_tcl, rf_raw, rf_mism;
 };
+
+// reformat: what the emit side needs to know about a record's header, packed into RecMeta (tpl byte + a flag bit)
+MGK_HD uint32_t rf_pack(uint32_t tcl, uint32_t raw) { return tcl | (raw << 8); }
+struct RfHeader {
+  uint32_t sep;           // offset of the separator inside the header (src/lib.rs:1091-1102)
+  uint32_t tcl;           // header bytes carried over from sep on
+  uint32_t at_end;        // sep == header length - 3 (:1104, :1132, :1256)
+  uint32_t header_shift;  // :1129, :1135
+  uint32_t tail_offset;   // :1130, :1136
+  uint32_t append;        // " n:N:0:" + the sample's barcode is appended (:1256-1264)
+};
+MGK_HD RfHeader rf_header(const Params& P, uint32_t hl, uint32_t rf) {   // hl: header incl. '\n'
+  RfHeader h;
+  const uint32_t raw = rf >> 8;
+  h.tcl = rf & 0xffu;
+  h.sep = hl - (raw ? 2u : 0u) - 1u - h.tcl;
+  h.at_end = h.sep == hl - 3u;
+  h.header_shift = hl - h.sep - 3u;
+  h.tail_offset = h.header_shift + 1u;
+  h.append = (h.at_end && P.rf_bc_len > 0) ? 1u : 0u;
+  if (h.append) {
+    h.header_shift = 0;
+    h.tail_offset = (uint32_t)P.rf_bc_len + 6u;
+  }
+  return h;
+}
 
 MGK_HD uint32_t barcode_text_len(const Params& P, int bar_t) {
   if (bar_t < 0) return 0;
@@ -359,6 +392,7 @@ MGK_HD uint32_t umi_text_len(const Params& P, int umi_t) { return umi_t < 0 ? 0u
 MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G, int sample, int bar_t, int umi_t) {
   RecPlan pl;
   pl.z = pl.f1 = pl.f2 = 0;
+  pl.rf_tcl = pl.rf_raw = pl.rf_mism = 0;
   const uint32_t BL = (uint32_t)P.BL, L = (uint32_t)P.L;
   const uint32_t hl = G.s2 - G.h2;  // header incl. '\n'
   pl.fmt_error = (G.p2 - G.s2 < BL + 1u) || (G.e2 - G.q2 < BL) || hl < 3u ||
@@ -367,6 +401,60 @@ MGK_HD RecPlan record_plan(const Params& P, const uint8_t* r2, const RecGeom& G,
   const uint32_t rec2 = G.e2 + 1u - G.h2, rec1 = P.paired ? G.e1 + 1u - G.h1 : 0u;
   if (pl.fmt_error) {
     pl.len2 = pl.len1 = 0;
+    return pl;
+  }
+  if (P.reformat) {   // src/lib.rs:1090-1147, :1240-1293 with demultiplex == false
+    const uint8_t* H = r2 + G.h2;
+    uint32_t sep = hl;
+    for (uint32_t i = 0; i < hl; ++i)   // memchr(b' ', header), :1091
+      if (ldg_u8(H + i) == ' ') {
+        sep = i;
+        break;
+      }
+    pl.rf_raw = sep == hl ? 1u : 0u;   // "You might be using MGI raw data": raw_shift = 2
+    if (pl.rf_raw) sep = hl - 3u;
+    const uint32_t bcl = (uint32_t)P.rf_bc_len;
+    const bool at_end = sep == hl - 3u;
+    // a ' ' in the last two header bytes wraps header_shift (:1129); a header barcode of another length panics in
+    // hamming_distance(..).unwrap() (:1108-1112)
+    if (sep > hl - 3u || (bcl && !at_end && (sep + 7u > hl - 1u || hl - 1u - (sep + 7u) != bcl))) {
+      pl.fmt_error = 1;
+      pl.len2 = pl.len1 = 0;
+      return pl;
+    }
+    pl.rf_tcl = hl - (pl.rf_raw ? 2u : 0u) - 1u - sep;
+    if (bcl && !at_end) {
+      const uint8_t* bc = P.consts + P.prefix_len + LIT_BYTES;
+      uint32_t d = 0;
+      for (uint32_t k = 0; k < bcl; ++k) d += ldg_u8(H + sep + 7u + k) != ldg_u8(bc + k) ? 1u : 0u;
+      pl.rf_mism = d > 4u ? 4u : d;   // :1140-1141
+    }
+    const RfHeader rh = rf_header(P, hl, rf_pack(pl.rf_tcl, pl.rf_raw));
+    // the header tail must fit its byte of RecMeta; the paired read's own digit is looked up header_shift + 2 bytes
+    // in front of its sequence (:1275): a shorter header would reach into the record before it
+    if (pl.rf_tcl > (uint32_t)RF_MAX_TAIL || (P.paired && P.out_mode == MGK_OUT_ILLUMINA && G.s1 - G.h1 < rh.header_shift + 2u)) {
+      pl.fmt_error = 1;
+      pl.len2 = pl.len1 = 0;
+      return pl;
+    }
+    if (P.out_mode != MGK_OUT_ILLUMINA) {   // :1224: nothing is written unless demultiplex || illumina_format
+      pl.len2 = pl.len1 = 0;
+      return pl;
+    }
+    uint32_t z = sep;
+    for (uint32_t i = L + 10u; i < sep; ++i)
+      if (ldg_u8(H + i) != '0') {
+        z = i;
+        break;
+      }
+    pl.z = z;
+    pl.f1 = ldg_u8(H + L + 3) != '0' ? L + 3u : (ldg_u8(H + L + 4) != '0' ? L + 4u : L + 5u);
+    pl.f2 = ldg_u8(H + L + 7) != '0' ? L + 7u : (ldg_u8(H + L + 8) != '0' ? L + 8u : L + 9u);
+    const uint32_t hdr = (uint32_t)P.prefix_len + 2u + (sep - z) + 1u + (L + 6u - pl.f1) + 1u + (L + 10u - pl.f2) +
+                         (BL ? 1u + BL : 0u) + pl.rf_tcl + (rh.append ? 7u + bcl : 0u);
+    const uint32_t body2 = (G.p2 - BL - 1u - (G.s2 - 1u)) + (G.e2 - BL - (G.p2 - 1u)) + 1u;
+    pl.len2 = hdr + body2;
+    pl.len1 = P.paired ? hdr + (G.e1 + 1u - (G.s1 - 1u)) : 0u;
     return pl;
   }
   if (!pl.matched) {  // src/lib.rs:1225-1235: verbatim

@@ -102,10 +102,10 @@ MGK_HD uint32_t bytes_ne(uint32_t x, uint32_t pat) {   // 0x80 in every byte of 
   const uint32_t v = x ^ pat;
   return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
 }
-MGK_HD HdrInfo hdr_info(const Params& P, const uint8_t* S, const RecGeom& G) {
+MGK_HD HdrInfo hdr_info(const Params& P, const uint8_t* S, const RecGeom& G, uint32_t sep) {   // sep: S offset of the separator
   HdrInfo h;
   const uint32_t L = (uint32_t)P.L, H = G.h2;
-  h.sep = G.s2 - 3u;
+  h.sep = sep;
   // bytes H+L+3 .. H+L+18: ccc R rrr and the first nine digits of the read number, in one go
   const uint4 v = ld16u(S, H + L + 3u);
   const uint32_t Z = 0x30303030u, C = 0x00204081u;   // 0x80 flags of a word -> 4 bits at the top of the product
@@ -211,7 +211,8 @@ struct ReadPlan {
   uint32_t patch_at;     // illumina paired read: index of the read-number digit inside the header (else ~0)
   uint32_t patch_src;    // ... and where its own digit is in S
 };
-MGK_HD ReadPlan plan_read(const Params& P, const RecGeom& G, int which, int sample, int bar_t, uint32_t out_len) {
+// `rf`: reformat only, rf_pack() of the record (RecMeta::tpl and flag bit 1).
+MGK_HD ReadPlan plan_read(const Params& P, const RecGeom& G, int which, int sample, int bar_t, uint32_t out_len, uint32_t rf = 0) {
   ReadPlan r;
   const bool br = which == 2;
   const uint32_t h = br ? G.h2 : G.h1, s = br ? G.s2 : G.s1, p = br ? G.p2 : G.p1, e = br ? G.e2 : G.e1;
@@ -233,9 +234,15 @@ MGK_HD ReadPlan plan_read(const Params& P, const RecGeom& G, int which, int samp
       r.hdr = br ? HDR_SLOT0 : HDR_SLOT1;
     } else {
       r.hdr = HDR_SLOT0;
-      if (!br) {   // fix_paired_read_header: n is tail_offset = len(barcode) + 6 from the end, src/lib.rs:1019
+      if (!br && !P.reformat) {   // fix_paired_read_header: n is tail_offset = len(barcode) + 6 from the end, src/lib.rs:1019
         r.patch_at = r.hl - 6u - barcode_text_len(P, bar_t);
         r.patch_src = G.s1 - 2u;
+      } else if (!br) {           // reformat: only when the header ends with a read number at all, src/lib.rs:1269-1277
+        const RfHeader rh = rf_header(P, G.s2 - G.h2, rf);
+        if (P.rf_bc_len > 0 || !rh.at_end) {
+          r.patch_at = r.hl - rh.tail_offset;
+          r.patch_src = G.s1 - 2u - rh.header_shift;
+        }
       }
     }
   }
@@ -246,17 +253,42 @@ MGK_HD ReadPlan plan_read(const Params& P, const RecGeom& G, int which, int samp
 // part 0 = everything in front of the tail, part 1 = the tail ([umi] n ":N:0:" barcode).
 // which = 2: the barcode read's (illumina: also the paired read's, up to one digit); which = 1:
 // the paired read's own full header (--mgi-full-header only).  `hl` = the header's length.
+// reformat (`rf` = rf_pack() of the record): the tail is [":" umi] + what the input header holds from its separator on
+// [+ " " n ":N:0:" + the sample's barcode when it holds nothing] (src/sample_data.rs:627-637, src/lib.rs:1256-1264).
 MGK_HD void build_header(const Params& P, const uint8_t* S, uint32_t cs0, const RecGeom& G, int which, int bar_t, int umi_t,
-                         uint32_t hl, uint8_t* o, int part) {
-  const TailSpec t = make_tail(P, G, bar_t, umi_t);
-  const uint32_t tl = tail_len(t);
+                         uint32_t hl, uint8_t* o, int part, uint32_t rf = 0) {
   const bool full = P.out_mode == MGK_OUT_MGI_FULL_HEADER;
   const uint32_t h = which == 2 ? G.h2 : G.h1, s = which == 2 ? G.s2 : G.s1;
+  RfHeader rh;
+  rh.sep = G.s2 - G.h2 - 3u;   // demultiplex: the '/' (src/lib.rs:1007)
+  if (P.reformat) rh = rf_header(P, G.s2 - G.h2, rf);
+  if (P.reformat && part == 1) {
+    const uint32_t U = (uint32_t)P.BL, bcl = (uint32_t)P.rf_bc_len;
+    o += hl - ((U ? 1u + U : 0u) + rh.tcl + (rh.append ? 7u + bcl : 0u));
+    if (U) {
+      *o++ = ':';
+      o = put_span(o, S, G.p2 - 1u - U, U);   // src/lib.rs:1117-1124
+    }
+    o = put_span(o, S, G.h2 + rh.sep, rh.tcl);
+    if (rh.append) {
+      *o++ = ' ';
+      *o++ = (uint8_t)s_u8(S, G.s2 - 2u);
+      *o++ = ':';
+      *o++ = 'N';
+      *o++ = ':';
+      *o++ = '0';
+      *o++ = ':';
+      put_span(o, S, cs0 + (uint32_t)P.prefix_len + (uint32_t)LIT_BYTES, bcl);
+    }
+    return;
+  }
+  const TailSpec t = make_tail(P, G, bar_t, umi_t);
+  const uint32_t tl = tail_len(t);
   if (part == 0) {
     if (full) {
       put_span(o, S, h, s - h - 1u);   // its own header line without the '\n'
     } else {                             // prefix lane ":" readno ":" ccc ":" rrr
-      const HdrInfo hi = hdr_info(P, S, G);
+      const HdrInfo hi = hdr_info(P, S, G, G.h2 + rh.sep);
       const uint32_t L = (uint32_t)P.L, H = G.h2, Pn = (uint32_t)P.prefix_len;
       if (((uintptr_t)o & 3u) == 0) {   // a staging slot: whole words (the constants are aligned too); the up to three
                                         // bytes past the prefix are overwritten by this thread right below

@@ -44,7 +44,8 @@ struct __align__(16) RecMeta {
   uint16_t sample;       // 0..S+1; the bin is writing[sample] for a matched read, the sample itself otherwise
   uint16_t len2, len1;   // output bytes of the two records
   uint8_t tpl;           // template that cut the barcode text (low nibble) and the UMI (high nibble); 15 = none
-  uint8_t flags;         // bit0: format error
+                         // (reformat: bytes of the input header carried over, rf_pack())
+  uint8_t flags;         // bit0: format error; bit1 (reformat): MGI raw header
 };
 static_assert(sizeof(RecMeta) == 16, "RecMeta is one 16-byte row");
 
@@ -713,10 +714,19 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
         bar = c.r2 + bar_off;
       }
     }
-    const MatchOut mo = cta_match(P, s_codes, bar, ms);   // CTA-wide: every thread calls it
+    MatchOut mo;
+    if (P.reformat) {   // one sample, nothing to match (src/lib.rs:1114); the mismatches come with the record's plan
+      mo.sample = 0;
+      mo.mism = 0;
+      mo.bar_t = mo.umi_t = -1;
+      mo.panicked = 0;
+    } else {
+      mo = cta_match(P, s_codes, bar, ms);   // CTA-wide: every thread calls it
+    }
     if (active) {
       if (mo.panicked) atomicOr(&c.status->error, ERR_PANIC);
       const RecPlan pl = record_plan(P, c.r2, G, mo.sample, mo.bar_t, mo.umi_t);
+      if (P.reformat) mo.mism = (int)pl.rf_mism;
       if (pl.fmt_error) {
         atomicMin(&c.status->fmt_record, (unsigned long long)rec);
         mt.flags = 1;
@@ -728,6 +738,10 @@ __global__ void __launch_bounds__(TILE_RECORDS, 5) k_match_plan(const Params* __
       mt.len2 = (uint16_t)l2;
       mt.len1 = (uint16_t)l1;
       mt.tpl = (uint8_t)((mo.bar_t & 15) | ((mo.umi_t & 15) << 4));
+      if (P.reformat) {
+        mt.tpl = (uint8_t)pl.rf_tcl;
+        mt.flags |= (uint8_t)(pl.rf_raw << 1);
+      }
       if (l2 > 0xffffu || l1 > 0xffffu) atomicOr(&c.status->error, ERR_REC_TOO_LONG);
       if (!pl.fmt_error) {
         // update_mismatches(sample_id, curr_mismatch + 1, 1), src/lib.rs:1212
@@ -974,7 +988,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
   __syncthreads();
   const int total = P.total, paired = P.paired;
   {  // constants, QC accumulators, bin of every sample
-    const uint32_t nconst = (uint32_t)P.prefix_len + LIT_BYTES;
+    const uint32_t nconst = (uint32_t)P.prefix_len + LIT_BYTES + (uint32_t)P.rf_bc_len;
     for (uint32_t i = tid; i < nconst; i += EMIT_THREADS) smem[lay.consts + i] = P.consts[i];
     uint32_t* st = reinterpret_cast<uint32_t*>(smem + lay.stats);
     for (int i = tid; i < total * QC_SLOTS; i += EMIT_THREADS) st[i] = 0;
@@ -1157,11 +1171,12 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       return;
     }
     const RecGeom G = geom_one(T, i, which);
-    const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15);
+    const int bar_t = (P.reformat || (mt.tpl & 15) == 15) ? -1 : (mt.tpl & 15);
+    const uint32_t rf = rf_pack(mt.tpl, (mt.flags >> 1) & 1u);   // read in reformat mode only
     const int bin = mt.sample < P.S ? s_writing[mt.sample] : (int)mt.sample;
     const uint32_t buf = which == 2 ? 0u : 1u << 31;
     const uint32_t dst = which == 2 ? T.bins[bin] + mt.off2 : T.bins[total + bin] + mt.off1;
-    const ReadPlan r = plan_read(P, G, which, mt.sample, bar_t, which == 2 ? mt.len2 : mt.len1);
+    const ReadPlan r = plan_read(P, G, which, mt.sample, bar_t, which == 2 ? mt.len2 : mt.len1, rf);
     const Piece a = read_piece(r, 0), b = read_piece(r, 1);   // b follows a in the output
     put(kb, dst + a.dst_off, a.src | buf, b.src | ((r.trim && r.len) ? 1u << 31 : 0u), a.n | (b.n << 16));
     const bool staged = r.len && r.hdr != HDR_VERBATIM && r.hl <= HDR_SLOT_BYTES;
@@ -1230,14 +1245,15 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
       const uint32_t i = (uint32_t)tid % EMIT_NMAX;
       if (i < T.n) {
         const RecMeta mt = T.metas[i];
-        const int bar_t = (mt.tpl & 15) == 15 ? -1 : (mt.tpl & 15), umi_t = (mt.tpl >> 4) == 15 ? -1 : (mt.tpl >> 4);
+        const int bar_t = (P.reformat || (mt.tpl & 15) == 15) ? -1 : (mt.tpl & 15), umi_t = (P.reformat || (mt.tpl >> 4) == 15) ? -1 : (mt.tpl >> 4);
+        const uint32_t rf = rf_pack(mt.tpl, (mt.flags >> 1) & 1u);
         if (role < 2) {
           if (!(mt.flags & 1) && mt.sample < P.S && P.out_mode != MGK_OUT_MGI) {   // rewritten headers
             const RecGeom G = geom(T, i);
-            const ReadPlan p2 = plan_read(P, G, 2, mt.sample, bar_t, mt.len2);
+            const ReadPlan p2 = plan_read(P, G, 2, mt.sample, bar_t, mt.len2, rf);
             ReadPlan p1 = p2;
             p1.len = 0;
-            if (paired) p1 = plan_read(P, G, 1, mt.sample, bar_t, mt.len1);
+            if (paired) p1 = plan_read(P, G, 1, mt.sample, bar_t, mt.len1, rf);
 #pragma unroll 1
             for (int which = 2; which >= 1; --which) {
               const ReadPlan& r = which == 2 ? p2 : p1;
@@ -1246,14 +1262,14 @@ __global__ void __launch_bounds__(EMIT_THREADS, 1) k_emit(const Params* __restri
               if (!own && !lent) continue;
               const uint32_t hl = own ? r.hl : p1.hl;   // illumina: both reads carry the same header
               if (hl <= HDR_SLOT_BYTES) {
-                build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, smem + lay.hdr + hdr_slot((uint32_t)slot - 1u, i), role);
+                build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, smem + lay.hdr + hdr_slot((uint32_t)slot - 1u, i), role, rf);
               } else {   // too long for a slot: byte by byte at its destination(s)
 #pragma unroll 1
                 for (int to = 2; to >= 1; --to) {
                   const ReadPlan& t = to == 2 ? p2 : p1;
                   if (t.hdr != slot || t.len == 0) continue;
                   uint8_t* g = dest(T, mt, to);
-                  build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, g, role);
+                  build_header(P, smem, lay.consts, G, which, bar_t, umi_t, hl, g, role, rf);
                   if (role == 1 && t.patch_at != 0xffffffffu) g[t.patch_at] = smem[t.patch_src];
                 }
               }

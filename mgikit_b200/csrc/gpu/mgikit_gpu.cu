@@ -229,7 +229,8 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   if (!cfg || !out) return fail(ctx, MGK_ERR_ARG, "mgk_create: null argument");
   *out = nullptr;
   if (cfg->abi_version != MGK_ABI_VERSION) return fail(ctx, MGK_ERR_ARG, "mgk_create: ABI version %d, library speaks %d", cfg->abi_version, MGK_ABI_VERSION);
-  if (cfg->n_templates < 1 || cfg->n_templates > MGK_MAX_TEMPLATES || cfg->n_samples < 1 || !cfg->templates || !cfg->writing_sample)
+  if (cfg->n_templates < (cfg->reformat ? 0 : 1) || cfg->n_templates > MGK_MAX_TEMPLATES || cfg->n_samples < 1 ||
+      (!cfg->templates && cfg->n_templates > 0) || !cfg->writing_sample)
     return fail(ctx, MGK_ERR_ARG, "mgk_create: bad sample/template tables");
   if (cfg->n_samples + 2 > 60000) return fail(ctx, MGK_ERR_ARG, "mgk_create: more than 60000 samples are not supported");
   if (cfg->max_chunk_bytes == 0 || cfg->max_chunk_bytes >= (1ull << 31) || cfg->max_chunk_records == 0)
@@ -330,7 +331,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
   // capacities
   ctx->cap_bytes = cfg->max_chunk_bytes;
   ctx->cap_records = cfg->max_chunk_records;
-  const uint64_t growth = (uint64_t)P.prefix_len + 2ull * P.BL + 32ull;
+  const uint64_t growth = (uint64_t)P.prefix_len + 2ull * P.BL + 32ull + (uint64_t)P.rf_bc_len;
   ctx->out_cap = ctx->cap_bytes + ctx->cap_records * growth;
   if (ctx->out_cap >= (1ull << 32) - 4096) BAD("mgk_create: chunk capacity too large for 32-bit output offsets; lower max_chunk_bytes");
   // newline scan: one CTA per SM and stream, each with its own run of the staging array.  A run holds four times
@@ -360,7 +361,7 @@ extern "C" int mgk_create(const mgk_config* cfg, mgk_ctx** out) {
     EmitLayout& L = ctx->lay;
     uint32_t at = 0;
     L.consts = at;
-    at += up((uint32_t)P.prefix_len + LIT_BYTES + 48u, 16u);
+    at += up((uint32_t)P.prefix_len + LIT_BYTES + (uint32_t)P.rf_bc_len + 48u, 16u);
     L.stats = at;
     at += up((uint32_t)P.total * QC_SLOTS * 4u, 16u);
     L.writing = at;
@@ -557,7 +558,7 @@ extern "C" int mgk_submit(mgk_ctx* ctx, uint64_t seq, const uint8_t* r2, uint64_
       g.blk_off = s.gz_off; g.gzseg = s.gz_seg; g.total = (uint32_t)P.total; g.blocks_cap = (uint32_t)blocks_cap;
       g.cap2 = ctx->out_cap; g.cap1 = ctx->out_cap; g.error = &s.status->error; g.err_capacity = ERR_OUT_CAPACITY;
     }
-    const uint64_t out_bound = std::min<uint64_t>(ctx->out_cap, r2_len + r1_len + rec_bound * ((uint64_t)P.prefix_len + 2ull * P.BL + 32ull));
+    const uint64_t out_bound = std::min<uint64_t>(ctx->out_cap, r2_len + r1_len + rec_bound * ((uint64_t)P.prefix_len + 2ull * P.BL + 32ull + (uint64_t)P.rf_bc_len));
     const uint32_t blocks_bound = (uint32_t)std::min<uint64_t>(s.gz.blocks_cap, out_bound / GZ_BLOCK + 2ull * P.total + 2ull);
     k_gz_plan<<<1, 1024, 0, st>>>(s.gz);
     k_gz_blocks<<<std::min<uint32_t>(blocks_bound, (uint32_t)ctx->n_sm * 2u), GZ_THREADS, sizeof(GzShared), st>>>(s.gz, ctx->gzk);

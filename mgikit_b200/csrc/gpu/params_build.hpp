@@ -56,14 +56,27 @@ inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, 
   P.L = cfg->l_position;
   P.S = cfg->n_samples;
   P.total = cfg->n_samples + 2;
-  P.BL = cfg->templates[0].geometry[9];
+  P.reformat = cfg->reformat ? 1 : 0;
+  const std::string rf_barcode = (cfg->reformat && cfg->reformat_barcode) ? cfg->reformat_barcode : "";
+  P.rf_bc_len = (int)rf_barcode.size();
+  if (P.reformat) {   // src/lib.rs:2302-2322, :2422-2441
+    if (cfg->n_samples != 1 || cfg->n_templates != 0) { why = "reformat: one sample, no barcode templates"; return false; }
+    if (!cfg->read2_has_sequence || cfg->out_mode == MGK_OUT_MGI_FULL_HEADER || cfg->keep_barcode) { why = "reformat: flags the command does not have"; return false; }
+    if (cfg->reformat_umi_length < 0 || cfg->reformat_umi_length > MGK_MAX_BARCODE_LEN) { why = "umi length outside [0,255]"; return false; }
+    if (P.rf_bc_len > MGK_MAX_BARCODE_LEN) { why = "barcode longer than 255 bases"; return false; }
+    if (cfg->allowed_mismatches < 4) { why = "reformat counts up to 4 mismatches: allowed_mismatches must be >= 4 (the reference passes 5)"; return false; }
+  } else if (cfg->n_templates < 1 || !cfg->templates) {
+    why = "no barcode template";
+    return false;
+  }
+  P.BL = P.reformat ? cfg->reformat_umi_length : cfg->templates[0].geometry[9];
   P.mism_w = 2 * cfg->allowed_mismatches + 2;
   P.n_tpl = cfg->n_templates;
   const std::string prefix = cfg->illumina_prefix ? cfg->illumina_prefix : "";
   P.prefix_len = (int)prefix.size();
   if (P.out_mode < 0 || P.out_mode > 2) { why = "unknown out_mode"; return false; }
   if (P.out_mode == MGK_OUT_ILLUMINA && prefix.empty()) { why = "illumina output needs the header prefix"; return false; }
-  if (P.BL < 1 || P.BL > MGK_MAX_BARCODE_LEN) { why = "barcode length outside [1,255]"; return false; }
+  if (P.BL < (P.reformat ? 0 : 1) || P.BL > MGK_MAX_BARCODE_LEN) { why = "barcode length outside [1,255]"; return false; }
   if (P.L < 0) { why = "negative l_position"; return false; }
   for (int t = 0; t < P.n_tpl; ++t) {
     const mgk_template& s = cfg->templates[t];
@@ -133,6 +146,7 @@ inline bool build_params_host(const mgk_config* cfg, Params& P, HostTables& tb, 
   lit[LIT_PLUS] = '+';
   lit[LIT_NL] = '\n';
   tb.consts.append(lit, LIT_BYTES);
+  tb.consts += rf_barcode;
   tb.writing.assign(cfg->writing_sample, cfg->writing_sample + P.total);
   for (int i = 0; i < P.total; ++i)
     if (tb.writing[(size_t)i] < 0 || tb.writing[(size_t)i] >= P.total) { why = "writing_sample out of range"; return false; }

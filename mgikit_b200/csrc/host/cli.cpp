@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <vector>
 
 #include "log.hpp"
 #include "template_cmd.hpp"
@@ -87,6 +88,58 @@ const Opt TEMPLATE_OPTS[] = {
     {"log-level", 'l', true, "info", nullptr},
 };
 
+// `reformat` subcommand, src/main.rs:541-712 (+ the same extensions as demultiplex)
+const Opt REFORMAT_OPTS[] = {
+    {"read2", 'r', true, "", "2"},
+    {"read1", 'f', true, "", "1"},
+    {"output", 'o', true, "", nullptr},
+    {"reports", 0, true, "", nullptr},
+    {"disable-illumina", 0, false, "false", nullptr},
+    {"writing-buffer-size", 0, true, "67108864", nullptr},
+    {"lane", 0, true, "", nullptr},
+    {"instrument", 0, true, "", nullptr},
+    {"run", 0, true, "", nullptr},
+    {"force", 0, false, "false", nullptr},
+    {"info-file", 0, true, "", nullptr},
+    {"report-level", 0, true, "2", nullptr},
+    {"compression-level", 0, true, "1", nullptr},
+    {"compression-buffer-size", 0, true, "131072", nullptr},
+    {"memory", 0, true, "0", nullptr},
+    {"validate", 0, false, "false", nullptr},
+    {"umi-length", 0, true, "0", nullptr},
+    {"sample-index", 0, true, "1", nullptr},
+    {"barcode", 0, true, "", nullptr},
+    {"sample-label", 0, true, "", nullptr},
+    {"log-level", 'l', true, "info", nullptr},
+    {"threads", 't', true, "0", nullptr},
+    {"reader-threads", 0, true, "0", nullptr},
+    {"gpus", 0, true, "1", nullptr},
+    {"chunk-size", 0, true, "67108864", nullptr},
+    {"slots", 0, true, "4", nullptr},
+    {"host-gzip", 0, false, "false", nullptr},
+};
+
+// parse_sb_file_name(), src/formater.rs:44-61: Flowcell_Lane_SampleLabel_1/2 -> (label, flowcell, lane, rest)
+void parse_sb_file_name(const std::string& stem, std::string& label, std::string& lane) {
+  std::vector<std::string> parts;
+  size_t a = 0;
+  for (;;) {
+    const size_t b = stem.find('_', a);
+    parts.push_back(stem.substr(a, b == std::string::npos ? std::string::npos : b - a));
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  label.clear();
+  lane.clear();
+  if (parts.size() < 3) {
+    log_warn("Input file name is expected to have the following format 'Flowcell_Lane_SampleLabel_1/2.fq/fastq.gz'");
+    log_warn("Ignore this warning if you provided Sample label and lane parameters.");
+    return;
+  }
+  for (size_t k = 2; k + 1 < parts.size(); ++k) label += (k > 2 ? "_" : "") + parts[k];
+  lane = parts[1];
+}
+
 void print_logo() {
   std::printf("\n");
   std::printf("        MGIKIT  -  B200 hot path\n");
@@ -95,7 +148,8 @@ void print_logo() {
 
 void usage() {
   std::printf("MGIKIT - MGI data demultipexing kit (B200 hot path).\n\nUsage: mgikit demultiplex [OPTIONS] --sample-sheet <FILE>\n"
-              "       mgikit template [OPTIONS] --sample-sheet <FILE>   (barcode template detection)\n\nOptions of demultiplex:\n");
+              "       mgikit template [OPTIONS] --sample-sheet <FILE>   (barcode template detection)\n"
+              "       mgikit reformat -f <R1> -r <R2> [OPTIONS]         (one sample: Illumina headers + quality report)\n\nOptions of demultiplex:\n");
   for (const auto& o : OPTS) {
     if (o.short_name) std::printf("  -%c, --%s", o.short_name, o.long_name);
     else std::printf("      --%s", o.long_name);
@@ -117,7 +171,7 @@ size_t parse_usize(const std::string& name, const std::string& v) {
 int cli_main(int argc, char** argv, const Backend& be) {
   // the subcommand decides the option table: it is the first word that is neither an option nor the value of the
   // global -l/--log-level in front of it
-  bool is_template = false;
+  bool is_template = false, is_reformat = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "-l" || a == "--log-level") {
@@ -126,10 +180,12 @@ int cli_main(int argc, char** argv, const Backend& be) {
     }
     if (!a.empty() && a[0] == '-') continue;
     is_template = a == "template";
+    is_reformat = a == "reformat";
     break;
   }
-  const Opt* table = is_template ? TEMPLATE_OPTS : OPTS;
-  const size_t n_table = is_template ? sizeof(TEMPLATE_OPTS) / sizeof(Opt) : sizeof(OPTS) / sizeof(Opt);
+  const Opt* table = is_template ? TEMPLATE_OPTS : (is_reformat ? REFORMAT_OPTS : OPTS);
+  const size_t n_table = is_template ? sizeof(TEMPLATE_OPTS) / sizeof(Opt)
+                                     : (is_reformat ? sizeof(REFORMAT_OPTS) / sizeof(Opt) : sizeof(OPTS) / sizeof(Opt));
   std::map<std::string, std::string> val;
   for (size_t k = 0; k < n_table; ++k)
     if (table[k].def) val[table[k].long_name] = table[k].def;
@@ -197,12 +253,12 @@ int cli_main(int argc, char** argv, const Backend& be) {
     usage();
     return 2;
   }
-  if (command != "demultiplex" && command != "template") {
-    std::fprintf(stderr, "error: this build provides the `demultiplex` and `template` commands (got '%s'); "
-                         "use the reference mgikit for report/reformat\n", command.c_str());
+  if (command != "demultiplex" && command != "template" && command != "reformat") {
+    std::fprintf(stderr, "error: this build provides the `demultiplex`, `template` and `reformat` commands (got '%s'); "
+                         "`report` panics in the reference itself (v2.2.0, index out of bounds in write_reports)\n", command.c_str());
     return 2;
   }
-  if (!val.count("sample-sheet")) {
+  if (command != "reformat" && !val.count("sample-sheet")) {
     std::fprintf(stderr, "error: the following required arguments were not provided:\n  --sample-sheet <arg_sample_sheet_file_path>\n");
     return 2;
   }
@@ -226,6 +282,93 @@ int cli_main(int argc, char** argv, const Backend& be) {
       ta.popular_template = flag("popular-template");
       ta.add_umi = !flag("no-umi");
       run_template(ta);
+    } catch (const std::exception& e) {
+      std::fflush(stdout);
+      std::fprintf(stderr, "mgikit error: %s\n", e.what());
+      return 101;
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    log_info("Exection time is " + std::to_string((long)secs) + " seconds.");
+    return 0;
+  }
+  if (command == "reformat") {
+    try {
+      // reformat(), src/lib.rs:2266-2464
+      DemuxOptions opt;
+      opt.report_level = (int)parse_usize("report-level", val["report-level"]);
+      RunArgs ra;
+      ra.read1 = val["read1"];
+      ra.read2 = val["read2"];
+      ra.output_dir = val["output"];
+      ra.report_dir = val["reports"];
+      ra.lane = val["lane"];
+      ra.instrument = val["instrument"];
+      ra.run = val["run"];
+      ra.mgi_data = true;
+      ra.force = flag("force");
+      ra.r1_suffix = "";
+      ra.r2_suffix = "";
+      ra.info_file = val["info-file"];
+      ra.illumina_format = !flag("disable-illumina");
+      ra.check_content = flag("validate");
+      RunInfo run = make_run_info(ra);
+      run.get_read_information();
+      if (run.lane.empty()) {
+        log_info("lane detected in the read header will be used for this run!");
+        run.lane = run.barcode_read_info.lane;
+      }
+      run.confirm_format();
+      const size_t cbs = parse_usize("compression-buffer-size", val["compression-buffer-size"]);
+      const size_t wbs = parse_usize("writing-buffer-size", val["writing-buffer-size"]);
+      std::string stem = run.barcode_reads;   // Path::file_stem(): the name without its last extension
+      if (stem.find_last_of('/') != std::string::npos) stem = stem.substr(stem.find_last_of('/') + 1);
+      if (stem.find_last_of('.') != std::string::npos && stem.find_last_of('.') > 0) stem = stem.substr(0, stem.find_last_of('.'));
+      std::string label_sb, lane_sb;
+      parse_sb_file_name(stem, label_sb, lane_sb);
+      ReformatSample rf;
+      rf.label = val["sample-label"];
+      if (rf.label.empty()) {
+        if (label_sb.empty())
+          throw Fatal("Sample label needs to be passed either through '--sample-label' parameter or the third part of the file name after separation by '_'");
+        rf.label = label_sb;
+      }
+      if (lane_sb != run.lane)
+        log_warn("The lane extracted from the file name (" + lane_sb + ") is not the same as the provided lane (" + run.lane + ")");
+      rf.sample_index = parse_usize("sample-index", val["sample-index"]);
+      if (rf.sample_index < 1)   // ReformatedSample::new, src/formater.rs:23-25
+        throw Fatal("Sample index (val: " + std::to_string(rf.sample_index) + ") needs to be greater than 0!");
+      rf.umi_length = (int)parse_usize("umi-length", val["umi-length"]);
+      rf.barcode = val["barcode"];
+      log_info("Sample's id, extracted from the file name is: " + rf.label);
+      log_info("Sample's index to be used in file naming is: " + std::to_string(rf.sample_index));
+      log_info("Sample's barcode: " + rf.barcode);
+      if (rf.barcode.empty())
+        log_warn("No mismatches will be considered as sample's barcode is not provided to compare against!");
+      log_info("Umi length to be extracted from the tail of R2: " + std::to_string(rf.umi_length));
+      // BufferInfo::new(), src/sample_data.rs:413-455 — kept for flag compatibility
+      if (cbs > wbs)
+        throw Fatal("Compression buffer size '--compression-buffer-size' should be less than Writing buffer size ('--writing-buffer-size').");
+      if (wbs < 65536)
+        throw Fatal("Writing buffer size '--writing-buffer-size' will be increased to minimal allowed value (65536).");
+      if (wbs > 536870912)
+        throw Fatal("Writing buffer size '--writing-buffer-size' will be reduced to the maximum allowed value (536870912).");
+      const double mem = std::atof(val["memory"].c_str());
+      if (0.0 < mem && mem <= 0.5) throw Fatal("Requested memory should be greater than 0.5 GB!");
+      if ((size_t)rf.umi_length > run.barcode_read_info.sequence_length)
+        throw Fatal("The UMI is longer than the read that carries it!");
+      opt.compression_level = (int)parse_usize("compression-level", val["compression-level"]);
+      if (opt.compression_level > 12) throw Fatal("compression level must be in [0, 12]");
+      opt.threads = (int)parse_usize("threads", val["threads"]);
+      opt.gpus = (int)parse_usize("gpus", val["gpus"]);
+      opt.chunk_bytes = parse_usize("chunk-size", val["chunk-size"]);
+      opt.slots = (int)parse_usize("slots", val["slots"]);
+      opt.reader_threads = (int)parse_usize("reader-threads", val["reader-threads"]);
+      opt.host_gzip = flag("host-gzip");
+      opt.leave_teardown_to_exit = be.exits_after_command;
+      opt.reformat = &rf;
+      const SampleSheet sheet = dummy_sample_sheet(rf.label);
+      log_info("Reporting level is: " + std::to_string(opt.report_level));
+      run_demultiplex(be, sheet, run, opt);
     } catch (const std::exception& e) {
       std::fflush(stdout);
       std::fprintf(stderr, "mgikit error: %s\n", e.what());

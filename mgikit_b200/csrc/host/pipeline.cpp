@@ -400,24 +400,38 @@ class Channel {
 
 }  // namespace
 
+SampleSheet dummy_sample_sheet(const std::string& label) {
+  SampleSheet sh;
+  sh.info.push_back({label, "", "", "", "", "", "."});
+  sh.info.push_back({"Undetermined", "", "", "", "", "", "."});
+  sh.info.push_back({"Ambiguous", "", "", "", "", "", "."});
+  sh.writing_samples = {0, 1, 2};
+  sh.unique_samples_ids = {0, 1, 2};
+  sh.project_samples["."] = {};
+  return sh;
+}
+
 void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, const DemuxOptions& opt) {
   const auto t_start = std::chrono::steady_clock::now();
   const bool paired = run.paired_read_input();
   const bool illumina = run.illumina_format;
+  const ReformatSample* rf = opt.reformat;
   const int total = sheet.total(), und = total - 2;
-  const int BL = sheet.barcode_length();
-  const int m = opt.mismatches;
+  const int BL = rf ? rf->umi_length : sheet.barcode_length();   // src/lib.rs:878-882
+  const int m = rf ? 5 : opt.mismatches;                          // analyse_fastq(.., 5, ..), src/lib.rs:2431
 
-  log_info(std::string("Comprehensive scan mode: ") + (run.comprehensive_scan ? "true" : "false"));
-  log_info("Allowed mismatches when finding the index are: " + std::to_string(m));
-  if (!opt.per_index_error)
-    log_info("The allowed mismatches will be compared to the total mismatches for all indicies combined.");
-  else
-    log_info("The allowed mismatches will be considered per index.");
-  if (m > 2)
-    log_warn("It is not recommended to allow more than 2 mismatches per index! This might decrease the accuracy of the demultipexing!");
-  log_info("Reads that match with multiple samples will be saved in ambiguous_read1/2.fastq file");
-  log_info("The paired read files are assumed to contain the paired reads in the same order!");
+  if (!rf) log_info(std::string("Comprehensive scan mode: ") + (run.comprehensive_scan ? "true" : "false"));
+  if (!rf) {
+    log_info("Allowed mismatches when finding the index are: " + std::to_string(m));
+    if (!opt.per_index_error)
+      log_info("The allowed mismatches will be compared to the total mismatches for all indicies combined.");
+    else
+      log_info("The allowed mismatches will be considered per index.");
+    if (m > 2)
+      log_warn("It is not recommended to allow more than 2 mismatches per index! This might decrease the accuracy of the demultipexing!");
+    log_info("Reads that match with multiple samples will be saved in ambiguous_read1/2.fastq file");
+    log_info("The paired read files are assumed to contain the paired reads in the same order!");
+  }
 
   // ---- output files: create_sample_data_list(), src/sample_data.rs:656-726
   std::vector<SampleFiles> files((size_t)total);
@@ -425,6 +439,13 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     if (sheet.writing_samples[(size_t)i] != i) continue;
     std::string r1, r2;
     const bool pseudo = i >= und;
+    if (rf) {   // one sample, named by --sample-index (src/lib.rs:1386-1400); SampleData::minimal_sample() has no files
+      if (i != 0) continue;
+      output_file_names(rf->label, run.lane, rf->sample_index, illumina, paired, r1, r2);
+      files[0].barcode_path = path_join(run.output_dir, r2);
+      if (paired) files[0].paired_path = path_join(run.output_dir, r1);
+      continue;
+    }
     output_file_names(sheet.info[(size_t)i][SAMPLE_COLUMN], run.lane,
                       (pseudo && illumina) ? (size_t)-1 : (size_t)sheet.unique_samples_ids[(size_t)i] + 1, illumina, paired,
                       r1, r2);
@@ -453,6 +474,11 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
   if (illumina) fl.illumina_prefix = run.create_illumina_header_prefix();
   GpuPlan plan;
   build_plan(sheet, fl, plan);
+  if (rf) {
+    plan.cfg.reformat = 1;
+    plan.cfg.reformat_umi_length = rf->umi_length;
+    plan.cfg.reformat_barcode = rf->barcode.c_str();
+  }
 
   // records per chunk: batch_size, src/lib.rs:600-605
   const size_t rec_len = std::max(run.barcode_read_info.read_length, run.paired_read_info.read_length);
@@ -514,7 +540,8 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
     if (paired) rd1.reset(new BlockReader(std::move(gz1), chunk_bytes, rpb, n_buffers, be, pool));
 
     const bool single_template = sheet.templates.size() == 1;
-    const auto& g0 = sheet.templates[0].geometry;
+    static const std::array<int, 10> no_geometry{};
+    const auto& g0 = sheet.templates.empty() ? no_geometry : sheet.templates[0].geometry;
     Channel<ChunkJob*> to_commit, finished;
     std::atomic<bool> failed{false};
 
@@ -792,9 +819,14 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
   log_info(std::to_string(report.get_total_reads()) + " reads were processed in " + std::to_string((long)secs) + " secs.");
 
   // src/lib.rs:1827-1853
-  const int max_mismatches = !opt.per_index_error ? m + 1 : 2 * m + 1;
-  report.prepare_final_data(max_mismatches, paired ? 1 : 0, run.barcode_read_info, run.paired_read_info, BL);
-  report.write_reports(run, sheet, opt.report_level, opt.report_limit, max_mismatches);
+  if (rf) {   // src/lib.rs:2445-2457
+    if (opt.report_level > 0) report.prepare_final_data(5, paired ? 1 : 0, run.barcode_read_info, run.paired_read_info, BL);
+    report.write_sample_report(run, sheet, opt.report_level);
+  } else {
+    const int max_mismatches = !opt.per_index_error ? m + 1 : 2 * m + 1;
+    report.prepare_final_data(max_mismatches, paired ? 1 : 0, run.barcode_read_info, run.paired_read_info, BL);
+    report.write_reports(run, sheet, opt.report_level, opt.report_limit, max_mismatches);
+  }
   {
     char msg[96];
     snprintf(msg, sizeof msg, "reports written after %.2f s", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());

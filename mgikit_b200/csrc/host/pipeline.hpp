@@ -35,6 +35,14 @@ struct Backend {
   bool exits_after_command;   // the binary leaves with _exit: contexts and pinned buffers need no orderly teardown
 };
 
+// `mgikit reformat` (src/lib.rs:2266-2464, src/formater.rs): the run of ONE sample whose reads are already apart
+struct ReformatSample {
+  std::string label;        // --sample-label, or the third '_' part of the barcode read's file name
+  size_t sample_index = 1;  // --sample-index: the S<n> of the Illumina file names
+  int umi_length = 0;       // --umi-length
+  std::string barcode;      // --barcode
+};
+
 struct DemuxOptions {
   int mismatches = 1;
   bool per_index_error = false;
@@ -48,7 +56,11 @@ struct DemuxOptions {
   int reader_threads = 0;   // --reader-threads: inflate threads per input file (0 = share of -t)
   bool leave_teardown_to_exit = false;   // the product binary: it calls _exit right after the command
   bool host_gzip = false;   // --host-gzip (extension): gzip on the host threads even at the default level
+  const ReformatSample* reformat = nullptr;   // set: the `reformat` command (the sheet is dummy_sample_sheet())
 };
+
+// SampleManager::dummy_sample(), src/sample_manager.rs:133-185: the sample, Undetermined, Ambiguous
+SampleSheet dummy_sample_sheet(const std::string& label);
 
 // Runs the whole command; throws Fatal on any error the reference would panic on.
 void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, const DemuxOptions& opt);

@@ -250,4 +250,27 @@ void ReportData::write_reports(const RunInfo& run, const SampleSheet& sheet, int
   }
 }
 
+void ReportData::write_sample_report(const RunInfo& run, const SampleSheet& sheet, int reporting_level) const {
+  if (reporting_level < 1) return;   // :567: nothing else is written for one sample (the barcode histograms are empty)
+  const auto& row = sample_statistics[0];
+  size_t width = row.size();
+  for (size_t i = row.size(); i-- > 11;) {   // :504-512
+    if (row[i] != 0) break;
+    width = i;
+  }
+  const int max_mismatches = (int)width - 10;
+  std::string out =
+      "job_number\tsample_id\tr1_qc_30\tr2_qc_30\tr3_qc_30\tr1_bases\tr2_bases\tr3_bases\tr1_qc\tr2_qc\tr3_qc\tall_reads";
+  for (int cnt = 0; cnt < max_mismatches; ++cnt) out += "\t" + std::to_string(cnt) + "-mismatches";
+  out += "\n";
+  out += sheet.info[0][PROJECT_ID_COLUMN] + "\t" + sheet.info[0][SAMPLE_COLUMN];
+  for (size_t c = 0; c < width; ++c) out += "\t" + std::to_string(row[c]);
+  out += "\n";
+  const std::string path = path_join(run.report_dir, sheet.info[0][SAMPLE_COLUMN] + ".mgikit.sample_stats");
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw Fatal("couldn't create output");
+  fwrite(out.data(), 1, out.size(), f);
+  fclose(f);
+}
+
 }  // namespace mgikit

@@ -27,6 +27,9 @@ struct ReportData {
                           const ReadInfo& paired_read, int barcode_length);  // :437-463
   void write_reports(const RunInfo& run, const SampleSheet& sheet, int reporting_level, size_t report_limit,
                      int max_mismatches) const;                  // :465-676 (individual_sample == usize::MAX)
+  // the same with individual_sample == 0 (`reformat`, src/lib.rs:2457): only <sample>.mgikit.sample_stats, the row of
+  // sample 0, mismatch columns cut after the last one that is not zero (:504-512)
+  void write_sample_report(const RunInfo& run, const SampleSheet& sheet, int reporting_level) const;
 };
 
 std::string fmt_f64(double v);    // Rust `{}`

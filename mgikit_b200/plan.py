@@ -69,6 +69,10 @@ class RunSpec:
     max_chunk_records: int = 1 << 20
     n_slots: int = 2
     device: int = 0
+    # `reformat` (one Sample with any index, its template list is not sent): UMI length, the sample's barcode
+    reformat: bool = False
+    reformat_umi_length: int = 0
+    reformat_barcode: str = ""
 
 
 def build_config(spec: RunSpec):
@@ -154,5 +158,12 @@ def build_config(spec: RunSpec):
     cfg.max_chunk_bytes = spec.max_chunk_bytes
     cfg.max_chunk_records = spec.max_chunk_records
     cfg.n_slots = spec.n_slots
+    if spec.reformat:
+        bc = spec.reformat_barcode.encode()
+        cfg.reformat = 1
+        cfg.reformat_umi_length = spec.reformat_umi_length
+        cfg.reformat_barcode = bc
+        cfg.n_templates = 0
+        keep.append(bc)
     keep += [tarr, warr, prefix]
     return cfg, keep

@@ -203,6 +203,9 @@ struct orc_ctx {
   int n_tpl;
   otpl* tpl;
   int S, total, BL, mism_w;
+  int reformat;     /* process_buffer with demultiplex == false */
+  char* rf_barcode; /* ReformatedSample::barcode, src/formater.rs:10-11 */
+  size_t rf_barcode_len;
   uint64_t* stats; /* [total][10] */
   uint64_t* mism;  /* [total][2m+2] */
   uint64_t* red_stats; /* result of the last orc_allreduce_counters */
@@ -220,8 +223,11 @@ static char g_create_err[512];
 const char* orc_last_error(const orc_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 
 int orc_create(const mgk_config* cfg, orc_ctx** out) {
-  if (!cfg || !out || cfg->abi_version != MGK_ABI_VERSION || cfg->n_templates < 1 ||
-      cfg->n_templates > MGK_MAX_TEMPLATES || cfg->n_samples < 1) {
+  if (!cfg || !out || cfg->abi_version != MGK_ABI_VERSION || cfg->n_templates < (cfg->reformat ? 0 : 1) ||
+      cfg->n_templates > MGK_MAX_TEMPLATES || cfg->n_samples < 1 ||
+      (cfg->reformat && (cfg->n_samples != 1 || cfg->n_templates != 0 || cfg->reformat_umi_length < 0 ||
+                         cfg->reformat_umi_length > MGK_MAX_BARCODE_LEN || !cfg->read2_has_sequence ||
+                         cfg->out_mode == MGK_OUT_MGI_FULL_HEADER))) { /* src/lib.rs:2302-2322, run_manager.rs:137 */
     snprintf(g_create_err, sizeof g_create_err, "orc_create: bad config");
     return MGK_ERR_ARG;
   }
@@ -235,7 +241,7 @@ int orc_create(const mgk_config* cfg, orc_ctx** out) {
   c->writing = (int32_t*)malloc(sizeof(int32_t) * (size_t)c->total);
   memcpy(c->writing, cfg->writing_sample, sizeof(int32_t) * (size_t)c->total);
   c->n_tpl = cfg->n_templates;
-  c->tpl = (otpl*)calloc((size_t)c->n_tpl, sizeof(otpl));
+  c->tpl = (otpl*)calloc((size_t)(c->n_tpl ? c->n_tpl : 1), sizeof(otpl));
   for (int t = 0; t < c->n_tpl; ++t) {
     const mgk_template* s = &cfg->templates[t];
     otpl* o = &c->tpl[t];
@@ -259,7 +265,10 @@ int orc_create(const mgk_config* cfg, orc_ctx** out) {
     get_all_mismatches(&o->d7, o->i7, o->n_i7, o->g[1], cfg->allowed_mismatches);
     get_all_mismatches(&o->d5, o->i5, o->n_i5, o->g[4], cfg->allowed_mismatches);
   }
-  c->BL = c->tpl[0].g[9]; /* src/lib.rs:878-879 */
+  c->reformat = cfg->reformat != 0;
+  c->rf_barcode = strdup(cfg->reformat && cfg->reformat_barcode ? cfg->reformat_barcode : "");
+  c->rf_barcode_len = strlen(c->rf_barcode);
+  c->BL = c->reformat ? cfg->reformat_umi_length : c->tpl[0].g[9]; /* src/lib.rs:878-882 */
   c->stats = (uint64_t*)calloc((size_t)c->total * MGK_N_STATS, sizeof(uint64_t));
   c->mism = (uint64_t*)calloc((size_t)c->total * (size_t)c->mism_w, sizeof(uint64_t));
   c->red_stats = (uint64_t*)calloc((size_t)c->total * MGK_N_STATS, sizeof(uint64_t));
@@ -309,6 +318,7 @@ void orc_destroy(orc_ctx* c) {
   free(c->mism);
   free(c->writing);
   free(c->prefix);
+  free(c->rf_barcode);
   free(c);
 }
 
@@ -417,10 +427,13 @@ static match_out find_matching_sample(const orc_ctx* c, const uint8_t* bar) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* write_illumina_header() free fn with sb_header == false, src/sample_data.rs:569-654.
- * h = MGI header INCLUDING its '\n'; returns bytes written to out. */
+/* write_illumina_header() free fn, src/sample_data.rs:569-654.
+ * h = the header slice handed over: the MGI header INCLUDING its '\n' (reformat of raw MGI headers: without
+ * its last two bytes, src/lib.rs:1246); returns bytes written to out.
+ * sb_header (reformat): [":" umi] + what the input header holds from sep on (:627-637);
+ * else (demultiplex): umi (its ':' included) + " " n ":N:0:" (:638-652). */
 static size_t illumina_fields(uint8_t* out, const uint8_t* h, size_t hl, size_t L, size_t sep,
-                              const uint8_t* umi, size_t umi_len) {
+                              const uint8_t* umi, size_t umi_len, int sb_header) {
   size_t e = 0;
   out[e++] = h[L + 1];
   out[e++] = ':';
@@ -445,6 +458,16 @@ static size_t illumina_fields(uint8_t* out, const uint8_t* h, size_t hl, size_t 
       out[e++] = h[o + 2];
     }
     if (f == 0) out[e++] = ':';
+  }
+  if (sb_header) {
+    if (umi_len) { /* :628-633 */
+      out[e++] = ':';
+      memcpy(out + e, umi, umi_len);
+      e += umi_len;
+    }
+    memcpy(out + e, h + sep, hl - sep - 1); /* :634-637 */
+    e += hl - sep - 1;
+    return e;
   }
   if (umi_len) { /* :640-643 */
     memcpy(out + e, umi, umi_len);
@@ -592,9 +615,51 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
       hdr_cap = c->prefix_len + hl + 1024;
       hdr = (uint8_t*)realloc(hdr, hdr_cap);
     }
-    const size_t sep_position = seq_start - header_start - 3; /* :1007 */
-    const uint8_t* bar = r2 + plus_start - 1 - BL;            /* :1012 */
-    match_out mo = find_matching_sample(c, bar);
+    size_t sep_position = seq_start - header_start - 3; /* :1007 */
+    const uint8_t* bar = r2 + plus_start - 1 - BL;      /* :1012 */
+    size_t raw_shift = 0, header_shift = 0, rf_tail_offset = 0;
+    match_out mo;
+    if (c->reformat) { /* :1090-1147 */
+      memset(&mo, 0, sizeof mo);
+      mo.bar_t = mo.umi_t = -1;
+      const uint8_t* sp = (const uint8_t*)memchr(r2 + header_start, ' ', hl);
+      if (sp) {
+        sep_position = (size_t)(sp - (r2 + header_start));
+      } else { /* "You might be using MGI raw data" */
+        raw_shift = 2;
+        sep_position = hl - 3;
+      }
+      /* header_shift = seq_start - sep_position - header_start - 3 (:1129) wraps for a space in the last two
+       * header bytes, and hamming_distance(..).unwrap() (:1108-1112) panics on barcodes of another length */
+      if (sep_position > hl - 3 ||
+          (c->rf_barcode_len && sep_position != hl - 3 && hl - 1 - (sep_position + 7) != c->rf_barcode_len) ||
+          (c->rf_barcode_len && sep_position != hl - 3 && sep_position + 7 > hl - 1)) {
+        snprintf(c->err, sizeof c->err, "record %llu: header does not end with ` n:N:0:<barcode of %zu bases>`",
+                 (unsigned long long)i, c->rf_barcode_len);
+        rc = MGK_ERR_FORMAT;
+        break;
+      }
+      if (c->rf_barcode_len && sep_position != hl - 3) {
+        const uint8_t* hb = r2 + header_start + sep_position + 7;
+        for (size_t k = 0; k < c->rf_barcode_len; ++k) mo.curr_mismatch += hb[k] != (uint8_t)c->rf_barcode[k];
+      }
+      if (mo.curr_mismatch > 4) mo.curr_mismatch = 4; /* :1140-1141 */
+      mo.sample_id = 0;                               /* :1114 */
+      header_shift = hl - sep_position - 3;           /* :1129-1130 */
+      rf_tail_offset = header_shift + 1;
+      if (c->rf_barcode_len && sep_position == hl - 3) { /* :1132-1137 */
+        header_shift = 0;
+        rf_tail_offset = c->rf_barcode_len + 6;
+      }
+      if (paired && illumina && seq_start_pr - header_start_pr < header_shift + 2) { /* :1275 would read in front of the record */
+        snprintf(c->err, sizeof c->err, "record %llu: the paired read's header is shorter than the barcode read's tail",
+                 (unsigned long long)i);
+        rc = MGK_ERR_FORMAT;
+        break;
+      }
+    } else {
+      mo = find_matching_sample(c, bar);
+    }
     if (mo.panicked) {
       snprintf(c->err, sizeof c->err, "record %llu: reference would panic (stale dictionary lookup)",
                (unsigned long long)i);
@@ -624,7 +689,11 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
       memcpy(umi + 1, bar + BL - g[8], (size_t)g[7]);
       umi_len = 1 + (size_t)g[7];
     }
-    const size_t tail_offset = barcode_len + 6; /* :1019 */
+    if (c->reformat && BL > 0) { /* :1117-1124: the last umi_length bases, no ':' */
+      memcpy(umi, r2 + plus_start - 1 - BL, BL);
+      umi_len = BL;
+    }
+    const size_t tail_offset = c->reformat ? rf_tail_offset : barcode_len + 6; /* :1019 */
 
     if (sample_id == und || sample_id == amb) {
       /* :1048-1088: the label is rebuilt on the host from this offset */
@@ -678,7 +747,8 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
     c->mism[(size_t)sample_id * (size_t)c->mism_w + (size_t)mo.curr_mismatch + 1] += 1; /* :1212 */
 
     const int w = c->writing[sample_id]; /* :1214 */
-    if (sample_id >= und) {              /* :1225-1235 */
+    if (c->reformat && !illumina) {      /* :1224: if demultiplex || illumina_format */
+    } else if (sample_id >= und) {       /* :1225-1235 */
       bb_add(&S->bin_r2[sample_id], r2 + header_start, read_end + 1 - header_start);
       if (paired) bb_add(&S->bin_r1[sample_id], r1 + header_start_pr, read_end_pr + 1 - header_start_pr);
     } else {
@@ -687,12 +757,25 @@ int orc_submit(orc_ctx* c, uint64_t seq, const uint8_t* r2, uint64_t r2_len, con
       if (illumina) { /* :1240-1293 */
         size_t e = c->prefix_len;
         memcpy(hdr, c->prefix, e); /* src/sample_data.rs:256 */
-        e += illumina_fields(hdr + e, r2 + header_start, hl, L, sep_position, umi, umi_len);
-        memcpy(hdr + e, barcode, barcode_len); /* :1255 */
-        e += barcode_len;
+        e += illumina_fields(hdr + e, r2 + header_start, hl - raw_shift, L, sep_position, umi, umi_len, c->reformat);
+        if (!c->reformat) {
+          memcpy(hdr + e, barcode, barcode_len); /* :1255 */
+          e += barcode_len;
+        } else if (sep_position == hl - 3 && c->rf_barcode_len) { /* :1256-1264 */
+          hdr[e++] = ' ';
+          hdr[e++] = r2[seq_start - 2];
+          memcpy(hdr + e, ":N:0:", 5);
+          e += 5;
+          memcpy(hdr + e, c->rf_barcode, c->rf_barcode_len);
+          e += c->rf_barcode_len;
+        }
         if (B2) bb_add(B2, hdr, e);
         if (B1) { /* copy_header_2_paired + fix_paired_read_header, or direct write (:1265-1292) */
-          hdr[e - tail_offset] = r1[seq_start_pr - 2];
+          if (!c->reformat) {
+            hdr[e - tail_offset] = r1[seq_start_pr - 2];
+          } else if (c->rf_barcode_len || sep_position < hl - 3) { /* :1269-1277 */
+            hdr[e - tail_offset] = r1[seq_start_pr - 2 - header_shift];
+          }
           bb_add(B1, hdr, e);
         }
         header_start = seq_start - 1; /* :1293 */

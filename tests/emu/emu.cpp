@@ -105,10 +105,12 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     R.mo.mism = 0;
     R.mo.bar_t = R.mo.umi_t = -1;
     R.mo.panicked = 0;
-    if (G.p2 - G.s2 >= (uint32_t)P.BL + 1u) R.mo = match_barcode(P, P.codes, r2 + G.p2 - 1 - P.BL);
+    if (P.reformat) R.mo.sample = 0;   // src/lib.rs:1114
+    else if (G.p2 - G.s2 >= (uint32_t)P.BL + 1u) R.mo = match_barcode(P, P.codes, r2 + G.p2 - 1 - P.BL);
     if (R.mo.panicked) { rc = MGK_ERR_FORMAT; c->err = "panic"; break; }
     R.pl = record_plan(P, r2, G, R.mo.sample, R.mo.bar_t, R.mo.umi_t);
-    if (R.pl.fmt_error) { rc = MGK_ERR_FORMAT; c->err = "format"; break; }
+    if (R.pl.fmt_error) { rc = MGK_ERR_FORMAT; c->err = P.reformat ? "record does not have the header / line layout `reformat` slices" : "format"; break; }
+    if (P.reformat) R.mo.mism = (int)R.pl.rf_mism;
     R.bin = R.pl.matched ? P.writing[R.mo.sample] : R.mo.sample;
     R.d2 = bin2[(size_t)R.bin];
     R.d1 = bin1[(size_t)R.bin];
@@ -149,8 +151,9 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     uint8_t* dst[3] = {nullptr, o1 + c->off1[(size_t)R.bin] + R.d1, o2 + c->off2[(size_t)R.bin] + R.d2};
     // what k_emit does for one pair: header halves by scalar roles, byte ranges by copy_piece (lanes looped; the kernel's PTX movers do the same bytes)
     ReadPlan plan[3];
-    plan[2] = plan_read(P, G, 2, R.mo.sample, R.mo.bar_t, R.pl.len2);
-    plan[1] = plan_read(P, G, 1, R.mo.sample, R.mo.bar_t, P.paired ? R.pl.len1 : 0u);
+    const uint32_t rf = rf_pack(R.pl.rf_tcl, R.pl.rf_raw);   // what the kernel carries in RecMeta
+    plan[2] = plan_read(P, G, 2, R.mo.sample, R.mo.bar_t, R.pl.len2, rf);
+    plan[1] = plan_read(P, G, 1, R.mo.sample, R.mo.bar_t, P.paired ? R.pl.len1 : 0u, rf);
     for (int which = 2; which >= 1; --which) {   // scalar roles: the rewritten headers
       const ReadPlan& r = plan[which];
       const int slot = which == 2 ? HDR_SLOT0 : HDR_SLOT1;
@@ -159,13 +162,13 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
       const uint32_t hl = own ? r.hl : plan[1].hl;   // illumina: both reads carry the same header
       if (hl <= HDR_SLOT_BYTES) {
         uint8_t* o = S + hs + (uint32_t)(slot - 1) * HDR_SLOT_BYTES;
-        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 1 : 0);   // the two halves, either order
-        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 0 : 1);
+        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 1 : 0, rf);   // the two halves, either order
+        build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, o, (i & 1) ? 0 : 1, rf);
       } else {   // too long for a slot: at its destination(s)
         for (int to = 2; to >= 1; --to) {
           if (plan[to].hdr != slot || plan[to].len == 0) continue;
-          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 0);
-          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 1);
+          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 0, rf);
+          build_header(P, S, cs0, G, which, R.mo.bar_t, R.mo.umi_t, hl, dst[to], 1, rf);
           if (plan[to].patch_at != 0xffffffffu) dst[to][plan[to].patch_at] = S[plan[to].patch_src];
         }
       }

@@ -11,6 +11,10 @@
  3. runs the reference's own binary (oracle/_ref/mgikit, v2.2.0) on seeded
     synthetic lanes shaped like BASELINE.json configs 2-5 and records the same
     digests -> synthetic_reference.json.
+ 4. `reformat` (also alone: `make_golden.py reformat`): the inputs and expected
+    digests of the reference's extras_test fixtures -> reformat_matrix.json, and
+    the reference binary's answer on seeded one-sample lanes
+    -> reformat_reference.json.
 """
 import dataclasses
 import hashlib
@@ -27,6 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import lanes  # noqa: E402
 import ref_matrix as M  # noqa: E402
+import reformat_cases as RF  # noqa: E402
 from mgikit_b200 import synth  # noqa: E402
 
 REF = "/root/reference/testing_data"
@@ -94,7 +99,46 @@ def run_template(binary, lane, n, flags, d):
         return hashlib.sha256(f.read()).hexdigest()
 
 
+def copy_fixture(rel):
+    src = os.path.join(REF, rel)
+    if os.path.isdir(src):
+        for name in os.listdir(src):
+            if os.path.isfile(os.path.join(src, name)):
+                os.makedirs(os.path.join(DST, rel), exist_ok=True)
+                shutil.copy(os.path.join(src, name), os.path.join(DST, rel, name))
+    else:
+        os.makedirs(os.path.dirname(os.path.join(DST, rel)), exist_ok=True)
+        shutil.copy(src, os.path.join(DST, rel))
+
+
+def reformat_goldens():
+    matrix = {}
+    for c in RF.fixture_cases():
+        it = iter(c.args)
+        for a in it:
+            if a in RF.PATH_FLAGS:
+                copy_fixture(next(it))
+        matrix[c.name] = {"files": lanes.digest_dir(os.path.join(REF, "expected", c.expected))}
+    with open(os.path.join(HERE, "reformat_matrix.json"), "w") as f:
+        json.dump(matrix, f, indent=0, sort_keys=True)
+    syn = {}
+    for l in RF.synthetic_lanes():
+        d = tempfile.mkdtemp(prefix="golden_")
+        p1, p2 = RF.write_rf_lane(l, d)
+        out = os.path.join(d, "out")
+        lanes.run_binary(REF_BIN, RF.rf_args(l, p1, p2, out))
+        t1, t2 = RF.lane_text(l)
+        syn[l.name] = {"inputs": [hashlib.sha256(t).hexdigest() for t in (t1, t2) if t is not None], "files": lanes.digest_dir(out)}
+        shutil.rmtree(d)
+    with open(os.path.join(HERE, "reformat_reference.json"), "w") as f:
+        json.dump(syn, f, indent=0, sort_keys=True)
+    print(f"{len(matrix)} reformat fixture cases, {len(syn)} synthetic reformat lanes")
+
+
 def main():
+    if sys.argv[1:] == ["reformat"]:
+        reformat_goldens()
+        return
     cases = M.all_cases()
     needed = set()
     for _, r1, r2, sheet, _, expected in template_cases():
@@ -151,6 +195,7 @@ def main():
     with open(os.path.join(HERE, "template_reference.json"), "w") as f:
         json.dump(tpl, f, indent=0, sort_keys=True)
     print(f"{len(matrix)} fixture cases, {len(syn)} synthetic lanes, {len(tpl)} template lanes")
+    reformat_goldens()
 
 
 if __name__ == "__main__":
