@@ -178,17 +178,18 @@ def serial_run(hp, dev_args, n_chunks, flags):
     return rows
 
 
-def short_lane_line(lane, n, device, peak):
-    """other_configs: a short resident run of another BASELINE configuration (same CUDA-event method)."""
+def short_lane_line(lane, n, device, peak, reformat=False):
+    """other_configs: a short resident run of another BASELINE configuration (same CUDA-event method); reformat: the
+    lane as one sample's reads through the one-sample mode of the path (`mgikit reformat`, 8-base UMI)."""
     import numpy as np
     import torch
     from mgikit_b200 import synth
     from mgikit_b200.capi import MGK_IN_DEVICE, MGK_OUT_DEVICE, load_gpu_library
     from util import device_copy, make_hotpath
-    r1, r2 = synth.make_block(lane, 0, n)
+    r1, r2 = synth.reformat_block(lane, 0, n) if reformat else synth.make_block(lane, 0, n)
     in_bytes = r2.size + (r1.size if r1 is not None else 0)
-    spec = synth.run_spec(lane, max_chunk_bytes=max(r1.size if r1 is not None else 0, r2.size) + 4096, max_chunk_records=n + 64,
-                          n_slots=2, device=device)
+    caps = dict(max_chunk_bytes=max(r1.size if r1 is not None else 0, r2.size) + 4096, max_chunk_records=n + 64, n_slots=2, device=device)
+    spec = synth.reformat_run_spec(lane, umi_length=8, **caps) if reformat else synth.run_spec(lane, **caps)
     hp = make_hotpath(load_gpu_library(), "mgk_", spec)
     try:
         d2, a2 = device_copy(r2)
@@ -204,7 +205,7 @@ def short_lane_line(lane, n, device, peak):
         out_bytes = res.out_r2_bytes + res.out_r1_bytes
         emit_ms = float(k_ms[:, 3].mean())
         achieved = (in_bytes + out_bytes) / (emit_ms * 1e-3) / 1e9
-        return {"lane": lane.name, "units_per_chunk": n, "unit": "read pairs/s" if lane.paired else "reads/s",
+        return {"lane": lane.name + ("-as-one-sample-reformat-umi8" if reformat else ""), "units_per_chunk": n, "unit": "read pairs/s" if lane.paired else "reads/s",
                 "value": n * n_chunks / (span * 1e-3), "bytes_per_unit": {"in": in_bytes / n, "out": out_bytes / n},
                 "kernel_ms": {"scan_newlines": float(k_ms[:, 0].mean()), "match_plan": float(k_ms[:, 1].mean()),
                               "bin_scan": float(k_ms[:, 2].mean()), "emit_qc": emit_ms, "chunk": float(k_ms[:, 4].mean())},
@@ -490,6 +491,10 @@ def main():
                 other[key] = short_lane_line(ln, 1 << 20, local, peak)
             except Exception as e:
                 other[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            other["reformat"] = short_lane_line(synth.CONFIG2, 1 << 20, local, peak, reformat=True)
+        except Exception as e:
+            other["reformat"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     files = None
     if a.gpus == 1 and a.file_pairs > 0:

@@ -3,7 +3,8 @@
  *
  * This is the drop-in boundary for ONE call of the reference:
  *     process_buffer()                     /root/reference/src/lib.rs:840-868 (signature)
- *     its only call site                   src/lib.rs:1496-1536
+ *     its only call site                   src/lib.rs:1496-1536 (reached from demultiplex, :511-838, and,
+ *                                          with demultiplex == false, from reformat, :2266-2464)
  *     per-worker state it mutates          Vec<SampleData> (src/sample_data.rs:16-23)
  *                                          ReportManager   (src/report_manager.rs:254-261)
  * The reference has no FFI of its own (pure Rust crate); a Rust host would bind

@@ -198,6 +198,41 @@ def make_block(spec: LaneSpec, block: int, n_pairs: int, first_read: int = None)
     return r1, r2
 
 
+REFORMAT_BARCODE = "ACGTTGCAAC"
+
+
+def reformat_block(spec: LaneSpec, block: int, n_pairs: int):
+    """The lane's block as ONE sample's reads the way a splitting-barcode run leaves them: the header ends with
+    " n:N:0:BARCODE" instead of "/n" (a tenth of the reads with one base of it changed).  Input of `mgikit reformat`."""
+    r1, r2 = make_block(spec, block, n_pairs)
+    rng = np.random.default_rng([spec.seed, block, 11])
+    hl = 1 + len(FLOWCELL) + 2 + 4 + 4 + 8 + 2 + 1
+    tail = np.frombuffer((":N:0:" + REFORMAT_BARCODE + "\n").encode(), dtype=np.uint8)
+    bad = np.nonzero(rng.random(n_pairs) < 0.1)[0]
+    at = rng.integers(0, len(REFORMAT_BARCODE), size=bad.size)
+
+    def widen(flat):
+        if flat is None:
+            return None
+        rec = flat.reshape(n_pairs, -1)
+        out = np.empty((n_pairs, rec.shape[1] + tail.size - 1), dtype=np.uint8)
+        out[:, :hl - 3] = rec[:, :hl - 3]
+        out[:, hl - 3] = ord(" ")
+        out[:, hl - 2] = rec[:, hl - 2]          # the read number
+        out[:, hl - 1:hl - 1 + tail.size] = tail
+        out[bad, hl - 1 + 5 + at] = ord("N")
+        out[:, hl - 1 + tail.size:] = rec[:, hl:]
+        return out.reshape(-1)
+
+    return widen(r1), widen(r2)
+
+
+def reformat_run_spec(spec: LaneSpec, umi_length: int = 0, **kw) -> RunSpec:
+    return RunSpec(samples=[Sample("S001", REFORMAT_BARCODE, ".")], template="i7" + str(len(REFORMAT_BARCODE)), paired=spec.paired,
+                   mismatches=5, l_position=L_POSITION, illumina_prefix=f"@INS:20240101:{FLOWCELL}:", reformat=True,
+                   reformat_umi_length=umi_length, reformat_barcode=REFORMAT_BARCODE, **kw)
+
+
 def record_bytes(spec: LaneSpec) -> Tuple[int, int]:
     hl = 1 + len(FLOWCELL) + 2 + 4 + 4 + 8 + 2 + 1
     BL = sum(n for _, n in _template_items(spec.template))
