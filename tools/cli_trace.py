@@ -25,6 +25,9 @@ try:
         p = subprocess.run([CLI_BIN] + a, capture_output=True, text=True, env=dict(os.environ, MGK_TRACE="1"))
         print("run", k, "wall %.2f s" % (time.perf_counter() - t), "rc", p.returncode)
         print(p.stderr[-1200:])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"cli_trace_run{k}.txt"), "w") as f:
+            f.write(p.stderr)
         print("\n".join(line[30:] for line in p.stdout.split("\n") if "after" in line or "Exection" in line or "pump waited" in line))
 finally:
     shutil.rmtree(d, ignore_errors=True)
