@@ -230,6 +230,8 @@ def main():
               "l2_policy": f"every chunk streams {(r1_rec + r2_rec) * a.pairs >> 20} MiB in + about as much out per GPU (>> 126 MB L2); "
                            "no explicit flush needed",
               "parallelism": f"{a.gpus} GPU(s), read chunks sharded by rank, one NCCL allreduce of the counter tables"}
+    if a.gpus > 1:   # N = 1 runs config 2 (the headline), N > 1 config 5 (BASELINE's multi-GPU configuration)
+        config["weak_scaling_reference"] = "the N=1 line's other_configs.cfg5 (same lane, one GPU)"
 
     if a.impl == "reference":
         if rank != 0:

@@ -109,6 +109,8 @@ class RfLane:
     barcode: str = "ACGTTGCAAC"   # what the header carries (with errors); "" with style raw
     frac_mm: float = 0.3          # reads whose header barcode differs from it
     flags: list = field(default_factory=list)
+    instrument: str = "INS"
+    run: str = "20240101"
 
 
 BASES = "ACGT"
@@ -164,7 +166,7 @@ def write_rf_lane(l: RfLane, d: str):
 
 def rf_args(l: RfLane, p1, p2, out):
     a = ["reformat", "-f", p1] + (["-r", p2] if p2 else [])
-    return a + ["--lane", "L01", "--run", "20240101", "--instrument", "INS", "-o", out, "--force"] + list(l.flags)
+    return a + ["--lane", "L01", "--run", l.run, "--instrument", l.instrument, "-o", out, "--force"] + list(l.flags)
 
 
 def synthetic_lanes() -> list:
@@ -184,4 +186,9 @@ def synthetic_lanes() -> list:
         RfLane("rf-sb-umi-all", 1500, 71012, r2_len=20, flags=["--umi-length", "20"]),
         RfLane("rf-sb-dual", 2000, 71013, barcode="ACGTTGCAAC+TTGACCAGTA", flags=["--barcode", "ACGTTGCAAC+TTGACCAGTA"]),
         RfLane("rf-raw-long", 1500, 71014, style="raw", barcode="", r1_len=251, r2_len=301, flags=["--barcode", "ACGTACGT"]),
+        # rewritten headers longer than the 80-byte staging slots of k_emit: built at their destination
+        RfLane("rf-sb-long-header", 1500, 71015, barcode="ACGTTGCAAC+TTGACCAGTA", instrument="NOVASEQ-LIKE-INSTRUMENT-0123456789", run="2024010112345678",
+               flags=["--barcode", "ACGTTGCAAC+TTGACCAGTA", "--umi-length", "12"]),
+        RfLane("rf-raw-long-header", 1500, 71016, style="raw", barcode="", instrument="NOVASEQ-LIKE-INSTRUMENT-0123456789", run="2024010112345678",
+               flags=["--barcode", "ACGTTGCAACTTGACCAGTAACGT", "--umi-length", "3"]),
     ]

@@ -43,6 +43,27 @@ def _block(args):
     return _gz_member(r1.tobytes()) if r1 is not None else b"", _gz_member(r2.tobytes())
 
 
+def _rf_block(args):
+    lane, b, n = args
+    from mgikit_b200 import synth
+    r1, r2 = synth.reformat_block(lane, b, n)
+    return _gz_member(r1.tobytes()), _gz_member(r2.tobytes())
+
+
+def write_reformat_lane(lane, n_pairs, out_dir, block_pairs=BLOCK_PAIRS):
+    """One sample's reads with ` n:N:0:BARCODE` headers (synth.reformat_block), one gzip member per block, named the way
+    `reformat` reads sample label and lane from (Flowcell_Lane_Label_n.fq.gz)."""
+    os.makedirs(out_dir, exist_ok=True)
+    p1 = os.path.join(out_dir, "V350012345_L01_S001_1.fq.gz")
+    p2 = os.path.join(out_dir, "V350012345_L01_S001_2.fq.gz")
+    jobs = [(lane, b, min(block_pairs, n_pairs - b * block_pairs)) for b in range(-(-n_pairs // block_pairs))]
+    with mp.get_context("fork").Pool(max(1, min(len(jobs), os.cpu_count() or 2))) as pool, open(p1, "wb") as f1, open(p2, "wb") as f2:
+        for z1, z2 in pool.imap(_rf_block, jobs):
+            f1.write(z1)
+            f2.write(z2)
+    return p1, p2
+
+
 def write_lane_blocks(lane, n_pairs, out_dir, block_pairs=BLOCK_PAIRS, single_member=False):
     """The lane as .fq.gz, one gzip member per block of `block_pairs` (or one member in all, python's gzip
     writer, when single_member), read numbers continuing across blocks; returns (r1, r2, sheet, seconds)."""
@@ -227,6 +248,27 @@ def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figure
                                                "what": "the same lane as ONE gzip member per file (what plain gzip writes): each member is decoded in parts by all the inflate threads of its file"}
             t = _timed(ref_bin, a)
             out["reference_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "threads": cores}
+        if side_figures:   # `reformat`: one sample's reads, Illumina headers + UMI into the header + quality report
+            from mgikit_b200 import synth
+            nrf = min(n_pairs, 2_000_000)
+            shutil.rmtree(ours_dir, ignore_errors=True)   # (the single-member runs above wrote there)
+            shutil.rmtree(ref_dir, ignore_errors=True)
+            f1, f2 = write_reformat_lane(lane, nrf, os.path.join(d, "rf"))
+            a = ["reformat", "-f", f1, "-r", f2, "--lane", "L01", "--run", "20240101", "--instrument", "INS", "--force",
+                 "--umi-length", "8", "--barcode", synth.REFORMAT_BARCODE, "-o"]
+            _timed(product_cli, a + [ours_dir, "-t", str(cores)])
+            t = _timed(product_cli, a + [ours_dir, "-t", str(cores)])
+            t_r = _timed(ref_bin, a + [ref_dir])
+            for gz in (False, True):
+                x, y = _digest_dir(ours_dir, gz), _digest_dir(ref_dir, gz)
+                if x != y or not x:
+                    raise AssertionError(f"reformat: {'FASTQ' if gz else 'report'} files differ from the reference's")
+            out["reformat"] = {"pairs": nrf, "ours": {"pairs_per_s": nrf / t, "seconds": t, "threads": cores},
+                               "reference": {"pairs_per_s": nrf / t_r, "seconds": t_r, "threads": "its own (the command has no thread option)"},
+                               "ratio": t_r / t, "parity": "both FASTQ files (decompressed) and the sample_stats report identical",
+                               "cmd": "mgikit reformat --umi-length 8 --barcode " + synth.REFORMAT_BARCODE}
+            shutil.rmtree(ref_dir, ignore_errors=True)
+            shutil.rmtree(ours_dir, ignore_errors=True)
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
