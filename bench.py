@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-chunk-pairs", type=int, default=1 << 20, help="end to end, a chunk goes through the C ABI in pieces of at most this many pairs")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400000)
     ap.add_argument("--file-pairs", type=int, default=10_000_000, help="read pairs of the .fq.gz lane of the file-level leg (0: skip)")
+    ap.add_argument("--file-timeout", type=int, default=420, help="seconds the file-level leg may take before it is given up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
@@ -176,6 +177,15 @@ def serial_run(hp, dev_args, n_chunks, flags):
         rows.append(hp.last_timings())
         hp.release(k)
     return rows
+
+
+T_START = time.perf_counter()
+
+
+def progress(what):
+    """One line per finished leg on stderr (rank 0 only says where a run is, should it ever stop)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench] {time.perf_counter() - T_START:7.1f} s  {what}", file=sys.stderr, flush=True)
 
 
 def short_lane_line(lane, n, device, peak, reformat=False):
@@ -345,6 +355,7 @@ def main():
     span_max = max_over_ranks(span)
     value = n * a.steps * cps * world / (span_max * 1e-3)
 
+    progress("resident leg done")
     # ---- end to end through the C ABI: pinned host in, pinned host out; and the copies alone over the same buffers
     e2e = None
     if not a.no_e2e:
@@ -398,6 +409,7 @@ def main():
                "gzip_out": {"value": n * cps * gz_steps * world / dt_gz, "unit": UNIT, "d2h_bytes_per_step": int(d2h_gz), "steps": gz_steps,
                             "what": "same call with MGK_OUT_GZIP: per-sample segments come back as gzip members made on the device; 3 pieces in flight"}}
 
+        progress("end-to-end legs done")
         # copy-only leg: the same pinned input buffers and piece sizes, one cudaMemcpyAsync per piece and direction
         # (H2D of the text on one stream, D2H of as many bytes as the path returns on another), no kernels: what the
         # box's host<->device DMA gives this rank while every other rank does the same
@@ -487,6 +499,7 @@ def main():
                               "bin_scan": float(k_ms[:, 2].mean()), "emit_qc": scatter_ms, "chunk": float(k_ms[:, 4].mean())},
                 "whole_path_frac": (algo_bytes * a.steps * cps / (span_max * 1e-3) / 1e9) / peak}
 
+    progress("copy ceiling done")
     other = None
     if a.gpus == 1 and not a.no_other_configs:   # the BASELINE configurations that are not the headline, tracked round over round
         other = {}
@@ -500,15 +513,25 @@ def main():
         except Exception as e:
             other["reformat"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    progress("other configurations done")
     files = None
     if a.gpus == 1 and a.file_pairs > 0:
         try:
             os.sched_setaffinity(0, all_cpus)
-            import file_bench
-            files = file_bench.run(lane, a.file_pairs, CLI_BIN, reference_binary()[0])
+            # in a process of its own and under a clock: the leg forks worker pools (a process that holds CUDA
+            # contexts and a dozen threads is no place to fork from) and runs eight CLI commands; whatever goes wrong
+            # there is reported in this line, the line itself is printed
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "file_bench.py"), str(a.file_pairs)],
+                               stdout=subprocess.PIPE, text=True, timeout=a.file_timeout)   # its progress lines go to stderr
+            if p.returncode != 0:
+                raise RuntimeError(f"tools/file_bench.py failed ({p.returncode}), see stderr")
+            files = json.loads(p.stdout.strip().splitlines()[-1])
+        except subprocess.TimeoutExpired:
+            files = {"error": f"tools/file_bench.py did not finish within {a.file_timeout} s"}
         except Exception as e:
             files = {"error": f"{type(e).__name__}: {e}"[:400]}
 
+    progress("file-level leg done")
     cpu = None
     if not a.no_cpu_baseline and a.gpus == 1:
         try:

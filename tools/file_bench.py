@@ -116,7 +116,8 @@ def _scratch(need_bytes):
     return tempfile.gettempdir(), st.f_bavail * st.f_frsize
 
 
-def _timed(binary, args, timeout=3600, want_log=False):
+def _timed(binary, args, timeout=240, want_log=False):
+    print(f"[file_bench] {os.path.basename(binary)} {args[0]} -> {args[args.index('-o') + 1] if '-o' in args else ''}", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
     p = subprocess.run([binary] + args, capture_output=True, text=True, timeout=timeout)
     dt = time.perf_counter() - t0
@@ -153,7 +154,7 @@ def _digest_dir(d, gz):
     names = sorted(n for n in os.listdir(d) if os.path.isfile(os.path.join(d, n)) and n.endswith(".gz") == gz)
     if gz:
         with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
-            for n, h in zip(names, pool.map(_gz_digest, [os.path.join(d, n) for n in names])):
+            for n, h in zip(names, pool.map_async(_gz_digest, [os.path.join(d, n) for n in names]).get(timeout=300)):
                 out[n] = h
     else:
         for n in names:
@@ -236,42 +237,58 @@ def run(lane, n_pairs, product_cli, ref_bin, prefix_pairs=1_000_000, side_figure
             out["parity"]["fastq_prefix" if gz else "reports_prefix"] = f"{len(a)} files identical on a {pre}-pair prefix vs the reference at -t 1"
         shutil.rmtree(ref_dir, ignore_errors=True)
         shutil.rmtree(ours_dir, ignore_errors=True)
-        if side_figures:   # one member per file (what a plain `gzip` writes): the input decode is one thread per file
-            one = min(n_pairs, 2_000_000)
-            s1, s2, ssheet, _ = write_lane_blocks(lane, one, os.path.join(d, "single"), single_member=True)
-            a = lanes.demux_args(lane, s1, s2, ssheet, ours_dir)
-            a[a.index("-t") + 1] = str(cores)
-            _timed(product_cli, a)
-            t, log = _timed(product_cli, a, want_log=True)
-            ph = _phases(log)
-            out["ours_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "phases": ph,
-                                               "what": "the same lane as ONE gzip member per file (what plain gzip writes): each member is decoded in parts by all the inflate threads of its file"}
-            t = _timed(ref_bin, a)
-            out["reference_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "threads": cores}
-        if side_figures:   # `reformat`: one sample's reads, Illumina headers + UMI into the header + quality report
-            from mgikit_b200 import synth
-            nrf = min(n_pairs, 2_000_000)
-            shutil.rmtree(ours_dir, ignore_errors=True)   # (the single-member runs above wrote there)
-            shutil.rmtree(ref_dir, ignore_errors=True)
-            f1, f2 = write_reformat_lane(lane, nrf, os.path.join(d, "rf"))
-            a = ["reformat", "-f", f1, "-r", f2, "--lane", "L01", "--run", "20240101", "--instrument", "INS", "--force",
-                 "--umi-length", "8", "--barcode", synth.REFORMAT_BARCODE, "-o"]
-            _timed(product_cli, a + [ours_dir, "-t", str(cores)])
-            t = _timed(product_cli, a + [ours_dir, "-t", str(cores)])
-            t_r = _timed(ref_bin, a + [ref_dir])
-            for gz in (False, True):
-                x, y = _digest_dir(ours_dir, gz), _digest_dir(ref_dir, gz)
-                if x != y or not x:
-                    raise AssertionError(f"reformat: {'FASTQ' if gz else 'report'} files differ from the reference's")
-            out["reformat"] = {"pairs": nrf, "ours": {"pairs_per_s": nrf / t, "seconds": t, "threads": cores},
-                               "reference": {"pairs_per_s": nrf / t_r, "seconds": t_r, "threads": "its own (the command has no thread option)"},
-                               "ratio": t_r / t, "parity": "both FASTQ files (decompressed) and the sample_stats report identical",
-                               "cmd": "mgikit reformat --umi-length 8 --barcode " + synth.REFORMAT_BARCODE}
-            shutil.rmtree(ref_dir, ignore_errors=True)
-            shutil.rmtree(ours_dir, ignore_errors=True)
+        if side_figures:
+            try:
+                _single_member_figures(out, lane, n_pairs, d, ours_dir, product_cli, ref_bin, cores)
+            except Exception as e:
+                out["ours_single_member_input"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                _reformat_figures(out, lane, n_pairs, d, ours_dir, ref_dir, product_cli, ref_bin, cores)
+            except Exception as e:
+                out["reformat"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def _single_member_figures(out, lane, n_pairs, d, ours_dir, product_cli, ref_bin, cores):
+    """One member per file (what a plain `gzip` writes): each member is decoded in parts by the file's inflate threads."""
+    import lanes
+    one = min(n_pairs, 2_000_000)
+    s1, s2, ssheet, _ = write_lane_blocks(lane, one, os.path.join(d, "single"), single_member=True)
+    a = lanes.demux_args(lane, s1, s2, ssheet, ours_dir)
+    a[a.index("-t") + 1] = str(cores)
+    _timed(product_cli, a)
+    t, log = _timed(product_cli, a, want_log=True)
+    out["ours_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "phases": _phases(log),
+                                       "what": "the same lane as ONE gzip member per file (what plain gzip writes): each member is decoded in parts by all the inflate threads of its file"}
+    t = _timed(ref_bin, a)
+    out["reference_single_member_input"] = {"pairs_per_s": one / t, "seconds": t, "pairs": one, "threads": cores}
+    shutil.rmtree(ours_dir, ignore_errors=True)   # (both runs wrote there)
+
+
+def _reformat_figures(out, lane, n_pairs, d, ours_dir, ref_dir, product_cli, ref_bin, cores):
+    """`reformat`: one sample's reads, Illumina headers + UMI into the header + quality report, both binaries."""
+    from mgikit_b200 import synth
+    nrf = min(n_pairs, 2_000_000)
+    shutil.rmtree(ours_dir, ignore_errors=True)
+    shutil.rmtree(ref_dir, ignore_errors=True)
+    f1, f2 = write_reformat_lane(lane, nrf, os.path.join(d, "rf"))
+    a = ["reformat", "-f", f1, "-r", f2, "--lane", "L01", "--run", "20240101", "--instrument", "INS", "--force",
+         "--umi-length", "8", "--barcode", synth.REFORMAT_BARCODE, "-o"]
+    _timed(product_cli, a + [ours_dir, "-t", str(cores)])
+    t = _timed(product_cli, a + [ours_dir, "-t", str(cores)])
+    t_r = _timed(ref_bin, a + [ref_dir])
+    for gz in (False, True):
+        x, y = _digest_dir(ours_dir, gz), _digest_dir(ref_dir, gz)
+        if x != y or not x:
+            raise AssertionError(f"reformat: {'FASTQ' if gz else 'report'} files differ from the reference's")
+    out["reformat"] = {"pairs": nrf, "ours": {"pairs_per_s": nrf / t, "seconds": t, "threads": cores},
+                       "reference": {"pairs_per_s": nrf / t_r, "seconds": t_r, "threads": "its own (the command has no thread option)"},
+                       "ratio": t_r / t, "parity": "both FASTQ files (decompressed) and the sample_stats report identical",
+                       "cmd": "mgikit reformat --umi-length 8 --barcode " + synth.REFORMAT_BARCODE}
+    shutil.rmtree(ref_dir, ignore_errors=True)
+    shutil.rmtree(ours_dir, ignore_errors=True)
 
 
 if __name__ == "__main__":
