@@ -53,9 +53,14 @@ def digest_dir(d: str) -> dict:
         p = os.path.join(d, name)
         if not os.path.isfile(p):
             continue
-        with open(p, "rb") as f:
-            raw = f.read()
-        if name.endswith(".gz"):
-            raw = gzip.decompress(raw) if raw else b""
-        out[name] = hashlib.sha256(raw).hexdigest()
+        h = hashlib.sha256()
+        if name.endswith(".gz"):   # streamed: gzip.decompress() is quadratic in the number of members
+            if os.path.getsize(p):
+                with gzip.open(p, "rb") as f:
+                    for piece in iter(lambda: f.read(1 << 22), b""):
+                        h.update(piece)
+        else:
+            with open(p, "rb") as f:
+                h.update(f.read())
+        out[name] = h.hexdigest()
     return out

@@ -144,9 +144,14 @@ def _phases(log):
 
 
 def _gz_digest(path):
-    with open(path, "rb") as f:
-        raw = f.read()
-    return hashlib.sha256(gzip.decompress(raw) if raw else b"").hexdigest()   # all members, like MultiGzDecoder
+    """sha256 of the decompressed text, all members like MultiGzDecoder -- streamed: gzip.decompress() copies the rest of
+    the file once per member, hours for the 23 000 members of a one-sample output."""
+    h = hashlib.sha256()
+    if os.path.getsize(path):
+        with gzip.open(path, "rb") as f:
+            for piece in iter(lambda: f.read(1 << 22), b""):
+                h.update(piece)
+    return h.hexdigest()
 
 
 def _digest_dir(d, gz):
