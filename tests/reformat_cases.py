@@ -111,6 +111,7 @@ class RfLane:
     flags: list = field(default_factory=list)
     instrument: str = "INS"
     run: str = "20240101"
+    cpu_only: bool = False        # added after the last GPU session of the round: oracle and device logic on the CPU only
 
 
 BASES = "ACGT"
@@ -134,10 +135,22 @@ def lane_text(l: RfLane):
                 bc[p] = rng.choice(BASES + "N")
         bc = "".join(bc)
 
+        odd = i % 7 if (l.style == "odd" and i) else 0
+
         def rec(which, length):
             seq = "".join(rng.choice(BASES) if rng.random() > 0.01 else "N" for _ in range(length))
             qual = "".join(chr(33 + rng.choice([2, 11, 25, 30, 30, 37, 40])) for _ in range(length))
-            tail = f" {which}:N:0:{bc}" if l.style == "sb" else f"/{which}"
+            tail = f" {which}:N:0:{bc}" if l.style in ("sb", "odd") else f"/{which}"
+            if odd == 1:      # the blank three bytes before the end: "sep_position == len - 3" without being raw
+                tail = f" {which}"
+            elif odd == 2:    # no blank at all in an otherwise blank-separated file
+                tail = f"/{which}"
+            elif odd == 3:    # more fields behind the barcode
+                tail = f" {which}:N:0:{bc} extra:field {i}"
+            elif odd == 4:    # a long tail (taken over byte by byte: the header outgrows the staging slot)
+                tail = f" {which}:N:0:{bc}:" + "x" * 150
+            elif odd == 5:    # two blanks: the first one counts
+                tail = f" {which}:Y:18:{bc} {which}:N:0:{bc}"
             return f"{head}{tail}\n{seq}\n+\n{qual}\n"
 
         if l.paired:
@@ -189,6 +202,10 @@ def synthetic_lanes() -> list:
         # rewritten headers longer than the 80-byte staging slots of k_emit: built at their destination
         RfLane("rf-sb-long-header", 1500, 71015, barcode="ACGTTGCAAC+TTGACCAGTA", instrument="NOVASEQ-LIKE-INSTRUMENT-0123456789", run="2024010112345678",
                flags=["--barcode", "ACGTTGCAAC+TTGACCAGTA", "--umi-length", "12"]),
+        # headers nobody writes on purpose, one oddity per read (no --barcode: the reference panics on a header barcode of
+        # another length); with --barcode only the oddities that keep the barcode's place
+        RfLane("rf-odd-headers", 1400, 71017, style="odd", flags=["--umi-length", "5"], cpu_only=True),
+        RfLane("rf-odd-headers-se", 1400, 71018, style="odd", paired=False, r2_len=44, flags=[], cpu_only=True),
         RfLane("rf-raw-long-header", 1500, 71016, style="raw", barcode="", instrument="NOVASEQ-LIKE-INSTRUMENT-0123456789", run="2024010112345678",
                flags=["--barcode", "ACGTTGCAACTTGACCAGTAACGT", "--umi-length", "3"]),
     ]

@@ -26,6 +26,7 @@ with open(os.path.join(HERE, "golden", "reformat_reference.json")) as f:
     GOLD = json.load(f)
 FIXTURES = RF.fixture_cases()
 LANES = RF.synthetic_lanes()
+GPU_LANES = [l for l in LANES if not l.cpu_only]
 REF_BIN = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "mgikit")
 
 
@@ -94,7 +95,7 @@ def test_cuda_cli_reproduces_reference_fixture(product_cli, case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("l", LANES, ids=[l.name for l in LANES])
+@pytest.mark.parametrize("l", GPU_LANES, ids=[l.name for l in GPU_LANES])
 def test_cuda_cli_equals_reference_binary(product_cli, l):
     _lane(product_cli, l)
 
