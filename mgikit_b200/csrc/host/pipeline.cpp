@@ -717,7 +717,14 @@ void run_demultiplex(const Backend& be, const SampleSheet& sheet, RunInfo& run, 
           input_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - ti).count();
           if (!b2.error.empty()) throw Fatal(b2.error);
           if (paired && !b1.error.empty()) throw Fatal(b1.error);
-          if (paired && b2.n_records != b1.n_records) throw Fatal("Something wrong in the input files!");  // src/lib.rs:1490-1494
+          if (paired && b2.n_records != b1.n_records) {   // src/lib.rs:1490-1494
+            // a chunk is cut after `rpb` records, sized from the FIRST record of either file with 5 % of slack; one file
+            // falling short means its records grew beyond that (or the files are not in step at all)
+            const bool full = !b2.last && !b1.last && (b2.n_records < rpb || b1.n_records < rpb);
+            throw Fatal(full ? "Something wrong in the input files! (" + std::to_string(rpb) + " records of one file do not fit a chunk of " +
+                                   std::to_string(chunk_bytes) + " bytes: the records are longer than the first one of the file; raise --chunk-size)"
+                             : std::string("Something wrong in the input files!"));
+          }
           if (b2.n_records > 0) {
             const auto ts = std::chrono::steady_clock::now();
             if (be.submit(ctxs[(size_t)g], seq, b2.data, b2.len, paired ? b1.data : nullptr, paired ? b1.len : 0, submit_flags) != MGK_OK)

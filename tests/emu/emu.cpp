@@ -7,6 +7,8 @@
 // look-back, in-tile ranking) are NOT covered here — those only run on the GPU.
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -15,15 +17,18 @@
 
 using namespace mgk;
 
-struct emu_ctx {
-  Params P;
-  HostTables tb;
-  std::vector<uint64_t> stats, mism;
+struct emu_chunk {   // what one submitted chunk leaves behind until it is released
   std::vector<uint8_t> out2, out1;
   std::vector<uint64_t> off2, len2, off1, len1;
   std::vector<uint32_t> unassigned;
   mgk_result res;
-  bool have = false;
+};
+
+struct emu_ctx {
+  Params P;
+  HostTables tb;
+  std::vector<uint64_t> stats, mism;
+  std::deque<std::unique_ptr<emu_chunk>> submitted, collected;   // FIFO like the device contexts: any number in flight
   std::string err;
 };
 
@@ -62,6 +67,8 @@ static std::vector<uint32_t> newlines(const uint8_t* b, size_t n) {
 
 int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, const uint8_t* r1_in, uint64_t r1_len, uint32_t) {
   const Params& P = c->P;
+  std::unique_ptr<emu_chunk> chunk(new emu_chunk());
+  emu_chunk& K = *chunk;
   // 16-byte aligned, padded private copies like the device buffers
   uint8_t* r2 = (uint8_t*)aligned_alloc(64, ((size_t)r2_len + 128 + 63) / 64 * 64);
   uint8_t* r1 = (uint8_t*)aligned_alloc(64, ((size_t)r1_len + 128 + 63) / 64 * 64);
@@ -83,7 +90,7 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   };
   std::vector<Rec> recs(n_rec);
   std::vector<uint64_t> bin2((size_t)total, 0), bin1((size_t)total, 0);
-  c->unassigned.clear();
+  K.unassigned.clear();
   int rc = MGK_OK;
   for (uint32_t i = 0; i < n_rec; ++i) {
     Rec& R = recs[i];
@@ -118,18 +125,18 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     bin1[(size_t)R.bin] += R.pl.len1;
     c->mism[(size_t)R.mo.sample * P.mism_w + R.mo.mism + 1] += 1;
     if (!R.pl.matched && P.report_level > 1)
-      c->unassigned.push_back((G.p2 - 1 - (uint32_t)P.BL) | (R.mo.sample == total - 1 ? 0x80000000u : 0u));
+      K.unassigned.push_back((G.p2 - 1 - (uint32_t)P.BL) | (R.mo.sample == total - 1 ? 0x80000000u : 0u));
   }
   if (rc != MGK_OK) { free(r2); free(r1); return rc; }
-  c->off2.assign((size_t)total, 0); c->len2 = bin2; c->off1.assign((size_t)total, 0); c->len1 = bin1;
+  K.off2.assign((size_t)total, 0); K.len2 = bin2; K.off1.assign((size_t)total, 0); K.len1 = bin1;
   uint64_t t2 = 0, t1 = 0;
-  for (int b = 0; b < total; ++b) { c->off2[(size_t)b] = t2; t2 += bin2[(size_t)b]; c->off1[(size_t)b] = t1; t1 += bin1[(size_t)b]; }
+  for (int b = 0; b < total; ++b) { K.off2[(size_t)b] = t2; t2 += bin2[(size_t)b]; K.off1[(size_t)b] = t1; t1 += bin1[(size_t)b]; }
   // 16-byte aligned outputs (vector::data of a fresh allocation is) with slack
-  c->out2.assign((size_t)t2 + 64, 0xEE);
-  c->out1.assign((size_t)t1 + 64, 0xEE);
-  uint8_t* o2 = c->out2.data();
-  uint8_t* o1 = c->out1.data();
-  memset(&c->res, 0, sizeof c->res);
+  K.out2.assign((size_t)t2 + 64, 0xEE);
+  K.out1.assign((size_t)t1 + 64, 0xEE);
+  uint8_t* o2 = K.out2.data();
+  uint8_t* o1 = K.out1.data();
+  memset(&K.res, 0, sizeof K.res);
   // the staged tile: the whole chunk as ONE tile, laid out like the kernel's shared memory
   //   [slack | prefix + literals | two header staging slots | barcode read bytes | paired read bytes | slack]
   const uint32_t cs0 = 64;
@@ -148,7 +155,7 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
     RecGeom G = R.G;   // into S offsets
     G.h2 += b2; G.s2 += b2; G.p2 += b2; G.q2 += b2; G.e2 += b2;
     G.h1 += b1; G.s1 += b1; G.p1 += b1; G.q1 += b1; G.e1 += b1;
-    uint8_t* dst[3] = {nullptr, o1 + c->off1[(size_t)R.bin] + R.d1, o2 + c->off2[(size_t)R.bin] + R.d2};
+    uint8_t* dst[3] = {nullptr, o1 + K.off1[(size_t)R.bin] + R.d1, o2 + K.off2[(size_t)R.bin] + R.d2};
     // what k_emit does for one pair: header halves by scalar roles, byte ranges by copy_piece (lanes looped; the kernel's PTX movers do the same bytes)
     ReadPlan plan[3];
     const uint32_t rf = rf_pack(R.pl.rf_tcl, R.pl.rf_raw);   // what the kernel carries in RecMeta
@@ -206,29 +213,38 @@ int emu_submit(emu_ctx* c, uint64_t seq, const uint8_t* r2_in, uint64_t r2_len, 
   if (rc != MGK_OK) { free(r2); free(r1); return rc; }
   free(r2);
   free(r1);
-  c->res.seq = seq;
-  c->res.n_records = n_rec;
-  c->res.consumed_r2 = n_rec ? nl2[4 * n_rec - 1] + 1 : 0;
-  c->res.consumed_r1 = (P.paired && n_rec) ? nl1[4 * n_rec - 1] + 1 : 0;
-  c->res.out_r2 = o2;
-  c->res.out_r1 = P.paired ? o1 : nullptr;
-  c->res.out_r2_bytes = t2;
-  c->res.out_r1_bytes = t1;
-  c->res.seg_off_r2 = c->off2.data(); c->res.seg_len_r2 = c->len2.data();
-  c->res.seg_off_r1 = c->off1.data(); c->res.seg_len_r1 = c->len1.data();
-  c->res.unassigned = c->unassigned.data();
-  c->res.n_unassigned = c->unassigned.size();
-  if (vkey != ~0ull) { c->res.validate_error = validate_kind((int)(vkey & 15)); c->res.validate_record = vkey >> 4; }
-  c->have = true;
+  K.res.seq = seq;
+  K.res.n_records = n_rec;
+  K.res.consumed_r2 = n_rec ? nl2[4 * n_rec - 1] + 1 : 0;
+  K.res.consumed_r1 = (P.paired && n_rec) ? nl1[4 * n_rec - 1] + 1 : 0;
+  K.res.out_r2 = o2;
+  K.res.out_r1 = P.paired ? o1 : nullptr;
+  K.res.out_r2_bytes = t2;
+  K.res.out_r1_bytes = t1;
+  K.res.seg_off_r2 = K.off2.data(); K.res.seg_len_r2 = K.len2.data();
+  K.res.seg_off_r1 = K.off1.data(); K.res.seg_len_r1 = K.len1.data();
+  K.res.unassigned = K.unassigned.data();
+  K.res.n_unassigned = K.unassigned.size();
+  if (vkey != ~0ull) { K.res.validate_error = validate_kind((int)(vkey & 15)); K.res.validate_record = vkey >> 4; }
+  c->submitted.push_back(std::move(chunk));
   return MGK_OK;
 }
 
 int emu_collect(emu_ctx* c, mgk_result* r) {
-  if (!c->have) return MGK_ERR_STATE;
-  *r = c->res;
+  if (c->submitted.empty()) return MGK_ERR_STATE;
+  c->collected.push_back(std::move(c->submitted.front()));
+  c->submitted.pop_front();
+  *r = c->collected.back()->res;
   return MGK_OK;
 }
-int emu_release(emu_ctx* c, uint64_t) { c->have = false; return MGK_OK; }
+int emu_release(emu_ctx* c, uint64_t seq) {
+  for (auto it = c->collected.begin(); it != c->collected.end(); ++it)
+    if ((*it)->res.seq == seq) {
+      c->collected.erase(it);
+      return MGK_OK;
+    }
+  return MGK_ERR_STATE;
+}
 int emu_counters(emu_ctx* c, uint64_t* stats, uint64_t* mism) {
   if (stats) memcpy(stats, c->stats.data(), c->stats.size() * 8);
   if (mism) memcpy(mism, c->mism.data(), c->mism.size() * 8);

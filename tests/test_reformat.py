@@ -88,6 +88,11 @@ def test_device_logic_on_cpu_equals_reference_binary(emu_cli, l):
     _lane(emu_cli, l)
 
 
+def test_device_logic_on_cpu_many_chunks(emu_cli):
+    _lane(emu_cli, LANES[2], extra=("--chunk-size", "131072"))
+    _lane(emu_cli, LANES[5], extra=("--chunk-size", "131072"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", FIXTURES, ids=[c.name for c in FIXTURES])
 def test_cuda_cli_reproduces_reference_fixture(product_cli, case):

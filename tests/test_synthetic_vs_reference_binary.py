@@ -45,6 +45,13 @@ def test_oracle_cli_equals_reference_binary(oracle_cli, name, lane, extra, n):
     _check(oracle_cli, name, lane, extra, n)
 
 
+def test_device_logic_on_cpu_multi_chunk_equals_reference_binary(emu_cli):
+    """The per-record device logic through the host pump with many chunks in flight (chunk cuts, per-sample order)."""
+    for k in (0, 1, 3):
+        name, lane, extra, n = VARIANTS[k]
+        _check(emu_cli, name, lane, extra, n, extra_cli=("--chunk-size", "524288"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,lane,extra,n", VARIANTS, ids=[v[0] for v in VARIANTS])
 def test_cuda_cli_equals_reference_binary(product_cli, name, lane, extra, n):
