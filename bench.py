@@ -241,7 +241,7 @@ def main():
                            "no explicit flush needed",
               "parallelism": f"{a.gpus} GPU(s), read chunks sharded by rank, one NCCL allreduce of the counter tables"}
     if a.gpus > 1:   # N = 1 runs config 2 (the headline), N > 1 config 5 (BASELINE's multi-GPU configuration)
-        config["weak_scaling_reference"] = "the N=1 line's other_configs.cfg5 (same lane, one GPU)"
+        config["weak_scaling_reference"] = "single_gpu_same_lane of this line (rank 0 alone, same box), or the N=1 line's other_configs.cfg5"
 
     if a.impl == "reference":
         if rank != 0:
@@ -500,6 +500,12 @@ def main():
                 "whole_path_frac": (algo_bytes * a.steps * cps / (span_max * 1e-3) / 1e9) / peak}
 
     progress("copy ceiling done")
+    solo = None
+    if a.gpus > 1:   # the other ranks wait in teardown()'s barrier: this GPU alone on the lane every rank just ran
+        try:
+            solo = short_lane_line(lane, 1 << 20, local, peak)
+        except Exception as e:
+            solo = {"error": f"{type(e).__name__}: {e}"[:300]}
     other = None
     if a.gpus == 1 and not a.no_other_configs:   # the BASELINE configurations that are not the headline, tracked round over round
         other = {}
@@ -547,6 +553,8 @@ def main():
     if allreduce_ms is not None:
         line["allreduce"] = {"ms": allreduce_ms, "bytes": int(hp.total * (10 + hp.mism_w) * 8),
                              "checked": "reduced tables == element-wise sum of the per-rank tables, on every rank"}
+    if solo is not None:
+        line["single_gpu_same_lane"] = solo
     if other is not None:
         line["other_configs"] = other
     if files is not None:
