@@ -129,3 +129,83 @@ def test_random_mixed_library_device_logic_matches_oracle(oracle_lib, emu_lib, s
     spec, chunks = _mixed_case(5000 + seed)
     run_both(oracle_lib, "orc_", emu_lib, "emu_", spec, chunks,
              what=f"mixed fuzz seed {seed}: m={spec.mismatches} comp={spec.comprehensive_scan} mode={spec.out_mode}")
+
+
+def _reformat_case(seed):
+    """`reformat` mode: headers of every shape (blank-separated tails, raw "/n", blanks in odd places, several blanks,
+    long tails), UMI lengths from none to the whole read, with and without a sample barcode, both output modes."""
+    rng = np.random.default_rng(seed)
+    paired = bool(rng.random() < 0.8)
+    l_pos = int(rng.integers(3, 12))
+    bcl = int(rng.integers(0, 3)) * int(rng.integers(4, 13))          # 0 (none) in a third of the cases
+    barcode = _rand_seq(rng, bcl) + ("+" + _rand_seq(rng, bcl) if bcl and rng.random() < 0.3 else "")
+    umi = int(rng.integers(0, 3)) * int(rng.integers(1, 12))
+    spec = RunSpec(samples=[Sample("only", "ACGTACGT", ".")], template="i78", paired=paired,
+                   out_mode=0 if rng.random() < 0.85 else 1, report_level=int(rng.integers(0, 3)), mismatches=5, l_position=l_pos,
+                   validate=bool(rng.random() < 0.15), illumina_prefix="@" + _rand_seq(rng, int(rng.integers(1, 60)), "ABCxyz019") + ":",
+                   max_chunk_bytes=1 << 20, max_chunk_records=4096, reformat=True, reformat_umi_length=umi, reformat_barcode=barcode)
+    flow = _rand_seq(rng, l_pos - 1, "ABCDEFGHV0123456789")
+    strict = bool(rng.random() < 0.7)   # only headers both implementations must accept
+    recs2, recs1 = [], []
+    for i in range(int(rng.integers(1, 300))):
+        num = str(int(rng.integers(0, 10 ** int(rng.integers(1, 12))))).zfill(int(rng.integers(1, 14)))
+        h = f"@{flow}L{int(rng.integers(1, 5))}C{int(rng.integers(0, 1000)):03d}R{int(rng.integers(0, 1000)):03d}{num}"
+        hb = list(barcode)
+        if hb and rng.random() < 0.4:
+            for _ in range(int(rng.integers(1, 7))):
+                hb[int(rng.integers(0, len(hb)))] = "ACGTN+"[int(rng.integers(0, 6))]
+        hb = "".join(hb) if barcode else _rand_seq(rng, int(rng.integers(0, 20)))
+        shape = int(rng.integers(0, 8)) if not strict else int(rng.integers(0, 3))
+        def tail(n):
+            if shape in (0, 1):
+                return f" {n}:N:0:{hb}"
+            if shape == 2:
+                return f"/{n}"
+            if shape == 3:
+                return f" {n}"                                      # blank three bytes before the end
+            if shape == 4:
+                return f" {n}:N:0:{hb} " + _rand_seq(rng, int(rng.integers(0, 230)), "xyz: ")   # may break the barcode length
+            if shape == 5:
+                return f"{n} "                                      # blank in the last two bytes
+            if shape == 6:
+                return f" {n}:N:0:" + _rand_seq(rng, int(rng.integers(0, 30)))                  # barcode of another length
+            return ""                                               # no read number at all
+        t2, t1 = tail(2), tail(1)
+        if shape == 4:
+            t1 = t2.replace(" 2:", " 1:", 1)
+        n2 = int(rng.integers(umi, umi + 200))
+        s2 = _rand_seq(rng, n2, "ACGTN")
+        q2 = "".join(chr(int(v)) for v in rng.integers(33, 74, size=n2))
+        recs2.append(f"{h}{t2}\n{s2}\n+\n{q2}\n".encode())
+        n1 = int(rng.integers(1, 300))
+        recs1.append(f"{h}{t1}\n{_rand_seq(rng, n1)}\n+\n{''.join(chr(int(v)) for v in rng.integers(33, 74, size=n1))}\n".encode())
+    r2 = np.frombuffer(b"".join(recs2), np.uint8)
+    r1 = np.frombuffer(b"".join(recs1), np.uint8) if paired else None
+    return spec, [(r2, r1)]
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_reformat_case_device_logic_matches_oracle(oracle_lib, emu_lib, seed):
+    """Both accept and agree byte for byte, or both refuse the chunk (headers the reference itself would panic on)."""
+    from mgikit_b200.capi import MgkError
+    from util import assert_same_counters, assert_same_result, make_hotpath
+    spec, chunks = _reformat_case(5000 + seed)
+    ha, hb = make_hotpath(oracle_lib, "orc_", spec), make_hotpath(emu_lib, "emu_", spec)
+    try:
+        r2, r1 = chunks[0]
+        res, err = [], []
+        for hp in (ha, hb):
+            try:
+                res.append(hp.process(r2, r1, seq=0))
+                err.append(None)
+            except MgkError as e:
+                res.append(None)
+                err.append(e.code)
+        assert (err[0] is None) == (err[1] is None), f"seed {seed}: oracle {err[0]} vs device logic {err[1]}"
+        if err[0] is None:
+            assert_same_result(res[0], res[1], f"reformat fuzz seed {seed}")
+            if not res[0].validate_error:
+                assert_same_counters(ha, hb, f"reformat fuzz seed {seed}")
+    finally:
+        ha.close()
+        hb.close()
