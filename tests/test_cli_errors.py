@@ -50,3 +50,40 @@ def test_reads_of_different_length_are_an_error(oracle_cli, lane_dir):
     open(short, "wb").write(gzip.compress(text[:len(text) // 2 // 336 * 336], 1))
     rc, err = _run(oracle_cli, lane_dir, short, r2, ["--chunk-size", "1048576"])
     assert rc == 101 and "Something wrong in the input files" in err      # src/lib.rs:1490-1494
+
+
+def test_reformat_refusals(oracle_cli):
+    """`reformat`'s own argument checks (src/lib.rs:2352-2361, src/formater.rs:23-25) and what the pump says when the
+    records of a file outgrow the chunk they were sized for."""
+    import reformat_cases as RF
+    d = tempfile.mkdtemp(prefix="mgk_rferr_")
+    try:
+        l = RF.RfLane("e", 300, 9)
+        p1, p2 = RF.write_rf_lane(l, d)
+
+        def run(args):
+            p = subprocess.run([oracle_cli] + args, capture_output=True, text=True, timeout=120)
+            return p.returncode, p.stderr
+        base = RF.rf_args(l, p1, p2, os.path.join(d, "out"))
+        assert run(base)[0] == 0
+        rc, err = run(base + ["--sample-index", "0"])
+        assert rc == 101 and "needs to be greater than 0" in err
+        # a file name without a third '_' part and no --sample-label
+        q1, q2 = os.path.join(d, "a_1.fq.gz"), os.path.join(d, "a_2.fq.gz")
+        shutil.copy(p1, q1)
+        shutil.copy(p2, q2)
+        rc, err = run(RF.rf_args(l, q1, q2, os.path.join(d, "out2")))
+        assert rc == 101 and "Sample label needs to be passed" in err
+        assert run(RF.rf_args(l, q1, q2, os.path.join(d, "out2")) + ["--sample-label", "x"])[0] == 0
+        assert os.path.exists(os.path.join(d, "out2", "x_S1_L01_R1_001.fastq.gz"))
+        rc, err = run(base + ["--compression-buffer-size", "999999999"])
+        assert rc == 101 and "Compression buffer size" in err
+        rc, err = run(base + ["--umi-length", "500"])
+        assert rc == 101 and "UMI is longer" in err
+        # records that grow beyond the first one's size by more than the chunk's slack
+        odd = [x for x in RF.synthetic_lanes() if x.name == "rf-odd-headers"][0]
+        o1, o2 = RF.write_rf_lane(odd, os.path.join(d, "odd"))
+        rc, err = run(RF.rf_args(odd, o1, o2, os.path.join(d, "out3")) + ["--chunk-size", "65536"])
+        assert rc == 101 and "raise --chunk-size" in err
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
