@@ -18,6 +18,7 @@ import argparse
 import json
 import os
 import shutil
+import signal
 import statistics
 import subprocess
 import sys
@@ -527,11 +528,17 @@ def main():
             # in a process of its own and under a clock: the leg forks worker pools (a process that holds CUDA
             # contexts and a dozen threads is no place to fork from) and runs eight CLI commands; whatever goes wrong
             # there is reported in this line, the line itself is printed
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "file_bench.py"), str(a.file_pairs)],
-                               stdout=subprocess.PIPE, text=True, timeout=a.file_timeout)   # its progress lines go to stderr
+            p = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "file_bench.py"), str(a.file_pairs)],
+                                 stdout=subprocess.PIPE, text=True, start_new_session=True)   # its progress lines go to stderr
+            try:
+                out, _ = p.communicate(timeout=a.file_timeout)
+            except subprocess.TimeoutExpired:
+                os.killpg(p.pid, signal.SIGKILL)   # the leg, its worker pools and whatever command it was running
+                p.communicate()
+                raise
             if p.returncode != 0:
                 raise RuntimeError(f"tools/file_bench.py failed ({p.returncode}), see stderr")
-            files = json.loads(p.stdout.strip().splitlines()[-1])
+            files = json.loads(out.strip().splitlines()[-1])
         except subprocess.TimeoutExpired:
             files = {"error": f"tools/file_bench.py did not finish within {a.file_timeout} s"}
         except Exception as e:
